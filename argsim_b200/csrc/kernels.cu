@@ -1,0 +1,419 @@
+// kernels.cu -- HBM-bound kernels of the VAE step: embedding gather / scatter-add, latent
+// (reparameterisation + KL), fused softmax cross-entropy with gradient, Adam, reductions.
+// All are coalesced, 16-byte vectorised where alignment allows, warp-shuffle reductions.
+#include "kernels.h"
+
+long long g_launch_count = 0;
+
+// ------------------------------------------------------------------------------------------
+// embedding gather: one warp per row, 16-byte copies (model.py:111-112)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_embed_gather(const int* __restrict__ ids, long long n,
+                                                      const T* __restrict__ table, int D, T* __restrict__ out) {
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const T* src = table + (long long)ids[row] * D;
+    T* dst = out + row * D;
+    constexpr int VEC = 16 / sizeof(T);
+    if (D % VEC == 0) {
+        const int4* s4 = reinterpret_cast<const int4*>(src);
+        int4* d4 = reinterpret_cast<int4*>(dst);
+        int nv = D / VEC;
+        for (int i = lane; i < nv; i += 32) d4[i] = __ldg(s4 + i);
+    } else {
+        for (int i = lane; i < D; i += 32) dst[i] = src[i];
+    }
+}
+void launch_embed_gather_f32(const int* ids, long long n, const float* table, int D, float* out, cudaStream_t s) {
+    if (n <= 0) return;
+    k_embed_gather<float><<<cdiv(n, 8), 256, 0, s>>>(ids, n, table, D, out);
+    COUNT_LAUNCH();
+}
+void launch_embed_gather_bf16(const int* ids, long long n, const bf16* table, int D, bf16* out, cudaStream_t s) {
+    if (n <= 0) return;
+    k_embed_gather<bf16><<<cdiv(n, 8), 256, 0, s>>>(ids, n, table, D, out);
+    COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------
+// embedding gradient scatter-add (IndexedSlices part of dE): one warp per row, vector atomics
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_embed_scatter_add(const int* __restrict__ ids, long long n,
+                                                           const float* __restrict__ dx, int ld, int D,
+                                                           float* __restrict__ g) {
+    long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float* src = dx + row * ld;
+    float* dst = g + (long long)ids[row] * D;
+    if ((D & 3) == 0 && (ld & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = lane; i < D / 4; i += 32) atomicAdd(d4 + i, s4[i]);
+    } else {
+        for (int i = lane; i < D; i += 32) atomicAdd(dst + i, src[i]);
+    }
+}
+void launch_embed_scatter_add(const int* ids, long long n, const float* dx, int ld, int D, float* g, cudaStream_t s) {
+    if (n <= 0) return;
+    k_embed_scatter_add<<<cdiv(n, 8), 256, 0, s>>>(ids, n, dx, ld, D, g);
+    COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------
+// row gather / scatter (final-state gather model.py:135, decoder state fan-out model.py:159)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_row_gather(const float* __restrict__ in, int ld_in, const int* __restrict__ src_idx,
+                                                    float* __restrict__ out_f, bf16* __restrict__ out_h, int ld_out,
+                                                    const int* __restrict__ dst_idx, int n, int cols) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    long long si = src_idx ? src_idx[row] : row, di = dst_idx ? dst_idx[row] : row;
+    const float* src = in + si * ld_in;
+    for (int i = lane; i < cols; i += 32) {
+        float v = src[i];
+        if (out_f) out_f[di * ld_out + i] = v;
+        if (out_h) out_h[di * ld_out + i] = __float2bfloat16(v);
+    }
+}
+void launch_row_gather(const float* in, int ld_in, const int* src_idx, float* out_f, bf16* out_h, int ld_out,
+                       const int* dst_idx, int n, int cols, cudaStream_t s) {
+    if (n <= 0) return;
+    k_row_gather<<<cdiv(n, 8), 256, 0, s>>>(in, ld_in, src_idx, out_f, out_h, ld_out, dst_idx, n, cols);
+    COUNT_LAUNCH();
+}
+__global__ void __launch_bounds__(256) k_row_scatter(const float* __restrict__ in, int ld_in, float* __restrict__ out,
+                                                     int ld_out, const int* __restrict__ dst_idx, int n, int cols, int acc) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    long long di = dst_idx ? dst_idx[row] : row;
+    for (int i = lane; i < cols; i += 32) {
+        float v = in[(long long)row * ld_in + i];
+        if (acc) out[di * ld_out + i] += v; else out[di * ld_out + i] = v;   // dst rows are unique
+    }
+}
+void launch_row_scatter(const float* in, int ld_in, float* out, int ld_out, const int* dst_idx, int n, int cols,
+                        int accumulate, cudaStream_t s) {
+    if (n <= 0) return;
+    k_row_scatter<<<cdiv(n, 8), 256, 0, s>>>(in, ld_in, out, ld_out, dst_idx, n, cols, accumulate);
+    COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------
+// latent: reparameterisation + KL (model.py:147-156,182-184) and its gradient
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t step, uint32_t row, uint32_t col) {
+    uint32_t c[4] = {row, col >> 2, 1u, (uint32_t)(seed >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)step);
+    int pair = (col >> 1) & 1;
+    float u1 = ((float)(c[2 * pair] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float u2 = ((float)(c[2 * pair + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincosf(6.283185307179586f * u2, &sn, &cs);
+    return (col & 1) ? rad * sn : rad * cs;
+}
+__global__ void __launch_bounds__(256) k_latent_fwd(const float* __restrict__ mulv, const float* __restrict__ eps_in, int b,
+                                                    int R, int train, uint64_t seed, uint64_t step, long long row0,
+                                                    float* __restrict__ eps_used, float* __restrict__ z_f,
+                                                    bf16* __restrict__ z_h, float* __restrict__ kld_samp,
+                                                    float* __restrict__ stats) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float k = 0.f;
+    if (i < (long long)b * R) {
+        int r = (int)(i / R), c = (int)(i % R);
+        float mu = mulv[(long long)r * 2 * R + c], lv = mulv[(long long)r * 2 * R + R + c];
+        float z = mu;
+        if (train) {
+            float e = eps_in ? eps_in[i] : philox_normal(seed, step, (uint32_t)(row0 + r), (uint32_t)c);
+            eps_used[i] = e;
+            z = mu + expf(0.5f * lv) * e;
+        }
+        if (z_f) z_f[i] = z;
+        if (z_h) z_h[i] = __float2bfloat16(z);
+        k = 0.5f * (mu * mu + expf(lv) - lv - 1.0f);
+        if (kld_samp) kld_samp[i] = k;
+    }
+    k = warp_sum(k);
+    __shared__ float sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = k;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) t += sm[w];
+        atomicAdd(stats + 2, t);
+    }
+}
+void launch_latent_fwd(const float* mulv, const float* eps_in, int b, int R, int train, uint64_t seed, uint64_t step,
+                       long long row0, float* eps_used, float* z_f, bf16* z_h, float* kld_samp, float* stats, cudaStream_t s) {
+    k_latent_fwd<<<cdiv((long long)b * R, 256), 256, 0, s>>>(mulv, eps_in, b, R, train, seed, step, row0, eps_used, z_f, z_h,
+                                                             kld_samp, stats);
+    COUNT_LAUNCH();
+}
+__global__ void __launch_bounds__(256) k_latent_bwd(const float* __restrict__ dz, const float* __restrict__ mulv,
+                                                    const float* __restrict__ eps, int b, int R, int train, float a,
+                                                    float* __restrict__ df, bf16* __restrict__ dh) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)b * R) return;
+    int r = (int)(i / R), c = (int)(i % R);
+    float mu = mulv[(long long)r * 2 * R + c], lv = mulv[(long long)r * 2 * R + R + c];
+    float d = dz[i];
+    float dmu = d + a * mu;
+    float dlv = a * 0.5f * (expf(lv) - 1.0f);
+    if (train) dlv += d * 0.5f * expf(0.5f * lv) * eps[i];
+    long long o = (long long)r * 2 * R + c;
+    if (df) { df[o] = dmu; df[o + R] = dlv; }
+    if (dh) { dh[o] = __float2bfloat16(dmu); dh[o + R] = __float2bfloat16(dlv); }
+}
+void launch_latent_bwd(const float* dz, const float* mulv, const float* eps, int b, int R, int train, float a,
+                       float* dmulv_f, bf16* dmulv_h, cudaStream_t s) {
+    k_latent_bwd<<<cdiv((long long)b * R, 256), 256, 0, s>>>(dz, mulv, eps, b, R, train, a, dmulv_f, dmulv_h);
+    COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------
+// fused softmax cross entropy (model.py:170-181) + gradient, one CTA per row.
+// The row is staged once in shared memory (16-byte loads), reduced with warp shuffles, and the
+// gradient (softmax - onehot) * gscale is written back in place: 1 read + 1 write of N*V.
+// ------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_ce(T* __restrict__ logits, int ld, const int* __restrict__ labels, int V,
+                                            float gscale, int write_grad, float* __restrict__ loss_samp,
+                                            float* __restrict__ err_samp, int* __restrict__ pred, float* __restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* row = reinterpret_cast<T*>(smem_raw);
+    __shared__ float red_v[8];
+    __shared__ int red_i[8];
+    const long long r = blockIdx.x;
+    T* g = logits + r * ld;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr int VEC = 16 / sizeof(T);
+    const bool vec_ok = (V % VEC == 0) && (ld % VEC == 0);
+    // pass 0: stage row, track max / argmax (ties -> lowest index, like tf.argmax)
+    float mx = -INFINITY;
+    int mi = 0x7fffffff;
+    if (vec_ok) {
+        const int4* g4 = reinterpret_cast<const int4*>(g);
+        int4* r4 = reinterpret_cast<int4*>(row);
+        for (int i = tid; i < V / VEC; i += 256) {
+            int4 v = g4[i];
+            r4[i] = v;
+            const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float f = to_f<T>(e[j]);
+                if (f > mx) { mx = f; mi = i * VEC + j; }
+            }
+        }
+    } else {
+        for (int i = tid; i < V; i += 256) {
+            T v = g[i];
+            row[i] = v;
+            float f = to_f<T>(v);
+            if (f > mx) { mx = f; mi = i; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, mx, o);
+        int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (ov > mx || (ov == mx && oi < mi)) { mx = ov; mi = oi; }
+    }
+    if (lane == 0) { red_v[wid] = mx; red_i[wid] = mi; }
+    __syncthreads();
+    mx = red_v[0]; mi = red_i[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+        float ov = red_v[w]; int oi = red_i[w];
+        if (ov > mx || (ov == mx && oi < mi)) { mx = ov; mi = oi; }
+    }
+    __syncthreads();
+    // pass 1: sum exp
+    float sum = 0.f;
+    for (int i = tid; i < V; i += 256) sum += __expf(to_f<T>(row[i]) - mx);
+    sum = warp_sum(sum);
+    if (lane == 0) red_v[wid] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red_v[w];
+    const int lab = labels ? labels[r] : -1;
+    if (tid == 0) {
+        if (pred) pred[r] = mi;
+        if (labels) {
+            float loss = logf(sum) + mx - to_f<T>(row[lab]);
+            float err = (mi != lab) ? 1.f : 0.f;
+            if (loss_samp) loss_samp[r] = loss;
+            if (err_samp) err_samp[r] = err;
+            atomicAdd(stats + 0, loss);
+            atomicAdd(stats + 1, err);
+        }
+    }
+    if (!write_grad) return;
+    const float inv = gscale / sum;
+    if (vec_ok) {
+        int4* g4 = reinterpret_cast<int4*>(g);
+        const int4* r4 = reinterpret_cast<const int4*>(row);
+        for (int i = tid; i < V / VEC; i += 256) {
+            int4 v = r4[i];
+            T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                float p = __expf(to_f<T>(e[j]) - mx) * inv;
+                if (i * VEC + j == lab) p -= gscale;
+                e[j] = from_f<T>(p);
+            }
+            g4[i] = v;
+        }
+    } else {
+        for (int i = tid; i < V; i += 256) {
+            float p = __expf(to_f<T>(row[i]) - mx) * inv;
+            if (i == lab) p -= gscale;
+            g[i] = from_f<T>(p);
+        }
+    }
+}
+template <typename T>
+static void launch_ce(T* logits, int ld, const int* labels, long long n, int V, float gscale, int write_grad,
+                      float* loss_samp, float* err_samp, int* pred, float* stats, cudaStream_t s) {
+    if (n <= 0) return;
+    size_t smem = (size_t)V * sizeof(T);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_ce<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_ce<T><<<(unsigned)n, 256, smem, s>>>(logits, ld, labels, V, gscale, write_grad, loss_samp, err_samp, pred, stats);
+    COUNT_LAUNCH();
+}
+void launch_ce_f32(float* logits, int ld, const int* labels, long long n, int V, float gscale, int write_grad,
+                   float* loss_samp, float* err_samp, int* pred, float* stats, cudaStream_t s) {
+    launch_ce<float>(logits, ld, labels, n, V, gscale, write_grad, loss_samp, err_samp, pred, stats, s);
+}
+void launch_ce_bf16(bf16* logits, int ld, const int* labels, long long n, int V, float gscale, int write_grad,
+                    float* loss_samp, float* err_samp, int* pred, float* stats, cudaStream_t s) {
+    launch_ce<bf16>(logits, ld, labels, n, V, gscale, write_grad, loss_samp, err_samp, pred, stats, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam, TF-1 form (model.py:189): theta -= lr_t * m / (sqrt(v) + eps).  28 B/param (+2 shadow).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                              float* __restrict__ v, bf16* __restrict__ shadow, long long n4, long long n,
+                                              float lr_t, float b1, float b2, float eps) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n4; i += stride) {
+        float4 pp = reinterpret_cast<float4*>(p)[i];
+        float4 gg = reinterpret_cast<const float4*>(g)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+        float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* Vv = &vv.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            M[j] = b1 * M[j] + (1.f - b1) * G[j];
+            Vv[j] = b2 * Vv[j] + (1.f - b2) * G[j] * G[j];
+            P[j] -= lr_t * M[j] / (sqrtf(Vv[j]) + eps);
+        }
+        reinterpret_cast<float4*>(p)[i] = pp;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+        if (shadow) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(pp.x, pp.y), hi = __floats2bfloat162_rn(pp.z, pp.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(shadow)[i] = pk;
+        }
+    }
+    // tail (n not multiple of 4)
+    long long t = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) {
+        float mm = b1 * m[t] + (1.f - b1) * g[t];
+        float vv = b2 * v[t] + (1.f - b2) * g[t] * g[t];
+        float pp = p[t] - lr_t * mm / (sqrtf(vv) + eps);
+        m[t] = mm; v[t] = vv; p[t] = pp;
+        if (shadow) shadow[t] = __float2bfloat16(pp);
+    }
+}
+void launch_adam(float* p, const float* g, float* m, float* v, bf16* shadow, long long n, float lr_t, float b1,
+                 float b2, float eps, cudaStream_t s) {
+    if (n <= 0) return;
+    long long n4 = n / 4;
+    int blocks = (int)std::min<long long>(cdiv(std::max<long long>(n4, 1), 256), 148LL * 16);
+    k_adam<<<blocks, 256, 0, s>>>(p, g, m, v, shadow, n4, n, lr_t, b1, b2, eps);
+    COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------------
+// column sums (bias gradients)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_colsum(const T* __restrict__ in, int ld, long long rows, int cols,
+                                                float* __restrict__ out) {
+    __shared__ float sm[8][33];
+    int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    int ry = threadIdx.x >> 5;
+    long long chunk = (rows + gridDim.y - 1) / gridDim.y;
+    long long r0 = (long long)blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
+    float acc = 0.f;
+    if (c < cols)
+        for (long long r = r0 + ry; r < r1; r += 8) acc += to_f<T>(in[r * ld + c]);
+    sm[ry][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (ry == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t += sm[j][threadIdx.x];
+        atomicAdd(out + c, t);
+    }
+}
+template <typename T>
+static void launch_colsum(const T* in, int ld, long long rows, int cols, float* out, cudaStream_t s) {
+    CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
+    if (rows <= 0) return;
+    int gy = (int)std::max<long long>(1, std::min<long long>(64, rows / 64));
+    dim3 grid(cdiv(cols, 32), gy);
+    k_colsum<T><<<grid, 256, 0, s>>>(in, ld, rows, cols, out);
+    COUNT_LAUNCH();
+}
+void launch_colsum_f32(const float* in, int ld, long long rows, int cols, float* out, cudaStream_t s) {
+    launch_colsum<float>(in, ld, rows, cols, out, s);
+}
+void launch_colsum_bf16(const bf16* in, int ld, long long rows, int cols, float* out, cudaStream_t s) {
+    launch_colsum<bf16>(in, ld, rows, cols, out, s);
+}
+
+__global__ void __launch_bounds__(256) k_cast_bf16(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = __float2bfloat16(in[i]);
+}
+void launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s) {
+    if (n <= 0) return;
+    int blocks = (int)std::min<long long>(cdiv(n, 256), 148LL * 16);
+    k_cast_bf16<<<blocks, 256, 0, s>>>(in, out, n);
+    COUNT_LAUNCH();
+}
+__global__ void __launch_bounds__(256) k_fill(float* p, long long n, float v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+void launch_fill(float* p, long long n, float v, cudaStream_t s) {
+    if (n <= 0) return;
+    int blocks = (int)std::min<long long>(cdiv(n, 256), 148LL * 16);
+    k_fill<<<blocks, 256, 0, s>>>(p, n, v);
+    COUNT_LAUNCH();
+}

@@ -1,0 +1,85 @@
+// kernels.h -- launch wrappers of the bandwidth-bound kernels (kernels.cu), the GEMMs
+// (gemm_simt.cu, gemm_tc.cu) and the GRU recurrences (gru.cu).
+#pragma once
+#include "common.cuh"
+
+// ---- kernels.cu -------------------------------------------------------------------------
+// out[i,:] = table[ids[i],:]   (A5: tf.gather, model.py:111-112)
+void launch_embed_gather_f32(const int* ids, long long n, const float* table, int D, float* out, cudaStream_t s);
+void launch_embed_gather_bf16(const int* ids, long long n, const bf16* table, int D, bf16* out, cudaStream_t s);
+// table_grad[ids[i],:] += dx[i,:]   (A18: IndexedSlices part of dE)
+void launch_embed_scatter_add(const int* ids, long long n, const float* dx, int ld, int D, float* table_grad, cudaStream_t s);
+// generic row gather: out[dst[i] or i, :] = in[src[i] or i, :]; writes fp32 and/or bf16
+void launch_row_gather(const float* in, int ld_in, const int* src_idx, float* out_f, bf16* out_h, int ld_out,
+                       const int* dst_idx, int n, int cols, cudaStream_t s);
+// A9/A15: z = mu (+ exp(lv/2)*eps), kld_samp, sum(kld) -> stats[2]
+void launch_latent_fwd(const float* mulv, const float* eps_in, int b, int R, int train, uint64_t seed, uint64_t step,
+                       long long row0, float* eps_used, float* z_f, bf16* z_h, float* kld_samp, float* stats, cudaStream_t s);
+// A18: dmu = dz + a*mu ; dlv = dz*.5*exp(lv/2)*eps + a*.5*(exp(lv)-1)   (a = anneal/(b_global*R))
+void launch_latent_bwd(const float* dz, const float* mulv, const float* eps, int b, int R, int train, float a,
+                       float* dmulv_f, bf16* dmulv_h, cudaStream_t s);
+// A12-A14 + A18: fused softmax cross entropy; logits overwritten by (softmax-onehot)*gscale when write_grad
+void launch_ce_f32(float* logits, int ld, const int* labels, long long n, int V, float gscale, int write_grad,
+                   float* loss_samp, float* err_samp, int* pred, float* stats, cudaStream_t s);
+void launch_ce_bf16(bf16* logits, int ld, const int* labels, long long n, int V, float gscale, int write_grad,
+                    float* loss_samp, float* err_samp, int* pred, float* stats, cudaStream_t s);
+// A17: TF-form Adam over a flat buffer; optional bf16 shadow
+void launch_adam(float* p, const float* g, float* m, float* v, bf16* shadow, long long n, float lr_t,
+                 float b1, float b2, float eps, cudaStream_t s);
+// out[c] = sum_r in[r,c]
+void launch_colsum_f32(const float* in, int ld, long long rows, int cols, float* out, cudaStream_t s);
+void launch_colsum_bf16(const bf16* in, int ld, long long rows, int cols, float* out, cudaStream_t s);
+void launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s);
+// dst[dst_idx[i],:] += (or =) src[i,:]
+void launch_row_scatter(const float* in, int ld_in, float* out, int ld_out, const int* dst_idx, int n, int cols,
+                        int accumulate, cudaStream_t s);
+void launch_fill(float* p, long long n, float v, cudaStream_t s);
+
+// ---- gemm_simt.cu / gemm_tc.cu ----------------------------------------------------------
+// C(M,N) = alpha * A(M,K) * B(N,K)^T + bias[N] (+ C when accumulate).
+// a_mn/b_mn = 0: operand stored (M|N rows, K cols) K-contiguous; 1: stored (K rows, M|N cols).
+void gemm_simt(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc,
+               int M, int N, int K, float alpha, const float* bias, int accumulate, bf16* C_h, cudaStream_t s);
+// tcgen05 + TMA path (bf16 operands, fp32 accumulate in TMEM). Cf and/or Ch may be null.
+void gemm_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, float* Cf, bf16* Ch, int ldc,
+             int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s);
+void gemm_tc_init(int device);
+
+// ---- gru.cu -----------------------------------------------------------------------------
+struct GruSeq {
+    // one recurrence ("direction"): packed rows, sorted batch (descending length)
+    const float* gx;      // (rows, ld_gx) precomputed W x + bW, this direction's 3H columns
+    int ld_gx;
+    const float* R;       // (3H,H) fp32
+    const float* bR;      // (3H)
+    const float* h0;      // (b,H) or null (zeros)
+    float* hs;            // (rows, ld_hs) output, this direction's H columns
+    bf16* hs_h;           // bf16 twin or null
+    int ld_hs;
+    float* cache;         // (rows, 4H): r,u,n,q per row (training) or null
+    int reverse;          // 1: tf.reverse_sequence semantics (encoder bwd direction)
+    float* hT;            // (b,H) final state or null
+};
+struct GruSeqBwd {
+    const float* dhs;     // (rows, ld_dhs) gradient wrt outputs (this direction's columns)
+    int ld_dhs;
+    const float* hs;      // forward outputs
+    int ld_hs;
+    const float* h0;      // or null
+    const float* cache;   // (rows,4H)
+    const float* R;       // (3H,H)
+    float* dgx;           // (rows, ld_dg) out: grad wrt gx
+    bf16* dgx_h;
+    float* dgh;           // (rows, ld_dg) out: grad wrt (R h + bR)
+    bf16* dgh_h;
+    int ld_dg;
+    float* dh0_acc;       // (b,H) accumulated (+=) gradient wrt h0, or null
+    int reverse;
+};
+// lens (b) descending, off (Tmax+1) prefix offsets of active counts; both on device.
+void launch_gru_fwd(const GruSeq* seqs, int ndir, const int* lens, const int* off, int b, int Tmax, int H,
+                    float* work, unsigned* bar, cudaStream_t s);
+void launch_gru_bwd(const GruSeqBwd* seqs, int ndir, const int* lens, const int* off, int b, int Tmax, int H,
+                    float* work, unsigned* bar, cudaStream_t s);
+size_t gru_work_floats(int b, int H);
+void gru_init(int device);

@@ -1,0 +1,53 @@
+"""Builds libargsim_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libargsim_b200.so')
+SOURCES = ['kernels.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'gru_generic.cu', 'gru_mma.cu', 'plan.cpp', 'engine.cu', 'capi.cu']
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
+         '--expt-relaxed-constexpr']
+
+
+def _deps_mtime():
+    return max(os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC)
+               if f.endswith(('.cu', '.cuh', '.h', '.cpp'))) if os.path.isdir(CSRC) else 0
+
+
+def needs_build():
+    hdr = os.path.join(HERE, '..', 'include', 'argsim_b200.h')
+    return (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(_deps_mtime(), os.path.getmtime(hdr))
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    objdir = os.path.join(HERE, 'build')
+    os.makedirs(objdir, exist_ok=True)
+
+    def cc(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + '.o')
+        cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-x', 'cu', '-c', os.path.join(CSRC, src), '-o', obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))
+        if verbose:
+            sys.stderr.write(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(cc, SOURCES))
+    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-Xcompiler', '-fPIC', '-ldl', '-cudart', 'static',
+                                                  '-gencode', 'arch=compute_100a,code=sm_100a']
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

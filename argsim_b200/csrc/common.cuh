@@ -50,20 +50,4 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
-// ---- Philox4x32-10 counter RNG (Salmon et al. 2011), keyed by (seed, step | stream) ----------
-// counter = (row_global, position, stream, 0).  Restated bit-exactly in numpy by
-// argsim_b200/rng.py so the keep-mask / eps streams can be reproduced on the host.
-__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
-        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
-        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-        uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-        k0 += W0; k1 += W1;
-    }
-}
-// uniform in [0,1) with 24 bits
-__host__ __device__ __forceinline__ float u01_24(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+#include "philox.h"

@@ -1,0 +1,862 @@
+// engine.cu -- see engine.h.  Reference: src/model.py:75-189 (graph), src/train.py:104-121 (loops).
+#include "engine.h"
+#include "nccl_dyn.h"
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <random>
+
+#define RUN(...)                  \
+    do {                          \
+        if (!arena.dry) {         \
+            __VA_ARGS__;          \
+        }                         \
+    } while (0)
+
+static inline size_t align_up(size_t n, size_t a) { return (n + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------
+// construction: parameter table in backward-completion order (== allreduce bucket order)
+// ------------------------------------------------------------------------------------------
+Engine::Engine(const argsim_config& c) : cfg(c) {
+    V = c.dim_tgt; D = c.dim_emb; R = c.dim_rep; L = c.rnn_layers; H = D;
+    if (V <= 0 || D <= 0 || R <= 0 || L <= 0) throw std::runtime_error("bad model dimensions");
+    if (c.attentive)
+        throw std::runtime_error("attentive=true is not implemented (unused by config.json; the reference marks it 'todo fixme', src/model.py:136)");
+    if (!c.bidirectional || !c.bidir_stacked)
+        throw std::runtime_error("only the stacked bidirectional encoder of config.json is implemented (src/model.py:118-122)");
+    if (!c.logit_use_embed) throw std::runtime_error("logit_use_embed=false is not implemented (src/model.py:167-168)");
+    if (D % 8 || R % 8 || V % 8) throw std::runtime_error("dim_tgt, dim_emb and dim_rep must be multiples of 8");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        throw std::runtime_error("no CUDA device: argsim_b200 has no CPU fallback");
+    CUDA_CHECK(cudaSetDevice(c.device));
+    is_bf16 = (c.precision == ARGSIM_BF16);
+    use_tc = is_bf16;
+    if (use_tc) {
+        gemm_tc_init(c.device);
+        if (!gemm_tc_available()) throw std::runtime_error("BF16 precision needs the tcgen05 GEMM path (sm_100a device + driver TMA entry point)");
+    }
+    use_mma = is_bf16 && gru_mma_supported(H) && !(c.flags & 4);
+    for (auto& s : st) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_bucket, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
+    if (use_mma) mma = gru_mma_create(c.device);
+
+    auto add = [&](const std::string& name, int64_t r, int64_t cdim) {
+        ParamInfo pi;
+        pi.name = name;
+        pi.rank = cdim ? 2 : 1;
+        pi.shape[0] = r; pi.shape[1] = cdim;
+        pi.n = (size_t)r * (cdim ? cdim : 1);
+        pi.off = nflat;
+        nflat += align_up(pi.n, 64);
+        pindex[name] = (int)params.size();
+        params.push_back(pi);
+    };
+    add("decode/out/kernel", D, D);
+    add("decode/out/bias", D, 0);
+    for (int j = L - 1; j >= 0; --j) {
+        std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
+        add(pre + "W", 3 * H, D); add(pre + "R", 3 * H, H); add(pre + "bW", 3 * H, 0); add(pre + "bR", 3 * H, 0);
+    }
+    add("latent/ex/kernel", R, D); add("latent/ex/bias", D, 0);
+    add("latent/mu/kernel", 2 * H, R); add("latent/mu/bias", R, 0);
+    add("latent/lv/kernel", 2 * H, R); add("latent/lv/bias", R, 0);
+    for (int i = L; i >= 1; --i) {
+        std::string pre = "encode/rnn" + std::to_string(i) + "/";
+        const int in = (i == 1) ? D : 2 * H;
+        // fwd and bwd tensors adjacent so that [W_f;W_b] is one (6H,in) GEMM operand
+        add(pre + "fwd/W", 3 * H, in); add(pre + "bwd/W", 3 * H, in);
+        add(pre + "fwd/R", 3 * H, H); add(pre + "bwd/R", 3 * H, H);
+        add(pre + "fwd/bW", 3 * H, 0); add(pre + "bwd/bW", 3 * H, 0);
+        add(pre + "fwd/bR", 3 * H, 0); add(pre + "bwd/bR", 3 * H, 0);
+    }
+    add("embed/embedding", V, D);
+    // fwd/bwd tensor pairs are only contiguous when their sizes are multiples of the 64-element padding
+    if ((3 * H) % 64) throw std::runtime_error("dim_emb must be a multiple of 64");
+    CUDA_CHECK(cudaMalloc(&p, nflat * sizeof(float)));
+    CUDA_CHECK(cudaMalloc(&g, nflat * sizeof(float)));
+    CUDA_CHECK(cudaMalloc(&m, nflat * sizeof(float)));
+    CUDA_CHECK(cudaMalloc(&v, nflat * sizeof(float)));
+    CUDA_CHECK(cudaMemset(p, 0, nflat * sizeof(float)));
+    CUDA_CHECK(cudaMemset(g, 0, nflat * sizeof(float)));
+    CUDA_CHECK(cudaMemset(m, 0, nflat * sizeof(float)));
+    CUDA_CHECK(cudaMemset(v, 0, nflat * sizeof(float)));
+    if (is_bf16) {
+        CUDA_CHECK(cudaMalloc(&ph, nflat * sizeof(::bf16)));
+        CUDA_CHECK(cudaMemset(ph, 0, nflat * sizeof(::bf16)));
+    }
+    CUDA_CHECK(cudaMalloc(&d_stats, 4 * sizeof(double)));
+    CUDA_CHECK(cudaMallocHost(&h_stats, 4 * sizeof(double)));
+
+    if (c.nranks > 1) {
+        NcclApi& n = NcclApi::get();
+        NcclApi::unique_id id;
+        memcpy(id.internal, c.nccl_id, 128);
+        NcclApi::comm_t comm;
+        n.check(n.CommInitRank(&comm, c.nranks, id, c.rank), "ncclCommInitRank");
+        nccl_comm = comm;
+    }
+    CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+Engine::~Engine() {
+    cudaDeviceSynchronize();
+    if (nccl_comm) NcclApi::get().CommDestroy((NcclApi::comm_t)nccl_comm);
+    if (mma) gru_mma_destroy(mma);
+    cudaFree(p); cudaFree(g); cudaFree(m); cudaFree(v); cudaFree(ph);
+    cudaFree(arena.base); cudaFree(d_stage); cudaFreeHost(h_stage); cudaFree(d_eps_in);
+    cudaFree(d_stats); cudaFreeHost(h_stats); cudaFreeHost(h_out); cudaFree(gru_work);
+    for (auto& e : pev) cudaEventDestroy(e);
+    for (auto& k : ktimers) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
+    cudaEventDestroy(ev_bucket); cudaEventDestroy(ev_comm);
+    for (auto& s : st) if (s) cudaStreamDestroy(s);
+}
+
+const ParamInfo& Engine::pinfo(const std::string& name) const {
+    auto it = pindex.find(name);
+    if (it == pindex.end()) throw std::runtime_error("unknown parameter: " + name);
+    return params[it->second];
+}
+Mat Engine::pmat(const std::string& name) {
+    const ParamInfo& pi = pinfo(name);
+    const int cols = pi.rank == 2 ? (int)pi.shape[1] : (int)pi.shape[0];
+    const long long rows = pi.rank == 2 ? pi.shape[0] : 1;
+    return Mat(p + pi.off, ph ? ph + pi.off : nullptr, rows, cols, cols);
+}
+Mat Engine::gmat(const std::string& name) {
+    const ParamInfo& pi = pinfo(name);
+    const int cols = pi.rank == 2 ? (int)pi.shape[1] : (int)pi.shape[0];
+    const long long rows = pi.rank == 2 ? pi.shape[0] : 1;
+    return Mat(g + pi.off, nullptr, rows, cols, cols);
+}
+
+void Engine::refresh_shadow(size_t off, size_t n) {
+    if (ph) launch_cast_bf16(p + off, ph + off, (long long)n, st[0]);
+}
+
+// A22: src/model.py:8-15,109-110.  Host RNG (mt19937_64); only the distributions are specified
+// by the reference, TF's own streams cannot be matched.
+void Engine::init_params(uint64_t seed_) {
+    std::mt19937_64 rng(seed_);
+    std::vector<float> host(nflat, 0.f);
+    auto uni = [&](float* dst, size_t n, float bound) {
+        std::uniform_real_distribution<float> d(-bound, bound);
+        for (size_t i = 0; i < n; ++i) dst[i] = d(rng);
+    };
+    for (const ParamInfo& pi : params) {
+        float* dst = host.data() + pi.off;
+        if (pi.rank == 1) continue;  // biases zero
+        if (pi.name == "embed/embedding") {
+            uni(dst, pi.n, sqrtf(6.0f / ((float)V / (float)D + 1.0f)));
+        } else if (pi.name.size() > 2 && (pi.name.substr(pi.name.size() - 2) == "/W" || pi.name.substr(pi.name.size() - 2) == "/R")) {
+            // variance_scaling(1,'fan_avg','uniform') per canonical (H,in) sub-matrix, one per gate
+            const int in = (int)pi.shape[1];
+            uni(dst, pi.n, sqrtf(6.0f / (float)(in + H)));
+        } else {
+            uni(dst, pi.n, sqrtf(6.0f / (float)(pi.shape[0] + pi.shape[1])));
+        }
+    }
+    CUDA_CHECK(cudaMemcpy(p, host.data(), nflat * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemset(m, 0, nflat * sizeof(float)));
+    CUDA_CHECK(cudaMemset(v, 0, nflat * sizeof(float)));
+    refresh_shadow(0, nflat);
+    CUDA_CHECK(cudaStreamSynchronize(st[0]));
+    step = 0;
+}
+
+void Engine::set_param(const std::string& name, const float* src) {
+    const ParamInfo& pi = pinfo(name);
+    CUDA_CHECK(cudaMemcpy(p + pi.off, src, pi.n * sizeof(float), cudaMemcpyHostToDevice));
+    refresh_shadow(pi.off, pi.n);
+    CUDA_CHECK(cudaStreamSynchronize(st[0]));
+}
+void Engine::get_flat(const float* flat, const std::string& name, float* dst) {
+    const ParamInfo& pi = pinfo(name);
+    CUDA_CHECK(cudaMemcpy(dst, flat + pi.off, pi.n * sizeof(float), cudaMemcpyDeviceToHost));
+}
+void Engine::set_flat(float* flat, const std::string& name, const float* src) {
+    const ParamInfo& pi = pinfo(name);
+    CUDA_CHECK(cudaMemcpy(flat + pi.off, src, pi.n * sizeof(float), cudaMemcpyHostToDevice));
+}
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+Mat Engine::act(long long rows, int cols) {
+    if (use_tc) return Mat(nullptr, (::bf16*)arena.alloc(sizeof(::bf16) * rows * cols), rows, cols, cols);
+    return Mat((float*)arena.alloc(sizeof(float) * rows * cols), nullptr, rows, cols, cols);
+}
+Mat Engine::f32(long long rows, int cols) {
+    return Mat((float*)arena.alloc(sizeof(float) * rows * cols), nullptr, rows, cols, cols);
+}
+Mat Engine::both(long long rows, int cols) {
+    float* f = (float*)arena.alloc(sizeof(float) * rows * cols);
+    ::bf16* h = use_tc ? (::bf16*)arena.alloc(sizeof(::bf16) * rows * cols) : nullptr;
+    return Mat(f, h, rows, cols, cols);
+}
+
+void Engine::gemm(const Mat& A, int a_mn, const Mat& B, int b_mn, const Mat& C, long long M, int N, long long K, float alpha,
+                  const float* bias, int accumulate) {
+    if (arena.dry || M <= 0 || N <= 0) return;
+    if (use_tc) {
+        if (!A.h || !B.h) throw std::runtime_error("gemm: bf16 operand view missing (internal error)");
+        gemm_tc(A.h, A.ld, a_mn, B.h, B.ld, b_mn, C.f, C.h, C.ld, (int)M, N, (int)K, alpha, bias, accumulate, st[0]);
+    } else {
+        if (!A.f || !B.f) throw std::runtime_error("gemm: fp32 operand view missing (internal error)");
+        gemm_simt(A.f, A.ld, a_mn, B.f, B.ld, b_mn, C.f, C.ld, (int)M, N, (int)K, alpha, bias, accumulate, C.h, st[0]);
+    }
+}
+void Engine::colsum(const Mat& A, long long rows, int cols, float* out) {
+    if (arena.dry) return;
+    if (A.f) launch_colsum_f32(A.f, A.ld, rows, cols, out, st[0]);
+    else launch_colsum_bf16(A.h, A.ld, rows, cols, out, st[0]);
+}
+void Engine::gather_embed(const int* ids, long long n, const Mat& out) {
+    if (arena.dry) return;
+    const ParamInfo& e = pinfo("embed/embedding");
+    if (out.h) launch_embed_gather_bf16(ids, n, ph + e.off, D, out.h, st[0]);
+    else launch_embed_gather_f32(ids, n, p + e.off, D, out.f, st[0]);
+}
+void Engine::gru_fwd(GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact) {
+    if (arena.dry) return;
+    kbegin(ndir == 2 ? "k:gru_fwd_enc" : "k:gru_fwd_dec");
+    if (use_mma) gru_mma_fwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0]);
+    else gru_generic_fwd(dirs, ndir, P, H, gru_work, st);
+    kend();
+}
+void Engine::gru_bwd(GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact) {
+    if (arena.dry) return;
+    kbegin(ndir == 2 ? "k:gru_bwd_enc" : "k:gru_bwd_dec");
+    if (use_mma) gru_mma_bwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0]);
+    else gru_generic_bwd(dirs, ndir, P, H, gru_work, st);
+    kend();
+}
+
+void Engine::allreduce_bucket(size_t off0, size_t off1) {
+    if (arena.dry || cfg.nranks <= 1 || off1 <= off0) return;
+    NcclApi& n = NcclApi::get();
+    CUDA_CHECK(cudaEventRecord(ev_bucket, st[0]));
+    CUDA_CHECK(cudaStreamWaitEvent(st[2], ev_bucket, 0));
+    n.check(n.AllReduce(g + off0, g + off0, off1 - off0, NcclApi::Float32, NcclApi::Sum, (NcclApi::comm_t)nccl_comm, st[2]),
+            "ncclAllReduce");
+}
+
+void Engine::phase(const char* name) {
+    if (arena.dry) return;
+    if (pcount == pev.size()) {
+        cudaEvent_t e;
+        CUDA_CHECK(cudaEventCreate(&e));
+        pev.push_back(e);
+        pnames.push_back("");
+    }
+    pnames[pcount] = name;
+    CUDA_CHECK(cudaEventRecord(pev[pcount], st[0]));
+    ++pcount;
+}
+void Engine::kbegin(const char* name) {
+    if (!(cfg.flags & 8)) return;
+    if (kcount == ktimers.size()) {
+        KTimer k;
+        CUDA_CHECK(cudaEventCreate(&k.a));
+        CUDA_CHECK(cudaEventCreate(&k.b));
+        ktimers.push_back(k);
+    }
+    ktimers[kcount].name = name;
+    CUDA_CHECK(cudaEventRecord(ktimers[kcount].a, st[0]));
+}
+void Engine::kend() {
+    if (!(cfg.flags & 8)) return;
+    CUDA_CHECK(cudaEventRecord(ktimers[kcount].b, st[0]));
+    ++kcount;
+}
+void Engine::collect_timings() {
+    tnames.clear(); tms.clear();
+    for (size_t i = 0; i + 1 < pcount; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, pev[i], pev[i + 1]);
+        tnames.push_back(pnames[i + 1]);
+        tms.push_back(ms);
+    }
+    std::map<std::string, std::pair<float, int>> agg;
+    for (size_t i = 0; i < kcount; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ktimers[i].a, ktimers[i].b);
+        agg[ktimers[i].name].first += ms;
+        agg[ktimers[i].name].second += 1;
+    }
+    for (auto& kv : agg) {
+        tnames.push_back(kv.first);
+        tms.push_back(kv.second.first);
+        tnames.push_back(kv.first + "#n");
+        tms.push_back((float)kv.second.second);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// staging: host plan -> one pinned buffer -> one H2D copy
+// ------------------------------------------------------------------------------------------
+void Engine::stage(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt, int need_dec, const DropoutSpec& drop,
+                   const float* eps) {
+    std::string e = build_batch_plan(src, b, Ts, tgt, Tt, cfg.bos, cfg.eos, need_dec, drop, &plan);
+    if (!e.empty()) throw std::runtime_error(e);
+    const SeqPlan& E = plan.enc;
+    const SeqPlan& Dp = plan.dec;
+    for (int x : plan.ids_src)
+        if (x < 0 || x >= V) throw std::runtime_error("src token id out of range [0, dim_tgt)");
+    for (int x : plan.ids_lead)
+        if (x < 0 || x >= V) throw std::runtime_error("tgt token id out of range [0, dim_tgt)");
+    for (int x : plan.labels)
+        if (x < 0 || x >= V) throw std::runtime_error("eos/tgt token id out of range [0, dim_tgt)");
+    size_t need = plan.ids_src.size() + plan.ids_lead.size() + plan.labels.size() + 2 * (size_t)b + (E.Tmax + 1) + E.Tmax +
+                  (Dp.Tmax + 1) + Dp.Tmax + 64 * 9;
+    if (need > stage_cap) {
+        CUDA_CHECK(cudaStreamSynchronize(st[0]));
+        cudaFreeHost(h_stage); cudaFree(d_stage);
+        stage_cap = need * 2;
+        CUDA_CHECK(cudaMallocHost(&h_stage, stage_cap * sizeof(int)));
+        CUDA_CHECK(cudaMalloc(&d_stage, stage_cap * sizeof(int)));
+    }
+    size_t o = 0;
+    auto put = [&](const std::vector<int>& vsrc, int** dev) {
+        *dev = d_stage + o;
+        if (!vsrc.empty()) memcpy(h_stage + o, vsrc.data(), vsrc.size() * sizeof(int));
+        o = align_up(o + vsrc.size(), 64);
+    };
+    put(plan.ids_src, &dp.ids_src);
+    put(plan.ids_lead, &dp.ids_lead);
+    put(plan.labels, &dp.labels);
+    put(plan.enc_last, &dp.enc_last);
+    put(Dp.perm, &dp.dec_perm);
+    put(E.off, &dp.enc_off);
+    put(E.nact, &dp.enc_nact);
+    put(Dp.off, &dp.dec_off);
+    put(Dp.nact, &dp.dec_nact);
+    CUDA_CHECK(cudaMemcpyAsync(d_stage, h_stage, o * sizeof(int), cudaMemcpyHostToDevice, st[0]));
+    have_eps = false;
+    if (eps) {
+        size_t n = (size_t)b * R;
+        if (n > eps_cap) {
+            cudaFree(d_eps_in);
+            CUDA_CHECK(cudaMalloc(&d_eps_in, n * sizeof(float)));
+            eps_cap = n;
+        }
+        CUDA_CHECK(cudaMemcpyAsync(d_eps_in, eps, n * sizeof(float), cudaMemcpyHostToDevice, st[0]));
+        have_eps = true;
+    }
+    size_t gw = gru_generic_work_floats(b, H) * 2;
+    if (gw > gru_work_cap) {
+        CUDA_CHECK(cudaStreamSynchronize(st[0]));
+        cudaFree(gru_work);
+        CUDA_CHECK(cudaMalloc(&gru_work, gw * sizeof(float)));
+        gru_work_cap = gw;
+    }
+}
+
+void Engine::ensure_arena(int mode) {
+    arena.reset(true);
+    arena.high = 0;
+    program(mode, false);
+    size_t need = arena.high + 4096;
+    if (need > arena.cap) {
+        CUDA_CHECK(cudaDeviceSynchronize());
+        cudaFree(arena.base);
+        arena.cap = need + need / 8;
+        CUDA_CHECK(cudaMalloc(&arena.base, arena.cap));
+    }
+    arena.reset(false);
+}
+
+void Engine::run_device(int mode, bool apply_update) {
+    ensure_arena(mode);
+    pcount = 0; kcount = 0;
+    program(mode, apply_update);
+}
+
+// ------------------------------------------------------------------------------------------
+// the device program
+// ------------------------------------------------------------------------------------------
+void Engine::program(int mode, bool apply_update) {
+    const bool train = (mode == 2);
+    const SeqPlan& E = plan.enc;
+    const SeqPlan& Dp = plan.dec;
+    const long long S = E.rows, N = Dp.rows;
+    const int b = plan.b;
+    cudaStream_t s = st[0];
+    const int64_t b_glob = last.b_global > 0 ? last.b_global : b;
+    const int64_t n_glob = last.n_tok_global > 0 ? last.n_tok_global : N;
+    float keepwd, anneal, lr;
+    schedule_f32(step, cfg.accelerate, cfg.learn_rate, &keepwd, &anneal, &lr);
+
+    phase("begin");
+    RUN(CUDA_CHECK(cudaMemsetAsync(d_stats, 0, 4 * sizeof(double), s)));
+    if (train) RUN(CUDA_CHECK(cudaMemsetAsync(g, 0, nflat * sizeof(float), s)));
+    bucket_lo = 0;
+
+    // ---------------- encoder (model.py:111-122): 3 x (fwd GRU || bwd GRU) over packed rows
+    std::vector<Mat> encX(L + 1);
+    std::vector<float*> encCache(2 * L, nullptr);
+    encX[0] = act(S, D);
+    gather_embed(dp.ids_src, S, encX[0]);
+    for (int i = 0; i < L; ++i) {
+        const int in = (i == 0) ? D : 2 * H;
+        const std::string pre = "encode/rnn" + std::to_string(i + 1) + "/";
+        Mat W = pmat(pre + "fwd/W");
+        W.rows = 6 * H;
+        Mat GX = f32(S, 6 * H);
+        gemm(encX[i], 0, W, 0, GX, S, 6 * H, in, 1.f, p + pinfo(pre + "fwd/bW").off, 0);
+        Mat HS = act(S, 2 * H);
+        GruFwdArgs a[2];
+        for (int d = 0; d < 2; ++d) {
+            const std::string pd = pre + (d ? "bwd/" : "fwd/");
+            if (train) encCache[2 * i + d] = (float*)arena.alloc(sizeof(float) * S * 4 * H);
+            a[d].gx = GX.f + d * 3 * H; a[d].ld_gx = 6 * H;
+            a[d].R_f = p + pinfo(pd + "R").off;
+            a[d].R_h = ph ? ph + pinfo(pd + "R").off : nullptr;
+            a[d].bR = p + pinfo(pd + "bR").off;
+            a[d].h0 = nullptr;
+            a[d].hs_f = HS.f ? HS.f + d * H : nullptr;
+            a[d].hs_h = HS.h ? HS.h + d * H : nullptr;
+            a[d].ld_hs = 2 * H;
+            a[d].cache = encCache[2 * i + d];
+            a[d].reverse = d;
+        }
+        gru_fwd(a, 2, E, dp.enc_off, dp.enc_nact);
+        encX[i + 1] = HS;
+    }
+    phase("enc_fwd");
+
+    // ---------------- final state + latent (model.py:133-156)
+    Mat henc = both(b, 2 * H);
+    RUN(launch_row_gather(encX[L].f, encX[L].h, 2 * H, dp.enc_last, henc.f, henc.h, 2 * H, nullptr, b, 2 * H, s));
+    Mat mulv = f32(b, 2 * R);
+    gemm(henc, 0, pmat("latent/mu/kernel"), 1, mulv.colslice(0, R), b, R, 2 * H, 1.f, p + pinfo("latent/mu/bias").off, 0);
+    outp = Out();
+    outp.mulv = mulv.f;
+    if (mode == 0) {
+        phase("latent_fwd");
+        return;
+    }
+    gemm(henc, 0, pmat("latent/lv/kernel"), 1, mulv.colslice(R, R), b, R, 2 * H, 1.f, p + pinfo("latent/lv/bias").off, 0);
+    Mat z = both(b, R);
+    float* eps_used = train ? (float*)arena.alloc(sizeof(float) * b * R) : nullptr;
+    float* kld_samp = (float*)arena.alloc(sizeof(float) * b * R);
+    outp.kld_samp = kld_samp;
+    RUN(launch_latent_fwd(mulv.f, have_eps ? d_eps_in : nullptr, b, R, train ? 1 : 0, seed, (uint64_t)step, last.row0, eps_used,
+                          z.f, z.h, kld_samp, d_stats, s));
+    Mat hx = f32(b, D);
+    gemm(z, 0, pmat("latent/ex/kernel"), 1, hx, b, D, R, 1.f, p + pinfo("latent/ex/bias").off, 0);
+    Mat hx_sorted = f32(b, H);
+    RUN(launch_row_gather(hx.f, nullptr, D, dp.dec_perm, hx_sorted.f, nullptr, H, nullptr, b, H, s));
+    phase("latent_fwd");
+
+    // ---------------- decoder (model.py:158-162): 3 stacked GRUs, all seeded with ex(z)
+    std::vector<Mat> decY(L + 1);
+    std::vector<float*> decCache(L, nullptr);
+    decY[0] = act(N, D);
+    gather_embed(dp.ids_lead, N, decY[0]);
+    for (int j = 0; j < L; ++j) {
+        const std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
+        Mat GX = f32(N, 3 * H);
+        gemm(decY[j], 0, pmat(pre + "W"), 0, GX, N, 3 * H, D, 1.f, p + pinfo(pre + "bW").off, 0);
+        Mat Y = act(N, H);
+        if (train) decCache[j] = (float*)arena.alloc(sizeof(float) * N * 4 * H);
+        GruFwdArgs a;
+        a.gx = GX.f; a.ld_gx = 3 * H;
+        a.R_f = p + pinfo(pre + "R").off;
+        a.R_h = ph ? ph + pinfo(pre + "R").off : nullptr;
+        a.bR = p + pinfo(pre + "bR").off;
+        a.h0 = hx_sorted.f;
+        a.hs_f = Y.f; a.hs_h = Y.h; a.ld_hs = H;
+        a.cache = decCache[j];
+        a.reverse = 0;
+        gru_fwd(&a, 1, Dp, dp.dec_off, dp.dec_nact);
+        decY[j + 1] = Y;
+    }
+    Mat HO = act(N, D);
+    gemm(decY[L], 0, pmat("decode/out/kernel"), 1, HO, N, D, D, 1.f, p + pinfo("decode/out/bias").off, 0);
+    phase("dec_fwd");
+
+    // ---------------- vocab projection + fused softmax-CE (+ its two backward GEMMs), row chunks
+    // sized so that the logits chunk stays L2 resident (126 MB) between its producer and consumers.
+    float* loss_samp = (float*)arena.alloc(sizeof(float) * N);
+    float* err_samp = (float*)arena.alloc(sizeof(float) * N);
+    int* pred = (int*)arena.alloc(sizeof(int) * N);
+    outp.loss_samp = loss_samp; outp.err_samp = err_samp; outp.pred = pred;
+    const float scale = 1.0f / sqrtf((float)D);
+    long long chunk = use_tc ? 4096 : 2048;
+    if (const char* ev = getenv("ARGSIM_LOGIT_CHUNK")) chunk = std::max(128, atoi(ev));
+    chunk = std::min<long long>(chunk, std::max<long long>(N, 1));
+    Mat logits = act(chunk, V);
+    Mat dHO = train ? act(N, D) : Mat();
+    Mat Emb = pmat("embed/embedding");
+    Mat gE = gmat("embed/embedding");
+    for (long long r0 = 0; r0 < N; r0 += chunk) {
+        const long long nr = std::min(chunk, N - r0);
+        RUN(kbegin("k:logits_gemm"));
+        gemm(HO.rowslice(r0, nr), 0, Emb, 0, logits, nr, V, D, scale, nullptr, 0);
+        RUN(kend());
+        RUN(kbegin("k:softmax_ce"));
+        if (logits.h)
+            RUN(launch_ce_bf16(logits.h, V, dp.labels + r0, nr, V, 1.0f / (float)n_glob, train, loss_samp + r0, err_samp + r0,
+                               pred + r0, d_stats, s));
+        else
+            RUN(launch_ce_f32(logits.f, V, dp.labels + r0, nr, V, 1.0f / (float)n_glob, train, loss_samp + r0, err_samp + r0,
+                              pred + r0, d_stats, s));
+        RUN(kend());
+        if (train) {
+            // dE (dense part) += D^-1/2 * dlogits^T . ho ;  dho = D^-1/2 * dlogits . E
+            RUN(kbegin("k:logits_wgrad"));
+            gemm(logits, 1, HO.rowslice(r0, nr), 1, gE, V, D, nr, scale, nullptr, 1);
+            RUN(kend());
+            RUN(kbegin("k:logits_dgrad"));
+            gemm(logits, 0, Emb, 1, dHO.rowslice(r0, nr), nr, D, V, scale, nullptr, 0);
+            RUN(kend());
+        }
+    }
+    phase("logits_ce");
+    if (!train) return;
+
+    // ---------------- backward: out affine
+    gemm(decY[L], 1, dHO, 1, gmat("decode/out/kernel"), D, D, N, 1.f, nullptr, 1);
+    colsum(dHO, N, D, gptr("decode/out/bias"));
+    Mat dY = f32(N, D);   // H == D (model.py:160: the decoder GRUs are dim_emb wide)
+    gemm(dHO, 0, pmat("decode/out/kernel"), 0, dY, N, D, D, 1.f, nullptr, 0);
+    allreduce_bucket(bucket_lo, pinfo("decode/out/bias").off + align_up(D, 64));
+    bucket_lo = pinfo("decode/out/bias").off + align_up(D, 64);
+
+    // ---------------- backward: decoder GRUs (BPTT), dh0 of all layers sums into d ex(z)
+    Mat dGX = act(N, 3 * H), dGH = act(N, 3 * H), HP = act(N, H);
+    Mat dYn = f32(N, D);
+    Mat dhx_sorted = f32(b, H);
+    RUN(CUDA_CHECK(cudaMemsetAsync(dhx_sorted.f, 0, sizeof(float) * b * H, s)));
+    for (int j = L - 1; j >= 0; --j) {
+        const std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
+        GruBwdArgs a;
+        a.dhs = dY.f; a.ld_dhs = dY.ld;
+        a.hs_f = decY[j + 1].f; a.hs_h = decY[j + 1].h; a.ld_hs = H;
+        a.h0 = hx_sorted.f;
+        a.cache = decCache[j];
+        a.R_f = p + pinfo(pre + "R").off;
+        a.R_h = ph ? ph + pinfo(pre + "R").off : nullptr;
+        a.dgx_f = dGX.f; a.dgx_h = dGX.h; a.dgh_f = dGH.f; a.dgh_h = dGH.h; a.ld_dg = 3 * H;
+        a.hp_f = HP.f; a.hp_h = HP.h; a.ld_hp = H;
+        a.dh0 = dhx_sorted.f;
+        a.reverse = 0;
+        gru_bwd(&a, 1, Dp, dp.dec_off, dp.dec_nact);
+        gemm(dGX, 1, decY[j], 1, gmat(pre + "W"), 3 * H, D, N, 1.f, nullptr, 1);
+        gemm(dGH, 1, HP, 1, gmat(pre + "R"), 3 * H, H, N, 1.f, nullptr, 1);
+        colsum(dGX, N, 3 * H, gptr(pre + "bW"));
+        colsum(dGH, N, 3 * H, gptr(pre + "bR"));
+        gemm(dGX, 0, pmat(pre + "W"), 1, dYn, N, D, 3 * H, 1.f, nullptr, 0);
+        std::swap(dY, dYn);
+        const size_t end = pinfo(pre + "bR").off + align_up(3 * H, 64);
+        allreduce_bucket(bucket_lo, end);
+        bucket_lo = end;
+    }
+    // d emb_tgt -> IndexedSlices part of dE (model.py:111)
+    RUN(launch_embed_scatter_add(dp.ids_lead, N, dY.f, D, D, gE.f, s));
+    phase("dec_bwd");
+
+    // ---------------- backward: latent
+    Mat dhx = both(b, D);
+    RUN(launch_row_gather(dhx_sorted.f, nullptr, H, nullptr, dhx.f, dhx.h, D, dp.dec_perm, b, H, s));
+    gemm(z, 1, dhx, 1, gmat("latent/ex/kernel"), R, D, b, 1.f, nullptr, 1);
+    colsum(dhx, b, D, gptr("latent/ex/bias"));
+    Mat dz = f32(b, R);
+    gemm(dhx, 0, pmat("latent/ex/kernel"), 0, dz, b, R, D, 1.f, nullptr, 0);
+    Mat dmulv = both(b, 2 * R);
+    RUN(launch_latent_bwd(dz.f, mulv.f, eps_used, b, R, 1, anneal / ((float)b_glob * (float)R), dmulv.f, dmulv.h, s));
+    gemm(henc, 1, dmulv.colslice(0, R), 1, gmat("latent/mu/kernel"), 2 * H, R, b, 1.f, nullptr, 1);
+    gemm(henc, 1, dmulv.colslice(R, R), 1, gmat("latent/lv/kernel"), 2 * H, R, b, 1.f, nullptr, 1);
+    {
+        Mat a_mu(dmulv.f, nullptr, b, R, 2 * R), a_lv(dmulv.f + R, nullptr, b, R, 2 * R);
+        colsum(a_mu, b, R, gptr("latent/mu/bias"));
+        colsum(a_lv, b, R, gptr("latent/lv/bias"));
+    }
+    Mat dhenc = f32(b, 2 * H);
+    gemm(dmulv.colslice(0, R), 0, pmat("latent/mu/kernel"), 0, dhenc, b, 2 * H, R, 1.f, nullptr, 0);
+    gemm(dmulv.colslice(R, R), 0, pmat("latent/lv/kernel"), 0, dhenc, b, 2 * H, R, 1.f, nullptr, 1);
+    {
+        const size_t end = pinfo("latent/lv/bias").off + align_up(R, 64);
+        allreduce_bucket(bucket_lo, end);
+        bucket_lo = end;
+    }
+    phase("latent_bwd");
+
+    // ---------------- backward: encoder (gather_nd adjoint, then BPTT through 3 x 2 GRUs)
+    Mat dHS = f32(S, 2 * H), dHSn = f32(S, 2 * H);
+    RUN(CUDA_CHECK(cudaMemsetAsync(dHS.f, 0, sizeof(float) * S * 2 * H, s)));
+    RUN(launch_row_scatter(dhenc.f, 2 * H, dHS.f, 2 * H, dp.enc_last, b, 2 * H, 0, s));
+    Mat dGXe = act(S, 6 * H), dGHe = act(S, 6 * H), HPe = act(S, 2 * H);
+    for (int i = L - 1; i >= 0; --i) {
+        const int in = (i == 0) ? D : 2 * H;
+        const std::string pre = "encode/rnn" + std::to_string(i + 1) + "/";
+        GruBwdArgs a[2];
+        for (int d = 0; d < 2; ++d) {
+            const std::string pd = pre + (d ? "bwd/" : "fwd/");
+            a[d].dhs = dHS.f + d * H; a[d].ld_dhs = 2 * H;
+            a[d].hs_f = encX[i + 1].f ? encX[i + 1].f + d * H : nullptr;
+            a[d].hs_h = encX[i + 1].h ? encX[i + 1].h + d * H : nullptr;
+            a[d].ld_hs = 2 * H;
+            a[d].h0 = nullptr;
+            a[d].cache = encCache[2 * i + d];
+            a[d].R_f = p + pinfo(pd + "R").off;
+            a[d].R_h = ph ? ph + pinfo(pd + "R").off : nullptr;
+            a[d].dgx_f = dGXe.f ? dGXe.f + d * 3 * H : nullptr;
+            a[d].dgx_h = dGXe.h ? dGXe.h + d * 3 * H : nullptr;
+            a[d].dgh_f = dGHe.f ? dGHe.f + d * 3 * H : nullptr;
+            a[d].dgh_h = dGHe.h ? dGHe.h + d * 3 * H : nullptr;
+            a[d].ld_dg = 6 * H;
+            a[d].hp_f = HPe.f ? HPe.f + d * H : nullptr;
+            a[d].hp_h = HPe.h ? HPe.h + d * H : nullptr;
+            a[d].ld_hp = 2 * H;
+            a[d].dh0 = nullptr;
+            a[d].reverse = d;
+        }
+        gru_bwd(a, 2, E, dp.enc_off, dp.enc_nact);
+        Mat gW = gmat(pre + "fwd/W");
+        gW.rows = 6 * H;
+        gemm(dGXe, 1, encX[i], 1, gW, 6 * H, in, S, 1.f, nullptr, 1);
+        for (int d = 0; d < 2; ++d) {
+            const std::string pd = pre + (d ? "bwd/" : "fwd/");
+            gemm(dGHe.colslice(d * 3 * H, 3 * H), 1, HPe.colslice(d * H, H), 1, gmat(pd + "R"), 3 * H, H, S, 1.f, nullptr, 1);
+        }
+        colsum(dGXe, S, 6 * H, gptr(pre + "fwd/bW"));   // fwd/bW and bwd/bW are adjacent
+        colsum(dGHe, S, 6 * H, gptr(pre + "fwd/bR"));
+        Mat W = pmat(pre + "fwd/W");
+        W.rows = 6 * H;
+        Mat dX(dHSn.f, nullptr, S, in, in);
+        gemm(dGXe, 0, W, 1, dX, S, in, 6 * H, 1.f, nullptr, 0);
+        std::swap(dHS, dHSn);
+        const size_t end = pinfo(pre + "bwd/bR").off + align_up(3 * H, 64);
+        allreduce_bucket(bucket_lo, end);
+        bucket_lo = end;
+    }
+    // d emb_src -> IndexedSlices part of dE (model.py:112); dHS now holds (S,D) with ld D
+    RUN(launch_embed_scatter_add(dp.ids_src, S, dHS.f, D, D, gE.f, s));
+    phase("enc_bwd");
+    allreduce_bucket(bucket_lo, nflat);
+    bucket_lo = nflat;
+    if (cfg.nranks > 1 && !arena.dry) {
+        NcclApi& n = NcclApi::get();
+        n.check(n.AllReduce(d_stats, d_stats, 4, NcclApi::Float64, NcclApi::Sum, (NcclApi::comm_t)nccl_comm, st[2]),
+                "ncclAllReduce(stats)");
+        CUDA_CHECK(cudaEventRecord(ev_comm, st[2]));
+        CUDA_CHECK(cudaStreamWaitEvent(s, ev_comm, 0));
+    }
+    phase("allreduce_wait");
+
+    // ---------------- Adam, TF-1 form (model.py:189)
+    if (apply_update) {
+        const double t = (double)(step + 1);
+        const float lr_t = (float)((double)lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
+        RUN(kbegin("k:adam"));
+        RUN(launch_adam(p, g, m, v, ph, (long long)nflat, lr_t, 0.9f, 0.999f, 1e-8f, s));
+        RUN(kend());
+    }
+    phase("adam");
+}
+
+// ------------------------------------------------------------------------------------------
+// public steps
+// ------------------------------------------------------------------------------------------
+void Engine::train_step(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt, const uint8_t* keep, const float* eps,
+                        int64_t n_tok_global, int64_t b_global, int64_t row0, bool apply_update, argsim_step_stats* out) {
+    float keepwd, anneal, lr;
+    schedule_f32(step, cfg.accelerate, cfg.learn_rate, &keepwd, &anneal, &lr);
+    DropoutSpec drop;
+    drop.train = 1; drop.keep = keep; drop.rate_keepwd = keepwd; drop.seed = seed; drop.step = (uint64_t)step; drop.row0 = row0;
+    last.train = 1; last.n_tok_global = n_tok_global; last.b_global = b_global; last.row0 = row0;
+    stage(src, tgt, b, Ts, Tt, 1, drop, eps);
+    run_device(2, apply_update);
+    CUDA_CHECK(cudaMemcpyAsync(h_stats, d_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st[0]));
+    CUDA_CHECK(cudaStreamSynchronize(st[0]));
+    CUDA_CHECK(cudaStreamSynchronize(st[2]));
+    collect_timings();
+    const double n_glob = n_tok_global > 0 ? (double)n_tok_global : (double)plan.dec.rows;
+    const double b_glob = b_global > 0 ? (double)b_global : (double)b;
+    if (apply_update) step += 1;
+    if (out) {
+        out->loss_gen = (float)(h_stats[0] / n_glob);
+        out->errt = (float)(h_stats[1] / n_glob);
+        out->loss_kld = (float)(h_stats[2] / (b_glob * R));
+        out->loss = anneal * out->loss_kld + out->loss_gen;
+        out->rate_keepwd = keepwd; out->rate_anneal = anneal; out->rate_update = lr;
+        out->n_tokens = (int64_t)n_glob;
+        out->step = step;
+    }
+}
+
+void Engine::bench_resident(int iters, float* ms) {
+    if (!last.train) throw std::runtime_error("bench_resident: no staged training batch (call argsim_train_step first)");
+    cudaEvent_t a, b2;
+    CUDA_CHECK(cudaEventCreate(&a));
+    CUDA_CHECK(cudaEventCreate(&b2));
+    CUDA_CHECK(cudaStreamSynchronize(st[0]));
+    CUDA_CHECK(cudaEventRecord(a, st[0]));
+    for (int i = 0; i < iters; ++i) {
+        run_device(2, true);
+        step += 1;
+    }
+    CUDA_CHECK(cudaEventRecord(b2, st[0]));
+    CUDA_CHECK(cudaStreamSynchronize(st[0]));
+    CUDA_CHECK(cudaStreamSynchronize(st[2]));
+    float t = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&t, a, b2));
+    collect_timings();
+    *ms = t / (float)std::max(iters, 1);
+    cudaEventDestroy(a); cudaEventDestroy(b2);
+}
+
+void Engine::eval_step(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt, float* errt, float* lgen, int64_t cap,
+                       float* lkld, int64_t* n_rows, int32_t* pred) {
+    DropoutSpec drop;
+    last = StepArgs();
+    stage(src, tgt, b, Ts, Tt, 1, drop, nullptr);
+    const long long N = plan.dec.rows;
+    if (n_rows) *n_rows = N;
+    if ((errt || lgen || pred) && cap < N) throw std::runtime_error("eval_step: per-row output capacity too small");
+    run_device(1, false);
+    size_t need = (size_t)N * 3 + (size_t)b * R;
+    if (need > h_out_cap) {
+        cudaFreeHost(h_out);
+        CUDA_CHECK(cudaMallocHost(&h_out, need * sizeof(float)));
+        h_out_cap = need;
+    }
+    float* hl = h_out; float* he = h_out + N; int* hp = (int*)(h_out + 2 * N); float* hk = h_out + 3 * N;
+    CUDA_CHECK(cudaMemcpyAsync(hl, outp.loss_samp, N * sizeof(float), cudaMemcpyDeviceToHost, st[0]));
+    CUDA_CHECK(cudaMemcpyAsync(he, outp.err_samp, N * sizeof(float), cudaMemcpyDeviceToHost, st[0]));
+    CUDA_CHECK(cudaMemcpyAsync(hp, outp.pred, N * sizeof(int), cudaMemcpyDeviceToHost, st[0]));
+    CUDA_CHECK(cudaMemcpyAsync(hk, outp.kld_samp, (size_t)b * R * sizeof(float), cudaMemcpyDeviceToHost, st[0]));
+    CUDA_CHECK(cudaStreamSynchronize(st[0]));
+    collect_timings();
+    // back to the reference's boolean_mask order
+    for (long long r = 0; r < N; ++r) {
+        const long long q = plan.ref_row[r];
+        if (lgen) lgen[q] = hl[r];
+        if (errt) errt[q] = he[r];
+        if (pred) pred[q] = hp[r];
+    }
+    if (lkld) memcpy(lkld, hk, (size_t)b * R * sizeof(float));
+}
+
+void Engine::embed(const int32_t* src, int b, int T, float* mu_out) {
+    DropoutSpec drop;
+    last = StepArgs();
+    stage(src, nullptr, b, T, 0, 0, drop, nullptr);
+    run_device(0, false);
+    // mulv is (b, 2R) with only the mu half written
+    CUDA_CHECK(cudaMemcpy2DAsync(mu_out, (size_t)R * sizeof(float), outp.mulv, (size_t)2 * R * sizeof(float),
+                                 (size_t)R * sizeof(float), b, cudaMemcpyDeviceToHost, st[0]));
+    CUDA_CHECK(cudaStreamSynchronize(st[0]));
+    collect_timings();
+}
+
+// decode(), model.py:204-219: fp32 SIMT path (host-driven single steps, batch <= a few hundred)
+void Engine::decode_init(const float* z, int b, float* state) {
+    float *dz, *dh;
+    CUDA_CHECK(cudaMalloc(&dz, sizeof(float) * b * R));
+    CUDA_CHECK(cudaMalloc(&dh, sizeof(float) * b * H));
+    CUDA_CHECK(cudaMemcpy(dz, z, sizeof(float) * b * R, cudaMemcpyHostToDevice));
+    const ParamInfo& k = pinfo("latent/ex/kernel");
+    gemm_simt(dz, R, 0, p + k.off, D, 1, dh, H, b, D, R, 1.f, p + pinfo("latent/ex/bias").off, 0, nullptr, st[0]);
+    for (int l = 0; l < L; ++l)
+        CUDA_CHECK(cudaMemcpyAsync(state + (size_t)l * b * H, dh, sizeof(float) * b * H, cudaMemcpyDeviceToHost, st[0]));
+    CUDA_CHECK(cudaStreamSynchronize(st[0]));
+    cudaFree(dz); cudaFree(dh);
+}
+
+void Engine::decode_step(const int32_t* lead, int b, float* state, int32_t* pred) {
+    for (int i = 0; i < b; ++i)
+        if (lead[i] < 0 || lead[i] >= V) throw std::runtime_error("decode_step: token id out of range");
+    cudaStream_t s = st[0];
+    int* dl; float *dst, *x, *gx, *gh, *ho, *lg; int* dpred;
+    CUDA_CHECK(cudaMalloc(&dl, sizeof(int) * b));
+    CUDA_CHECK(cudaMalloc(&dpred, sizeof(int) * b));
+    CUDA_CHECK(cudaMalloc(&dst, sizeof(float) * L * b * H));
+    CUDA_CHECK(cudaMalloc(&x, sizeof(float) * b * D));
+    CUDA_CHECK(cudaMalloc(&gx, sizeof(float) * b * 3 * H));
+    CUDA_CHECK(cudaMalloc(&gh, sizeof(float) * b * 3 * H));
+    CUDA_CHECK(cudaMalloc(&ho, sizeof(float) * b * D));
+    CUDA_CHECK(cudaMalloc(&lg, sizeof(float) * b * V));
+    CUDA_CHECK(cudaMemcpyAsync(dl, lead, sizeof(int) * b, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(dst, state, sizeof(float) * L * b * H, cudaMemcpyHostToDevice, s));
+    launch_embed_gather_f32(dl, b, p + pinfo("embed/embedding").off, D, x, s);
+    const float* in = x;
+    for (int l = 0; l < L; ++l) {
+        const std::string pre = "decode/rnn/l" + std::to_string(l) + "/";
+        gemm_simt(in, D, 0, p + pinfo(pre + "W").off, D, 0, gx, 3 * H, b, 3 * H, D, 1.f, p + pinfo(pre + "bW").off, 0, nullptr, s);
+        float* stl = dst + (size_t)l * b * H;
+        gru_generic_cell(gx, 3 * H, p + pinfo(pre + "R").off, p + pinfo(pre + "bR").off, stl, gh, b, H, s);
+        in = stl;
+    }
+    gemm_simt(in, H, 0, p + pinfo("decode/out/kernel").off, D, 1, ho, D, b, D, D, 1.f, p + pinfo("decode/out/bias").off, 0, nullptr, s);
+    gemm_simt(ho, D, 0, p + pinfo("embed/embedding").off, D, 0, lg, V, b, V, D, 1.0f / sqrtf((float)D), nullptr, 0, nullptr, s);
+    launch_ce_f32(lg, V, nullptr, b, V, 0.f, 0, nullptr, nullptr, dpred, d_stats, s);
+    CUDA_CHECK(cudaMemcpyAsync(pred, dpred, sizeof(int) * b, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(state, dst, sizeof(float) * L * b * H, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    cudaFree(dl); cudaFree(dpred); cudaFree(dst); cudaFree(x); cudaFree(gx); cudaFree(gh); cudaFree(ho); cudaFree(lg);
+}
+
+// ------------------------------------------------------------------------------------------
+// checkpoint container (tf.train.Saver stand-in, train.py:92-96,121): params + Adam slots + step
+// ------------------------------------------------------------------------------------------
+void Engine::save(const char* path) {
+    FILE* f = fopen(path, "wb");
+    if (!f) throw std::runtime_error(std::string("cannot open for writing: ") + path);
+    std::vector<float> hp(nflat), hm(nflat), hv(nflat);
+    CUDA_CHECK(cudaMemcpy(hp.data(), p, nflat * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(hm.data(), m, nflat * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_CHECK(cudaMemcpy(hv.data(), v, nflat * sizeof(float), cudaMemcpyDeviceToHost));
+    const char magic[8] = {'A', 'R', 'G', 'S', 'I', 'M', '0', '1'};
+    fwrite(magic, 1, 8, f);
+    int64_t hdr[2] = {step, (int64_t)params.size()};
+    fwrite(hdr, sizeof(int64_t), 2, f);
+    for (const ParamInfo& pi : params) {
+        int32_t nl = (int32_t)pi.name.size();
+        fwrite(&nl, 4, 1, f);
+        fwrite(pi.name.data(), 1, nl, f);
+        int64_t meta[3] = {pi.rank, pi.shape[0], pi.shape[1]};
+        fwrite(meta, sizeof(int64_t), 3, f);
+        fwrite(hp.data() + pi.off, sizeof(float), pi.n, f);
+        fwrite(hm.data() + pi.off, sizeof(float), pi.n, f);
+        fwrite(hv.data() + pi.off, sizeof(float), pi.n, f);
+    }
+    if (fclose(f) != 0) throw std::runtime_error("write failed");
+}
+
+void Engine::load(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) throw std::runtime_error(std::string("cannot open: ") + path);
+    char magic[8];
+    int64_t hdr[2];
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "ARGSIM01", 8) || fread(hdr, sizeof(int64_t), 2, f) != 2) {
+        fclose(f);
+        throw std::runtime_error("not an argsim_b200 checkpoint");
+    }
+    std::vector<float> hp(nflat, 0.f), hm(nflat, 0.f), hv(nflat, 0.f);
+    for (int64_t k = 0; k < hdr[1]; ++k) {
+        int32_t nl;
+        if (fread(&nl, 4, 1, f) != 1 || nl <= 0 || nl > 4096) { fclose(f); throw std::runtime_error("corrupt checkpoint"); }
+        std::string name(nl, 0);
+        int64_t meta[3];
+        if (fread(&name[0], 1, nl, f) != (size_t)nl || fread(meta, sizeof(int64_t), 3, f) != 3) { fclose(f); throw std::runtime_error("corrupt checkpoint"); }
+        auto it = pindex.find(name);
+        if (it == pindex.end()) { fclose(f); throw std::runtime_error("checkpoint has unknown tensor " + name); }
+        const ParamInfo& pi = params[it->second];
+        if (meta[0] != pi.rank || meta[1] != pi.shape[0] || meta[2] != pi.shape[1]) { fclose(f); throw std::runtime_error("shape mismatch for " + name); }
+        if (fread(hp.data() + pi.off, sizeof(float), pi.n, f) != pi.n || fread(hm.data() + pi.off, sizeof(float), pi.n, f) != pi.n ||
+            fread(hv.data() + pi.off, sizeof(float), pi.n, f) != pi.n) { fclose(f); throw std::runtime_error("truncated checkpoint"); }
+    }
+    fclose(f);
+    CUDA_CHECK(cudaMemcpy(p, hp.data(), nflat * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(m, hm.data(), nflat * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(v, hv.data(), nflat * sizeof(float), cudaMemcpyHostToDevice));
+    refresh_shadow(0, nflat);
+    CUDA_CHECK(cudaStreamSynchronize(st[0]));
+    step = hdr[0];
+}

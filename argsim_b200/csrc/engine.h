@@ -1,0 +1,155 @@
+// engine.h -- the sequence-VAE step (src/model.py:75-189) as a device program over packed,
+// length-sorted rows.  Owns parameters, Adam slots, the activation arena, streams and the
+// (optional) NCCL communicator.  The C ABI in capi.cu is a thin shell around this class.
+#pragma once
+#include "../../include/argsim_b200.h"
+#include "kernels.h"
+#include "plan.h"
+#include <map>
+#include <string>
+#include <vector>
+
+struct ParamInfo {
+    std::string name;
+    int rank;
+    int64_t shape[2];
+    size_t off;   // element offset in the flat buffers
+    size_t n;
+};
+
+class Arena {
+public:
+    char* base = nullptr;
+    size_t cap = 0, used = 0, high = 0;
+    bool dry = false;
+    void reset(bool dry_) { used = 0; dry = dry_; }
+    void* alloc(size_t bytes) {
+        size_t o = (used + 255) & ~size_t(255);
+        used = o + bytes;
+        if (used > high) high = used;
+        if (dry) return (void*)(uintptr_t)(o + 256);  // never dereferenced
+        if (used > cap) throw std::runtime_error("activation arena overflow (internal error)");
+        return base + o;
+    }
+};
+
+struct KTimer {
+    std::string name;
+    cudaEvent_t a, b;
+};
+
+class Engine {
+public:
+    explicit Engine(const argsim_config& c);
+    ~Engine();
+
+    argsim_config cfg;
+    int V, D, R, L, H;
+    bool is_bf16;    // precision mode
+    bool use_tc;     // tcgen05 GEMMs
+    bool use_mma;    // persistent GRU kernels
+    std::string err;
+
+    std::vector<ParamInfo> params;
+    std::map<std::string, int> pindex;
+    size_t nflat = 0;
+    float *p = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
+    bf16* ph = nullptr;
+    int64_t step = 0;
+    uint64_t seed = 0;
+
+    void init_params(uint64_t seed);
+    void set_param(const std::string& name, const float* src);
+    void get_flat(const float* flat, const std::string& name, float* dst);
+    void set_flat(float* flat, const std::string& name, const float* src);
+    void refresh_shadow(size_t off, size_t n);
+
+    // --- steps (host buffers in/out, blocking) ---
+    void train_step(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt, const uint8_t* keep, const float* eps,
+                    int64_t n_tok_global, int64_t b_global, int64_t row0, bool apply_update, argsim_step_stats* out);
+    void eval_step(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt, float* errt, float* lgen, int64_t cap,
+                   float* lkld, int64_t* n_rows, int32_t* pred);
+    void embed(const int32_t* src, int b, int T, float* mu_out);
+    void decode_init(const float* z, int b, float* state);
+    void decode_step(const int32_t* lead, int b, float* state, int32_t* pred);
+    void bench_resident(int iters, float* ms);
+    void save(const char* path);
+    void load(const char* path);
+
+    std::vector<std::string> tnames;
+    std::vector<float> tms;
+    long long launches0 = 0;
+
+private:
+    cudaStream_t st[3] = {nullptr, nullptr, nullptr};  // main, second GRU direction, comm
+    cudaEvent_t ev_bucket = nullptr, ev_comm = nullptr;
+    Arena arena;
+    GruMmaCtx* mma = nullptr;
+    void* nccl_comm = nullptr;
+
+    // staged plan
+    BatchPlan plan;
+    int* h_stage = nullptr;  // pinned
+    int* d_stage = nullptr;
+    size_t stage_cap = 0;
+    struct DevPlan {
+        int *ids_src, *ids_lead, *labels, *enc_last, *dec_perm, *enc_off, *enc_nact, *dec_off, *dec_nact;
+    } dp{};
+    float* d_eps_in = nullptr;  // injected eps staging (b,R)
+    size_t eps_cap = 0;
+    bool have_eps = false;
+    double* d_stats = nullptr;  // 4 doubles
+    double* h_stats = nullptr;  // pinned
+    float* h_out = nullptr;     // pinned scratch for per-row outputs
+    size_t h_out_cap = 0;
+
+    // last staged step parameters (bench_resident replays them)
+    struct StepArgs {
+        int train = 0;
+        int64_t n_tok_global = 0, b_global = 0, row0 = 0;
+    } last;
+
+    // phase timing
+    std::vector<cudaEvent_t> pev;
+    std::vector<std::string> pnames;
+    size_t pcount = 0;
+    void phase(const char* name);
+    std::vector<KTimer> ktimers;
+    size_t kcount = 0;
+    void kbegin(const char* name);
+    void kend();
+    void collect_timings();
+
+    Mat pmat(const std::string& name);
+    const ParamInfo& pinfo(const std::string& name) const;
+    float* gptr(const std::string& name) { return g + pinfo(name).off; }
+    Mat gmat(const std::string& name);
+
+    void stage(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt, int need_dec, const DropoutSpec& drop,
+               const float* eps);
+    // device program; mode: 0 = embed (mu only), 1 = valid, 2 = train(+backward)
+    struct Out {
+        float* mulv = nullptr;       // (b,2R)
+        float* kld_samp = nullptr;   // (b,R)
+        float* loss_samp = nullptr;  // (N)
+        float* err_samp = nullptr;
+        int* pred = nullptr;
+    } outp;
+    void run_device(int mode, bool apply_update);
+    void ensure_arena(int mode);
+    void program(int mode, bool apply_update);
+
+    Mat act(long long rows, int cols);    // operand-typed activation (fp32 view or bf16 view by mode)
+    Mat f32(long long rows, int cols);
+    Mat both(long long rows, int cols);
+    void gemm(const Mat& A, int a_mn, const Mat& B, int b_mn, const Mat& C, long long M, int N, long long K, float alpha,
+              const float* bias, int accumulate);
+    void colsum(const Mat& A, long long rows, int cols, float* out);
+    void gather_embed(const int* ids, long long n, const Mat& out);
+    void gru_fwd(GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact);
+    void gru_bwd(GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact);
+    void allreduce_bucket(size_t off0, size_t off1);
+    float* gru_work = nullptr;
+    size_t gru_work_cap = 0;
+    size_t bucket_lo = 0;  // grads below this offset are already reduced
+};

@@ -1,0 +1,347 @@
+// gemm_tc.cu -- bf16 x bf16 -> fp32 GEMM on the 5th-generation tensor cores (sm_100a only):
+//   C(M,N) = alpha * A(M,K) . B(N,K)^T (+ bias[N]) (+ C)
+// TMA (cp.async.bulk.tensor, 128-byte swizzle) stages 128x64 / 64x128 operand tiles through a
+// 4-deep shared-memory ring; ONE thread issues tcgen05.mma (M=128, N=128, K=16) into a TMEM
+// accumulator; four epilogue warps read it back with tcgen05.ld and write fp32 and/or bf16.
+// Both operands may be K-major (rows x K, K contiguous) or MN-major (K x rows, rows contiguous:
+// the wgrad / dgrad shapes), selected by the UMMA descriptors -- no transposes in HBM.
+// Split-K (fp32 red.global.add) keeps all 148 SMs busy on the weight-gradient shapes.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane group = warp_id % 4).
+#include "kernels.h"
+#include <cuda.h>
+#include <mutex>
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 128;
+constexpr int NTHREADS = 192;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+bool g_ready = false, g_tried = false;
+int g_num_sms = 148;
+
+// ---------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a pipeline bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SW128)
+// K-major tile  (rows x 64 bf16, 128 B per row)  : SBO = 1024 (8-row group), LBO unused (=1)
+// MN-major tile (64 k-rows x 64 mn, 128 B per k) : SBO = 1024 (8-k group),  LBO = BK*128 (next 64 mn)
+template <int MN_MAJOR>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    const uint64_t lbo = MN_MAJOR ? (uint64_t)((BK * 128) >> 4) : 1ull;
+    const uint64_t sbo = 1024 >> 4;
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6)=1, a=BF16 [7,10)=1, b=BF16 [10,13)=1,
+// a_major bit 15, b_major bit 16, N>>3 at [17,23), M>>4 at [24,29)
+template <int A_MN, int B_MN>
+__device__ __forceinline__ uint32_t make_idesc() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) | ((uint32_t)(BN >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
+}
+
+// epilogue modes
+enum { EPI_STORE = 0, EPI_ACCUM = 1, EPI_ATOMIC = 2 };
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ Cf,
+          bf16* __restrict__ Ch, int ldc, int M, int N, int K, float alpha, const float* __restrict__ bias, int mode,
+          int kb_per_split, int vec_ok) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = base + STAGES * STAGE_BYTES;
+    // barriers: full[STAGES], empty[STAGES], tmem_full ; then the TMEM base-address slot
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int nkb_total = (K + BK - 1) / BK;
+    const int kb0 = blockIdx.z * kb_per_split;
+    const int nkb = min(nkb_total, kb0 + kb_per_split) - kb0;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        if (lane == 0 && nkb > 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+                const int k = (kb0 + i) * BK;
+                if (!A_MN) {
+                    tma_load_2d(sa, &tmA, k, m0, full_bar(s));
+                } else {
+                    tma_load_2d(sa, &tmA, m0, k, full_bar(s));
+                    tma_load_2d(sa + BK * 128, &tmA, m0 + 64, k, full_bar(s));
+                }
+                if (!B_MN) {
+                    tma_load_2d(sb, &tmB, k, n0, full_bar(s));
+                } else {
+                    tma_load_2d(sb, &tmB, n0, k, full_bar(s));
+                    tma_load_2d(sb + BK * 128, &tmB, n0 + 64, k, full_bar(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && nkb > 0) {
+            const uint32_t idesc = make_idesc<A_MN, B_MN>();
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+                for (int k16 = 0; k16 < BK / 16; ++k16) {
+                    const uint64_t da = make_desc<A_MN>(sa + (A_MN ? k16 * 2048 : k16 * 32));
+                    const uint64_t db = make_desc<B_MN>(sb + (B_MN ? k16 * 2048 : k16 * 32));
+                    tc_mma(tmem_base, da, db, idesc, (i > 0 || k16 > 0) ? 1u : 0u);
+                }
+                tc_commit(empty_bar(s));  // smem slot reusable once these MMAs retire
+            }
+            tc_commit(tmem_full_bar);
+        }
+    } else if (nkb > 0) {
+        // ---- epilogue: TMEM -> registers -> global.  thread <-> one accumulator row (TMEM lane)
+        const int lg = warp & 3;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int row = m0 + lg * 32 + lane;
+        const bool add_bias = bias != nullptr && (mode != EPI_ATOMIC || blockIdx.z == 0);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tc_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(c * 32), r);
+            const int col0 = n0 + c * 32;
+            if (row >= M || col0 >= N) continue;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                v[i] = alpha * __uint_as_float(r[i]);
+                if (add_bias && col0 + i < N) v[i] += __ldg(bias + col0 + i);
+            }
+            const long long o = (long long)row * ldc + col0;
+            if (mode == EPI_ATOMIC) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (col0 + i < N) atomicAdd(Cf + o + i, v[i]);
+                continue;
+            }
+            const bool full = vec_ok && (col0 + 32 <= N);
+            if (Cf) {
+                if (full) {
+                    float4* dst = reinterpret_cast<float4*>(Cf + o);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float4 x = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        if (mode == EPI_ACCUM) {
+                            const float4 y = dst[i];
+                            x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+                            v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+                        }
+                        dst[i] = x;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (col0 + i < N) {
+                            if (mode == EPI_ACCUM) v[i] += Cf[o + i];
+                            Cf[o + i] = v[i];
+                        }
+                }
+            }
+            if (Ch) {
+                if (full) {
+                    uint4* dst = reinterpret_cast<uint4*>(Ch + o);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * i], v[8 * i + 1]);
+                        __nv_bfloat162 p1 = __floats2bfloat162_rn(v[8 * i + 2], v[8 * i + 3]);
+                        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * i + 4], v[8 * i + 5]);
+                        __nv_bfloat162 p3 = __floats2bfloat162_rn(v[8 * i + 6], v[8 * i + 7]);
+                        uint4 x;
+                        x.x = *reinterpret_cast<uint32_t*>(&p0); x.y = *reinterpret_cast<uint32_t*>(&p1);
+                        x.z = *reinterpret_cast<uint32_t*>(&p2); x.w = *reinterpret_cast<uint32_t*>(&p3);
+                        dst[i] = x;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (col0 + i < N) Ch[o + i] = __float2bfloat16(v[i]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+void encode_map(CUtensorMap* map, const bf16* ptr, int ld, int mn_major, long long rows_mn, long long K, int tile_mn) {
+    // K-major  : global (rows_mn, K), K contiguous  -> dims {K, rows_mn}, box {64, tile_mn}
+    // MN-major : global (K, rows_mn), rows contiguous -> dims {rows_mn, K}, box {64, 64}
+    cuuint64_t dims[2], strides[1];
+    cuuint32_t box[2], estr[2] = {1, 1};
+    if (!mn_major) {
+        dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows_mn;
+        box[0] = BK; box[1] = (cuuint32_t)tile_mn;
+    } else {
+        dims[0] = (cuuint64_t)rows_mn; dims[1] = (cuuint64_t)K;
+        box[0] = 64; box[1] = BK;
+    }
+    strides[0] = (cuuint64_t)ld * sizeof(bf16);
+    if (((uintptr_t)ptr & 15) || (strides[0] & 15)) throw std::runtime_error("gemm_tc: operand must be 16-byte aligned with ld % 8 == 0");
+    CUresult rc = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)rc));
+}
+
+template <int A_MN, int B_MN>
+void launch(const CUtensorMap& ta, const CUtensorMap& tb, float* Cf, bf16* Ch, int ldc, int M, int N, int K, float alpha,
+            const float* bias, int mode, int kbps, int splits, int vec_ok, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    dim3 grid(cdiv(N, BN), cdiv(M, BM), splits);
+    k_gemm_tc<A_MN, B_MN><<<grid, NTHREADS, SMEM_BYTES, s>>>(ta, tb, Cf, Ch, ldc, M, N, K, alpha, bias, mode, kbps, vec_ok);
+    COUNT_LAUNCH();
+}
+}  // namespace
+
+void gemm_tc_init(int device) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (g_tried) return;
+    g_tried = true;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return;
+    g_num_sms = prop.multiProcessorCount;
+    if (prop.major != 10) return;  // tcgen05 / TMEM exist on sm_100 family only
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess)
+        return;
+    g_encode = (EncodeTiledFn)fn;
+    g_ready = true;
+}
+bool gemm_tc_available() { return g_ready; }
+
+void gemm_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, float* Cf, bf16* Ch, int ldc, int M, int N,
+             int K, float alpha, const float* bias, int accumulate, cudaStream_t s) {
+    if (!g_ready) throw std::runtime_error("gemm_tc: tcgen05 path not initialised");
+    if (M <= 0 || N <= 0) return;
+    if (K <= 0) throw std::runtime_error("gemm_tc: K must be positive");
+    CUtensorMap ta, tb;
+    encode_map(&ta, A, lda, a_mn, M, K, BM);
+    encode_map(&tb, B, ldb, b_mn, N, K, BN);
+    const int tiles = cdiv(N, BN) * cdiv(M, BM);
+    const int nkb = cdiv(K, BK);
+    int splits = 1;
+    if (Cf && !Ch && tiles * 2 <= g_num_sms && nkb >= 8) {
+        splits = std::min(std::min(nkb / 4, cdiv(2 * g_num_sms, tiles)), 64);
+        if (splits < 1) splits = 1;
+    }
+    int kbps = cdiv(nkb, splits);
+    splits = cdiv(nkb, kbps);  // no empty split
+    int mode = accumulate ? EPI_ACCUM : EPI_STORE;
+    if (splits > 1) {
+        if (!accumulate) CUDA_CHECK(cudaMemset2DAsync(Cf, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s));
+        mode = EPI_ATOMIC;
+    }
+    const int vec_ok = (!Cf || (((uintptr_t)Cf & 15) == 0 && ldc % 4 == 0)) && (!Ch || (((uintptr_t)Ch & 15) == 0 && ldc % 8 == 0));
+    if (!a_mn && !b_mn) launch<0, 0>(ta, tb, Cf, Ch, ldc, M, N, K, alpha, bias, mode, kbps, splits, vec_ok, s);
+    else if (!a_mn && b_mn) launch<0, 1>(ta, tb, Cf, Ch, ldc, M, N, K, alpha, bias, mode, kbps, splits, vec_ok, s);
+    else if (a_mn && !b_mn) launch<1, 0>(ta, tb, Cf, Ch, ldc, M, N, K, alpha, bias, mode, kbps, splits, vec_ok, s);
+    else launch<1, 1>(ta, tb, Cf, Ch, ldc, M, N, K, alpha, bias, mode, kbps, splits, vec_ok, s);
+}

@@ -1,0 +1,181 @@
+// gru_generic.cu -- reference-order GRU recurrence, one fp32 GEMM + one gate kernel per time step.
+// Used by the FP32_VALIDATE precision mode (parity runs against the fp64/fp32 oracle at 1e-3),
+// for hidden sizes the persistent kernel does not cover, and as the on-device checker of
+// gru_mma.cu.  Cell = cuDNN form (src/model.py:15):
+//   r = sig(gx_r + R_r h + bR_r)   u = sig(gx_u + R_u h + bR_u)
+//   n = tanh(gx_n + r * (R_n h + bR_n))   h' = (1-u) n + u h
+#include "kernels.h"
+#include "plan.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256) k_gate_fwd(const float* __restrict__ gx, int ld_gx, const float* __restrict__ gh,
+                                                  const float* __restrict__ bR, float* __restrict__ state,
+                                                  float* __restrict__ hs_f, bf16* __restrict__ hs_h, int ld_hs,
+                                                  float* __restrict__ cache, int na, int H) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= na * H) return;
+    const int j = idx / H, u = idx - j * H;
+    const float* g = gx + (long long)j * ld_gx;
+    const float* q3 = gh + (long long)j * 3 * H;
+    const float r = 1.f / (1.f + expf(-(g[u] + q3[u] + bR[u])));
+    const float z = 1.f / (1.f + expf(-(g[H + u] + q3[H + u] + bR[H + u])));
+    const float q = q3[2 * H + u] + bR[2 * H + u];
+    const float n = tanhf(g[2 * H + u] + r * q);
+    const float hp = state[(long long)j * H + u];
+    const float h = (1.f - z) * n + z * hp;
+    state[(long long)j * H + u] = h;
+    if (hs_f) hs_f[(long long)j * ld_hs + u] = h;
+    if (hs_h) hs_h[(long long)j * ld_hs + u] = __float2bfloat16(h);
+    if (cache) {
+        float* c = cache + (long long)j * 4 * H;
+        c[u] = r; c[H + u] = z; c[2 * H + u] = n; c[3 * H + u] = q;
+    }
+}
+
+// hp_src_* point at the row of sequence 0 of the previous step (or null -> h0 / zeros); nprev rows valid
+__global__ void __launch_bounds__(256) k_gate_bwd(const float* __restrict__ dhs, int ld_dhs, const float* __restrict__ cache,
+                                                  const float* __restrict__ hp_f, const bf16* __restrict__ hp_h, int ld_hp_src,
+                                                  int nprev, const float* __restrict__ h0, float* __restrict__ carry,
+                                                  float* __restrict__ tmp_dgh, float* __restrict__ dgx_f,
+                                                  bf16* __restrict__ dgx_h, float* __restrict__ dgh_f, bf16* __restrict__ dgh_h,
+                                                  int ld_dg, float* __restrict__ hpo_f, bf16* __restrict__ hpo_h, int ld_hpo,
+                                                  int na, int H) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= na * H) return;
+    const int j = idx / H, u = idx - j * H;
+    const float* c = cache + (long long)j * 4 * H;
+    const float r = c[u], z = c[H + u], n = c[2 * H + u], q = c[3 * H + u];
+    float hp = 0.f;
+    if (j < nprev) {
+        if (hp_f) hp = hp_f[(long long)j * ld_hp_src + u];
+        else if (hp_h) hp = __bfloat162float(hp_h[(long long)j * ld_hp_src + u]);
+        else if (h0) hp = h0[(long long)j * H + u];
+    }
+    const float d = carry[(long long)j * H + u] + dhs[(long long)j * ld_dhs + u];
+    const float dn = d * (1.f - z) * (1.f - n * n);
+    const float du = d * (hp - n) * z * (1.f - z);
+    const float dr = dn * q * r * (1.f - r);
+    const float dnr = dn * r;
+    carry[(long long)j * H + u] = d * z;
+    float* t3 = tmp_dgh + (long long)j * 3 * H;
+    t3[u] = dr; t3[H + u] = du; t3[2 * H + u] = dnr;
+    const long long o = (long long)j * ld_dg;
+    if (dgx_f) { dgx_f[o + u] = dr; dgx_f[o + H + u] = du; dgx_f[o + 2 * H + u] = dn; }
+    if (dgx_h) { dgx_h[o + u] = __float2bfloat16(dr); dgx_h[o + H + u] = __float2bfloat16(du); dgx_h[o + 2 * H + u] = __float2bfloat16(dn); }
+    if (dgh_f) { dgh_f[o + u] = dr; dgh_f[o + H + u] = du; dgh_f[o + 2 * H + u] = dnr; }
+    if (dgh_h) { dgh_h[o + u] = __float2bfloat16(dr); dgh_h[o + H + u] = __float2bfloat16(du); dgh_h[o + 2 * H + u] = __float2bfloat16(dnr); }
+    if (hpo_f) hpo_f[(long long)j * ld_hpo + u] = hp;
+    if (hpo_h) hpo_h[(long long)j * ld_hpo + u] = __float2bfloat16(hp);
+}
+
+__global__ void __launch_bounds__(256) k_axpy(float* __restrict__ y, const float* __restrict__ x, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
+
+cudaEvent_t g_ev[4];
+bool g_ev_init = false;
+void fork_join_init() {
+    if (g_ev_init) return;
+    for (auto& e : g_ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    g_ev_init = true;
+}
+}  // namespace
+
+size_t gru_generic_work_floats(int b, int H) { return (size_t)b * H * 4; }
+
+void gru_generic_fwd(const GruFwdArgs* dirs, int ndir, const SeqPlan& P, int H, float* work, cudaStream_t* streams) {
+    fork_join_init();
+    const size_t wstride = gru_generic_work_floats(P.b, H);
+    if (ndir > 1) {
+        CUDA_CHECK(cudaEventRecord(g_ev[0], streams[0]));
+        for (int d = 1; d < ndir; ++d) CUDA_CHECK(cudaStreamWaitEvent(streams[d], g_ev[0], 0));
+    }
+    for (int d = 0; d < ndir; ++d) {
+        const GruFwdArgs& a = dirs[d];
+        cudaStream_t s = streams[d];
+        float* state = work + d * wstride;
+        float* gh = state + (size_t)P.b * H;
+        if (a.h0 && !a.reverse)
+            CUDA_CHECK(cudaMemcpyAsync(state, a.h0, sizeof(float) * P.b * H, cudaMemcpyDeviceToDevice, s));
+        else
+            CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(float) * P.b * H, s));
+        for (int k = 0; k < P.Tmax; ++k) {
+            const int t = a.reverse ? P.Tmax - 1 - k : k;
+            const int na = P.nact[t];
+            const long long r0 = P.off[t];
+            gemm_simt(state, H, 0, a.R_f, H, 0, gh, 3 * H, na, 3 * H, H, 1.f, nullptr, 0, nullptr, s);
+            k_gate_fwd<<<cdiv((long long)na * H, 256), 256, 0, s>>>(
+                a.gx + r0 * a.ld_gx, a.ld_gx, gh, a.bR, state, a.hs_f ? a.hs_f + r0 * a.ld_hs : nullptr,
+                a.hs_h ? a.hs_h + r0 * a.ld_hs : nullptr, a.ld_hs, a.cache ? a.cache + r0 * 4 * H : nullptr, na, H);
+            COUNT_LAUNCH();
+        }
+    }
+    if (ndir > 1) {
+        for (int d = 1; d < ndir; ++d) {
+            CUDA_CHECK(cudaEventRecord(g_ev[d], streams[d]));
+            CUDA_CHECK(cudaStreamWaitEvent(streams[0], g_ev[d], 0));
+        }
+    }
+}
+
+void gru_generic_bwd(const GruBwdArgs* dirs, int ndir, const SeqPlan& P, int H, float* work, cudaStream_t* streams) {
+    fork_join_init();
+    const size_t wstride = gru_generic_work_floats(P.b, H);
+    if (ndir > 1) {
+        CUDA_CHECK(cudaEventRecord(g_ev[0], streams[0]));
+        for (int d = 1; d < ndir; ++d) CUDA_CHECK(cudaStreamWaitEvent(streams[d], g_ev[0], 0));
+    }
+    for (int d = 0; d < ndir; ++d) {
+        const GruBwdArgs& a = dirs[d];
+        cudaStream_t s = streams[d];
+        float* carry = work + d * wstride;
+        float* tmp = carry + (size_t)P.b * H;
+        CUDA_CHECK(cudaMemsetAsync(carry, 0, sizeof(float) * P.b * H, s));
+        for (int k = P.Tmax - 1; k >= 0; --k) {  // reverse of the forward processing order
+            const int t = a.reverse ? P.Tmax - 1 - k : k;
+            const int na = P.nact[t];
+            const long long r0 = P.off[t];
+            // previous (in forward processing order) step's outputs = h_prev of this step
+            const float* hp_f = nullptr;
+            const bf16* hp_h = nullptr;
+            const float* h0 = nullptr;
+            int nprev = 0;
+            const int tp = a.reverse ? t + 1 : t - 1;
+            if (tp >= 0 && tp < P.Tmax) {
+                nprev = std::min(na, P.nact[tp]);
+                if (a.hs_f) hp_f = a.hs_f + (long long)P.off[tp] * a.ld_hs;
+                else hp_h = a.hs_h + (long long)P.off[tp] * a.ld_hs;
+            } else if (!a.reverse && a.h0) {
+                h0 = a.h0;
+                nprev = na;
+            }
+            k_gate_bwd<<<cdiv((long long)na * H, 256), 256, 0, s>>>(
+                a.dhs + r0 * a.ld_dhs, a.ld_dhs, a.cache + r0 * 4 * H, hp_f, hp_h, a.ld_hs, nprev, h0, carry, tmp,
+                a.dgx_f ? a.dgx_f + r0 * a.ld_dg : nullptr, a.dgx_h ? a.dgx_h + r0 * a.ld_dg : nullptr,
+                a.dgh_f ? a.dgh_f + r0 * a.ld_dg : nullptr, a.dgh_h ? a.dgh_h + r0 * a.ld_dg : nullptr, a.ld_dg,
+                a.hp_f ? a.hp_f + r0 * a.ld_hp : nullptr, a.hp_h ? a.hp_h + r0 * a.ld_hp : nullptr, a.ld_hp, na, H);
+            COUNT_LAUNCH();
+            // carry[0:na] += dgh[0:na] . R        (R is (3H,H): stored (K, N) -> b_mn = 1)
+            gemm_simt(tmp, 3 * H, 0, a.R_f, H, 1, carry, H, na, H, 3 * H, 1.f, nullptr, 1, nullptr, s);
+        }
+        if (a.dh0 && !a.reverse) {
+            k_axpy<<<cdiv((long long)P.b * H, 256), 256, 0, s>>>(a.dh0, carry, (long long)P.b * H);
+            COUNT_LAUNCH();
+        }
+    }
+    if (ndir > 1) {
+        for (int d = 1; d < ndir; ++d) {
+            CUDA_CHECK(cudaEventRecord(g_ev[d], streams[d]));
+            CUDA_CHECK(cudaStreamWaitEvent(streams[0], g_ev[d], 0));
+        }
+    }
+}
+
+void gru_generic_cell(const float* gx, int ld_gx, const float* R, const float* bR, float* state, float* gh_work, int nb,
+                      int H, cudaStream_t s) {
+    gemm_simt(state, H, 0, R, H, 0, gh_work, 3 * H, nb, 3 * H, H, 1.f, nullptr, 0, nullptr, s);
+    k_gate_fwd<<<cdiv((long long)nb * H, 256), 256, 0, s>>>(gx, ld_gx, gh_work, bR, state, nullptr, nullptr, H, nullptr, nb, H);
+    COUNT_LAUNCH();
+}

@@ -65,24 +65,24 @@ void launch_embed_scatter_add(const int* ids, long long n, const float* dx, int 
 // ------------------------------------------------------------------------------------------
 // row gather / scatter (final-state gather model.py:135, decoder state fan-out model.py:159)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_row_gather(const float* __restrict__ in, int ld_in, const int* __restrict__ src_idx,
-                                                    float* __restrict__ out_f, bf16* __restrict__ out_h, int ld_out,
-                                                    const int* __restrict__ dst_idx, int n, int cols) {
+__global__ void __launch_bounds__(256) k_row_gather(const float* __restrict__ in_f, const bf16* __restrict__ in_h, int ld_in,
+                                                    const int* __restrict__ src_idx, float* __restrict__ out_f,
+                                                    bf16* __restrict__ out_h, int ld_out, const int* __restrict__ dst_idx,
+                                                    int n, int cols) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (row >= n) return;
     long long si = src_idx ? src_idx[row] : row, di = dst_idx ? dst_idx[row] : row;
-    const float* src = in + si * ld_in;
     for (int i = lane; i < cols; i += 32) {
-        float v = src[i];
+        float v = in_f ? in_f[si * ld_in + i] : __bfloat162float(in_h[si * ld_in + i]);
         if (out_f) out_f[di * ld_out + i] = v;
         if (out_h) out_h[di * ld_out + i] = __float2bfloat16(v);
     }
 }
-void launch_row_gather(const float* in, int ld_in, const int* src_idx, float* out_f, bf16* out_h, int ld_out,
-                       const int* dst_idx, int n, int cols, cudaStream_t s) {
+void launch_row_gather(const float* in_f, const bf16* in_h, int ld_in, const int* src_idx, float* out_f, bf16* out_h,
+                       int ld_out, const int* dst_idx, int n, int cols, cudaStream_t s) {
     if (n <= 0) return;
-    k_row_gather<<<cdiv(n, 8), 256, 0, s>>>(in, ld_in, src_idx, out_f, out_h, ld_out, dst_idx, n, cols);
+    k_row_gather<<<cdiv(n, 8), 256, 0, s>>>(in_f, in_h, ld_in, src_idx, out_f, out_h, ld_out, dst_idx, n, cols);
     COUNT_LAUNCH();
 }
 __global__ void __launch_bounds__(256) k_row_scatter(const float* __restrict__ in, int ld_in, float* __restrict__ out,
@@ -107,7 +107,7 @@ void launch_row_scatter(const float* in, int ld_in, float* out, int ld_out, cons
 // latent: reparameterisation + KL (model.py:147-156,182-184) and its gradient
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t step, uint32_t row, uint32_t col) {
-    uint32_t c[4] = {row, col >> 2, 1u, (uint32_t)(seed >> 32)};
+    uint32_t c[4] = {row, col >> 2, (uint32_t)PHILOX_STREAM_EPS, (uint32_t)(seed >> 32)};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)step);
     int pair = (col >> 1) & 1;
     float u1 = ((float)(c[2 * pair] >> 8) + 0.5f) * (1.0f / 16777216.0f);
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) k_latent_fwd(const float* __restrict__ mu
                                                     int R, int train, uint64_t seed, uint64_t step, long long row0,
                                                     float* __restrict__ eps_used, float* __restrict__ z_f,
                                                     bf16* __restrict__ z_h, float* __restrict__ kld_samp,
-                                                    float* __restrict__ stats) {
+                                                    double* __restrict__ stats) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     float k = 0.f;
     if (i < (long long)b * R) {
@@ -145,11 +145,11 @@ __global__ void __launch_bounds__(256) k_latent_fwd(const float* __restrict__ mu
     if (threadIdx.x == 0) {
         float t = 0.f;
         for (int w = 0; w < (blockDim.x >> 5); ++w) t += sm[w];
-        atomicAdd(stats + 2, t);
+        atomicAdd(stats + 2, (double)t);
     }
 }
 void launch_latent_fwd(const float* mulv, const float* eps_in, int b, int R, int train, uint64_t seed, uint64_t step,
-                       long long row0, float* eps_used, float* z_f, bf16* z_h, float* kld_samp, float* stats, cudaStream_t s) {
+                       long long row0, float* eps_used, float* z_f, bf16* z_h, float* kld_samp, double* stats, cudaStream_t s) {
     k_latent_fwd<<<cdiv((long long)b * R, 256), 256, 0, s>>>(mulv, eps_in, b, R, train, seed, step, row0, eps_used, z_f, z_h,
                                                              kld_samp, stats);
     COUNT_LAUNCH();
@@ -190,7 +190,7 @@ template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __flo
 template <typename T>
 __global__ void __launch_bounds__(256) k_ce(T* __restrict__ logits, int ld, const int* __restrict__ labels, int V,
                                             float gscale, int write_grad, float* __restrict__ loss_samp,
-                                            float* __restrict__ err_samp, int* __restrict__ pred, float* __restrict__ stats) {
+                                            float* __restrict__ err_samp, int* __restrict__ pred, double* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* row = reinterpret_cast<T*>(smem_raw);
     __shared__ float red_v[8];
@@ -256,8 +256,8 @@ __global__ void __launch_bounds__(256) k_ce(T* __restrict__ logits, int ld, cons
             float err = (mi != lab) ? 1.f : 0.f;
             if (loss_samp) loss_samp[r] = loss;
             if (err_samp) err_samp[r] = err;
-            atomicAdd(stats + 0, loss);
-            atomicAdd(stats + 1, err);
+            atomicAdd(stats + 0, (double)loss);
+            atomicAdd(stats + 1, (double)err);
         }
     }
     if (!write_grad) return;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(256) k_ce(T* __restrict__ logits, int ld, cons
 }
 template <typename T>
 static void launch_ce(T* logits, int ld, const int* labels, long long n, int V, float gscale, int write_grad,
-                      float* loss_samp, float* err_samp, int* pred, float* stats, cudaStream_t s) {
+                      float* loss_samp, float* err_samp, int* pred, double* stats, cudaStream_t s) {
     if (n <= 0) return;
     size_t smem = (size_t)V * sizeof(T);
     static size_t configured = 0;
@@ -298,11 +298,11 @@ static void launch_ce(T* logits, int ld, const int* labels, long long n, int V, 
     COUNT_LAUNCH();
 }
 void launch_ce_f32(float* logits, int ld, const int* labels, long long n, int V, float gscale, int write_grad,
-                   float* loss_samp, float* err_samp, int* pred, float* stats, cudaStream_t s) {
+                   float* loss_samp, float* err_samp, int* pred, double* stats, cudaStream_t s) {
     launch_ce<float>(logits, ld, labels, n, V, gscale, write_grad, loss_samp, err_samp, pred, stats, s);
 }
 void launch_ce_bf16(bf16* logits, int ld, const int* labels, long long n, int V, float gscale, int write_grad,
-                    float* loss_samp, float* err_samp, int* pred, float* stats, cudaStream_t s) {
+                    float* loss_samp, float* err_samp, int* pred, double* stats, cudaStream_t s) {
     launch_ce<bf16>(logits, ld, labels, n, V, gscale, write_grad, loss_samp, err_samp, pred, stats, s);
 }
 

@@ -9,20 +9,20 @@ void launch_embed_gather_f32(const int* ids, long long n, const float* table, in
 void launch_embed_gather_bf16(const int* ids, long long n, const bf16* table, int D, bf16* out, cudaStream_t s);
 // table_grad[ids[i],:] += dx[i,:]   (A18: IndexedSlices part of dE)
 void launch_embed_scatter_add(const int* ids, long long n, const float* dx, int ld, int D, float* table_grad, cudaStream_t s);
-// generic row gather: out[dst[i] or i, :] = in[src[i] or i, :]; writes fp32 and/or bf16
-void launch_row_gather(const float* in, int ld_in, const int* src_idx, float* out_f, bf16* out_h, int ld_out,
-                       const int* dst_idx, int n, int cols, cudaStream_t s);
+// generic row gather: out[dst[i] or i, :] = in[src[i] or i, :]; reads fp32 or bf16, writes fp32 and/or bf16
+void launch_row_gather(const float* in_f, const bf16* in_h, int ld_in, const int* src_idx, float* out_f, bf16* out_h,
+                       int ld_out, const int* dst_idx, int n, int cols, cudaStream_t s);
 // A9/A15: z = mu (+ exp(lv/2)*eps), kld_samp, sum(kld) -> stats[2]
 void launch_latent_fwd(const float* mulv, const float* eps_in, int b, int R, int train, uint64_t seed, uint64_t step,
-                       long long row0, float* eps_used, float* z_f, bf16* z_h, float* kld_samp, float* stats, cudaStream_t s);
+                       long long row0, float* eps_used, float* z_f, bf16* z_h, float* kld_samp, double* stats, cudaStream_t s);
 // A18: dmu = dz + a*mu ; dlv = dz*.5*exp(lv/2)*eps + a*.5*(exp(lv)-1)   (a = anneal/(b_global*R))
 void launch_latent_bwd(const float* dz, const float* mulv, const float* eps, int b, int R, int train, float a,
                        float* dmulv_f, bf16* dmulv_h, cudaStream_t s);
 // A12-A14 + A18: fused softmax cross entropy; logits overwritten by (softmax-onehot)*gscale when write_grad
 void launch_ce_f32(float* logits, int ld, const int* labels, long long n, int V, float gscale, int write_grad,
-                   float* loss_samp, float* err_samp, int* pred, float* stats, cudaStream_t s);
+                   float* loss_samp, float* err_samp, int* pred, double* stats, cudaStream_t s);
 void launch_ce_bf16(bf16* logits, int ld, const int* labels, long long n, int V, float gscale, int write_grad,
-                    float* loss_samp, float* err_samp, int* pred, float* stats, cudaStream_t s);
+                    float* loss_samp, float* err_samp, int* pred, double* stats, cudaStream_t s);
 // A17: TF-form Adam over a flat buffer; optional bf16 shadow
 void launch_adam(float* p, const float* g, float* m, float* v, bf16* shadow, long long n, float lr_t,
                  float b1, float b2, float eps, cudaStream_t s);
@@ -34,6 +34,9 @@ void launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s);
 void launch_row_scatter(const float* in, int ld_in, float* out, int ld_out, const int* dst_idx, int n, int cols,
                         int accumulate, cudaStream_t s);
 void launch_fill(float* p, long long n, float v, cudaStream_t s);
+// one GRU cell step on nb rows (decode(), model.py:204-219): state updated in place
+void gru_generic_cell(const float* gx, int ld_gx, const float* R, const float* bR, float* state, float* gh_work, int nb,
+                      int H, cudaStream_t s);
 
 // ---- gemm_simt.cu / gemm_tc.cu ----------------------------------------------------------
 // C(M,N) = alpha * A(M,K) * B(N,K)^T + bias[N] (+ C when accumulate).
@@ -44,42 +47,56 @@ void gemm_simt(const float* A, int lda, int a_mn, const float* B, int ldb, int b
 void gemm_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, float* Cf, bf16* Ch, int ldc,
              int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s);
 void gemm_tc_init(int device);
+bool gemm_tc_available();
 
-// ---- gru.cu -----------------------------------------------------------------------------
-struct GruSeq {
-    // one recurrence ("direction"): packed rows, sorted batch (descending length)
-    const float* gx;      // (rows, ld_gx) precomputed W x + bW, this direction's 3H columns
+// ---- gru_generic.cu / gru_mma.cu ---------------------------------------------------------
+// One direction-layer of a GRU in cuDNN form (gate order r,u,n; src/model.py:15,118-122,160)
+// over a packed, length-sorted sequence set (plan.h).
+struct GruFwdArgs {
+    const float* gx;      // (rows, ld_gx) fp32: W x + bW for this direction (column offset applied)
     int ld_gx;
-    const float* R;       // (3H,H) fp32
+    const float* R_f;     // (3H,H) fp32 master
+    const bf16* R_h;      // (3H,H) bf16 shadow (bf16 mode) or null
     const float* bR;      // (3H)
-    const float* h0;      // (b,H) or null (zeros)
-    float* hs;            // (rows, ld_hs) output, this direction's H columns
-    bf16* hs_h;           // bf16 twin or null
+    const float* h0;      // (b,H) sorted order, or null = zeros.  Forward directions only.
+    float* hs_f;          // (rows, ld_hs) outputs (column offset applied); either view may be null
+    bf16* hs_h;
     int ld_hs;
     float* cache;         // (rows, 4H): r,u,n,q per row (training) or null
-    int reverse;          // 1: tf.reverse_sequence semantics (encoder bwd direction)
-    float* hT;            // (b,H) final state or null
+    int reverse;          // 1: runs t = Tmax-1 .. 0 (== tf.reverse_sequence o GRU o tf.reverse_sequence)
 };
-struct GruSeqBwd {
-    const float* dhs;     // (rows, ld_dhs) gradient wrt outputs (this direction's columns)
+struct GruBwdArgs {
+    const float* dhs;     // (rows, ld_dhs) gradient wrt outputs (column offset applied)
     int ld_dhs;
-    const float* hs;      // forward outputs
+    const float* hs_f;    // forward outputs (one of the two views)
+    const bf16* hs_h;
     int ld_hs;
     const float* h0;      // or null
-    const float* cache;   // (rows,4H)
-    const float* R;       // (3H,H)
-    float* dgx;           // (rows, ld_dg) out: grad wrt gx
+    const float* cache;   // (rows, 4H)
+    const float* R_f;
+    const bf16* R_h;
+    float* dgx_f;         // (rows, ld_dg) out: [dr,du,dn]      = grad wrt (W x + bW)
     bf16* dgx_h;
-    float* dgh;           // (rows, ld_dg) out: grad wrt (R h + bR)
+    float* dgh_f;         // (rows, ld_dg) out: [dr,du,dn*r]    = grad wrt (R h + bR)
     bf16* dgh_h;
     int ld_dg;
-    float* dh0_acc;       // (b,H) accumulated (+=) gradient wrt h0, or null
+    float* hp_f;          // (rows, ld_hp) out: h_{prev} of every row (operand of the R wgrad)
+    bf16* hp_h;
+    int ld_hp;
+    float* dh0;           // (b,H) += gradient wrt h0 (sorted order), or null
     int reverse;
 };
-// lens (b) descending, off (Tmax+1) prefix offsets of active counts; both on device.
-void launch_gru_fwd(const GruSeq* seqs, int ndir, const int* lens, const int* off, int b, int Tmax, int H,
-                    float* work, unsigned* bar, cudaStream_t s);
-void launch_gru_bwd(const GruSeqBwd* seqs, int ndir, const int* lens, const int* off, int b, int Tmax, int H,
-                    float* work, unsigned* bar, cudaStream_t s);
-size_t gru_work_floats(int b, int H);
-void gru_init(int device);
+struct SeqPlan;
+// generic path: one GEMM + one gate kernel per time step, fp32 (FP32_VALIDATE mode, any H)
+void gru_generic_fwd(const GruFwdArgs* dirs, int ndir, const SeqPlan& P, int H, float* work, cudaStream_t* streams);
+void gru_generic_bwd(const GruBwdArgs* dirs, int ndir, const SeqPlan& P, int H, float* work, cudaStream_t* streams);
+size_t gru_generic_work_floats(int b, int H);   // per direction
+// persistent path (H == 512, bf16 mode): register-stationary weights, LL exchange through L2
+struct GruMmaCtx;
+GruMmaCtx* gru_mma_create(int device);
+void gru_mma_destroy(GruMmaCtx*);
+bool gru_mma_supported(int H);
+void gru_mma_fwd(GruMmaCtx*, const GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
+                 int H, cudaStream_t s);
+void gru_mma_bwd(GruMmaCtx*, const GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
+                 int H, cudaStream_t s);

@@ -1,0 +1,346 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the hot path (BASELINE.json metric: train sequences/sec of the
+ELBO step: forward + backward + Adam) on synthetic IAC-shaped sentencepiece token batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload train|embed]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One rank per GPU.  Weak scaling: every rank owns 64 sequences of a seed-0 global batch of 64*N
+(N=1 is BASELINE configs[1]; N=8 is configs[2], global batch 512), sharded balanced on length.
+`value`  : device-timed (CUDA events inside the library, max over ranks) with the batch resident in HBM.
+`e2e`    : the same K steps through the public C-ABI call with HOST buffers (plan + H2D + step + D2H
+           of the step statistics inside the timed region), host-timed around the blocking calls.
+`--impl reference`: the reference's TF graph cannot run (no TensorFlow; CudnnGRU is GPU-only), so the
+CPU arm is the torch-CPU port of the same graph (oracle/vae_torch.py) on all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(dim_tgt=8192, dim_emb=512, dim_rep=1024, rnn_layers=3, bidirectional=True, bidir_stacked=True,
+           attentive=False, logit_use_embed=True, accelerate=1e-4, learn_rate=1e-3, bos=2, eos=1)
+PER_GPU = 64
+METRIC = 'train sequences/sec (ELBO fwd+bwd+Adam)'
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return dict(hbm=p['hbm_gbs'], tf_burst=p['bf16_tflops'], tf_sust=p['bf16_tflops_sustained'], src='measured')
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src='fallback')
+
+
+class Clocks:
+    """samples nvidia-smi during the timed region (B200_PROFILING.md clocks line)."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith('active') for r in self.rows)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def algo_flops(S, N, b, D=512, R=1024, V=8192, L=3):
+    """forward GEMM flops (2MNK), padding excluded; training = 3x forward."""
+    H = D
+    enc = (2 * 2 * 3 * H * (D + H) + 2 * (L - 1) * 2 * 3 * H * (2 * H + H)) * S
+    dec = (L * 2 * 3 * H * (D + H) + 2 * D * D) * N
+    voc = 2 * D * V * N
+    lat = (2 * 2 * (2 * H) * R + 2 * R * D) * b
+    return dict(enc=enc, dec=dec, voc=voc, lat=lat, fwd=enc + dec + voc + lat, train=3 * (enc + dec + voc + lat),
+                rec_fwd=2 * 3 * H * H * (2 * L * S + L * N))
+
+
+def dist_setup(n):
+    """returns (rank, world, local_rank, torch.distributed or None)"""
+    if n <= 1 and 'RANK' not in os.environ:
+        return 0, 1, 0, None
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', rank))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend='cpu:gloo,cuda:nccl' if torch.cuda.is_available() else 'gloo')
+        return rank, world, local, dist
+    return 0, 1, 0, None
+
+
+def reference_arm(args, rank, world):
+    """torch-CPU port of the reference graph on the host cores; bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    from argsim_b200.synth import synth_batch
+    from oracle import vae_oracle as O
+    from oracle import vae_torch as T
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    full = synth_batch(PER_GPU, 'iac', CFG['dim_tgt'], seed=0)
+    nrow = int(os.environ.get('ARGSIM_REF_ROWS', 8))
+    # bounded sample: the first rows of the C1 batch whose longest row is the batch's longest (keeps s = 512)
+    order = np.argsort(-(full != 1).sum(1), kind='stable')[:nrow]
+    sub = full[np.sort(order)]
+    sub = sub[:, :int((sub != 1).sum(1).max())]
+    P0 = O.init_params(CFG, seed=0, dtype=np.float32)
+    P = T.to_torch(P0, torch.float32, requires_grad=True)
+    M = {k: torch.zeros_like(v) for k, v in P.items()}
+    V = {k: torch.zeros_like(v) for k, v in P.items()}
+    rng = np.random.default_rng(0)
+    tmax = sub.shape[1]
+    keep = (rng.random((tmax, nrow)) < 0.5).astype(np.int64)
+    eps = rng.standard_normal((nrow, CFG['dim_rep'])).astype(np.float32)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        T.train_step(P, M, V, CFG, sub, sub, it, keep, eps)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = nrow / (ms / 1e3)
+    line = dict(metric=METRIC, value=val, unit='sequences/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                impl='reference',
+                config=dict(workload='config.json VAE, IAC-shaped synthetic batch (seed 0), %d longest of 64 rows per step' % nrow,
+                            global_batch=nrow, note='TF reference cannot run (no TensorFlow; CudnnGRU has no CPU kernel): '
+                            'torch-CPU port of the same padded graph, oracle/vae_torch.py'),
+                cpu_baseline=dict(value=val, unit='sequences/s', cores=cores, kind='port',
+                                  sample='%d longest rows of the 64-row C1 batch (max len %d), %d steps' % (nrow, tmax, args.steps)),
+                e2e=dict(value=val, unit='sequences/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg():
+    """rank 0, N=1: the torch-CPU port timed on a bounded sample of the same workload."""
+    import torch
+    from argsim_b200.synth import synth_batch
+    from oracle import vae_oracle as O
+    from oracle import vae_torch as T
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    full = synth_batch(PER_GPU, 'iac', CFG['dim_tgt'], seed=0)
+    nrow = 8
+    order = np.argsort(-(full != 1).sum(1), kind='stable')[:nrow]
+    sub = full[np.sort(order)]
+    sub = sub[:, :int((sub != 1).sum(1).max())]
+    P = T.to_torch(O.init_params(CFG, seed=0, dtype=np.float32), torch.float32, requires_grad=True)
+    M = {k: torch.zeros_like(v) for k, v in P.items()}
+    V = {k: torch.zeros_like(v) for k, v in P.items()}
+    rng = np.random.default_rng(0)
+    keep = (rng.random((sub.shape[1], nrow)) < 0.5).astype(np.int64)
+    eps = rng.standard_normal((nrow, CFG['dim_rep'])).astype(np.float32)
+    T.train_step(P, M, V, CFG, sub[:2, :32], sub[:2, :32], 0, keep[:32, :2], eps[:2])  # warm the thread pool
+    t0 = time.perf_counter()
+    nstep = 0
+    while nstep < 2 or (time.perf_counter() - t0 < 10 and nstep < 8):
+        T.train_step(P, M, V, CFG, sub, sub, nstep, keep, eps)
+        nstep += 1
+    dt = (time.perf_counter() - t0) / nstep
+    return dict(value=nrow / dt, unit='sequences/s', cores=cores, kind='port',
+                sample='%d longest rows of the 64-row C1 batch (max len %d), %d steps of fwd+bwd+Adam in torch-CPU fp32 '
+                       '(TF reference not runnable)' % (nrow, sub.shape[1], nstep))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=('ours', 'reference'))
+    ap.add_argument('--workload', default='train', choices=('train', 'embed'))
+    ap.add_argument('--precision', default='bf16', choices=('bf16', 'fp32'))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--generic-gru', action='store_true', help='bf16 GEMMs with the per-step generic GRU (debug)')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    rank, world, local, dist = dist_setup(args.gpus)
+    if args.impl == 'reference':
+        reference_arm(args, rank, world)
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    import torch  # device plumbing only: barrier / max over ranks
+    from argsim_b200 import _lib, parallel
+    from argsim_b200.synth import synth_batch
+    if not torch.cuda.is_available():
+        sys.exit('bench.py needs a CUDA device (no CPU fallback)')
+    pk = peaks()
+    nccl_id = None
+    if world > 1:
+        obj = [_lib.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        nccl_id = obj[0]
+    flags = _lib.FLAG_KERNEL_TIMERS | (_lib.FLAG_GENERIC_GRU if args.generic_gru else 0)
+    prec = _lib.BF16 if args.precision == 'bf16' else _lib.FP32_VALIDATE
+    h = _lib.Handle(precision=prec, device=local, nranks=world, rank=rank, nccl_id=nccl_id, flags=flags, **CFG)
+    h.init_params(0)
+    h.set_seed(0)
+
+    def barrier():
+        if dist:
+            t = torch.zeros(1, device='cuda')
+            dist.all_reduce(t)
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if args.workload == 'embed':
+        data = synth_batch(4096 * world, 'ibm', CFG['dim_tgt'], seed=0)
+        mine = data[rank::world]
+        mine = np.ascontiguousarray(mine[:, :int((mine != 1).sum(1).max())])
+        for _ in range(args.warmup):
+            h.embed(mine)
+        barrier()
+        clk = Clocks(local)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            h.embed(mine)
+        dt = time.perf_counter() - t0
+        barrier()
+        ms = max_over_ranks(1e3 * dt / args.steps)
+        if rank == 0:
+            S = int((data != 1).sum())
+            print(json.dumps(dict(metric='embed sequences/sec (encoder mu)', value=4096 * world / (ms / 1e3), unit='sequences/s',
+                                  n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
+                                  scaling='weak', vs_baseline=None, dtype=args.precision, data='synthetic',
+                                  config=dict(workload='encoder-only mu embedding, batch 4096 per GPU, IBM-shaped lengths (seed 0)',
+                                              tokens=S), clocks=clk.stop(),
+                                  e2e=dict(value=4096 * world / (ms / 1e3), unit='sequences/s',
+                                           h2d_bytes_per_step=int(mine.nbytes), d2h_bytes_per_step=4096 * 1024 * 4))), flush=True)
+        return
+
+    gb = PER_GPU * world
+    full = synth_batch(gb, 'iac', CFG['dim_tgt'], seed=0)
+    src, tgt, rows, n_tok_glob, b_glob = parallel.shard_batch(full, full, world, rank)
+    kw = dict(n_tokens_global=n_tok_glob, b_global=b_glob, row0=rank * PER_GPU) if world > 1 else {}
+    S_glob = int((full != 1).sum())
+    N_glob = n_tok_glob
+
+    # ---- e2e first (also serves as warm-up of the resident run): host buffers -> C ABI -> stats back
+    for _ in range(args.warmup):
+        st = h.train_step(src, tgt, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = h.train_step(src, tgt, **kw)
+    e2e_dt = time.perf_counter() - t0
+    barrier()
+    e2e_ms = max_over_ranks(1e3 * e2e_dt / args.steps)
+    plan = _lib.plan_batch(src, tgt)
+    h2d = 4 * (plan['S'] + 2 * plan['N'] + 2 * len(src) + 2 * (plan['Tmax_src'] + plan['Tmax_dec']) + 2)
+    d2h = 32
+
+    # ---- device-resident timed region: exactly K steps, CUDA events on the library's stream
+    for _ in range(2):
+        h.bench_resident(1)
+    barrier()
+    clk = Clocks(local)
+    l0 = h.launch_count()
+    ms_local = h.bench_resident(args.steps)
+    launches = h.launch_count() - l0
+    barrier()
+    clocks = clk.stop()
+    ms = max_over_ranks(ms_local)
+    tm = h.last_timings()   # phases + k: timers of the LAST step of the timed region
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+    value = gb / (ms / 1e3)
+    fl = algo_flops(S_glob, N_glob, gb)
+    # dominant kernel = largest k: timer of the last timed step
+    kt = {k[2:]: v for k, v in tm.items() if k.startswith('k:') and not k.endswith('#n')}
+    kn = {k[2:-2]: v for k, v in tm.items() if k.startswith('k:') and k.endswith('#n')}
+    phases = {k: round(v, 4) for k, v in tm.items() if not k.startswith('k:')}
+    plan_l = _lib.plan_batch(src, tgt)
+    S_l, N_l = plan_l['S'], plan_l['N']
+    H = CFG['dim_emb']
+    kalgo = {  # algorithmic work of one rank's step per kernel group (flops or bytes)
+        'gru_fwd_enc': ('tensor', 2 * 3 * H * H * 2 * 3 * S_l), 'gru_bwd_enc': ('tensor', 2 * 3 * H * H * 2 * 3 * S_l),
+        'gru_fwd_dec': ('tensor', 2 * 3 * H * H * 3 * N_l), 'gru_bwd_dec': ('tensor', 2 * 3 * H * H * 3 * N_l),
+        'logits_gemm': ('tensor', 2 * H * CFG['dim_tgt'] * N_l), 'logits_wgrad': ('tensor', 2 * H * CFG['dim_tgt'] * N_l),
+        'logits_dgrad': ('tensor', 2 * H * CFG['dim_tgt'] * N_l),
+        'softmax_ce': ('hbm', (4 if args.precision == 'bf16' else 8) * N_l * CFG['dim_tgt']),
+        'adam': ('hbm', 24410112 * (30 if args.precision == 'bf16' else 28)),
+    }
+    kernels = {}
+    for k, t in kt.items():
+        if k in kalgo and t > 0:
+            bound, work = kalgo[k]
+            ach = work / (t * 1e-3) / (1e9 if bound == 'hbm' else 1e12)
+            peak = pk['hbm'] if bound == 'hbm' else pk['tf_sust']
+            kernels[k] = dict(bound=bound, ms_per_step=round(t, 4), launches_per_step=int(kn.get(k, 0)), achieved=round(ach, 3),
+                              peak=peak, frac=round(ach / peak, 5), share_of_step=round(t / ms, 4))
+    dom = max(kernels, key=lambda k: kernels[k]['ms_per_step']) if kernels else None
+    roofline = None
+    if dom:
+        d = kernels[dom]
+        roofline = dict(kernel=dom, bound=d['bound'], achieved=d['achieved'], peak=d['peak'],
+                        unit='GB/s' if d['bound'] == 'hbm' else 'TFLOP/s', frac=d['frac'], traffic=None,
+                        peak_source='%s (%s)' % (pk['src'], 'hbm_gbs' if d['bound'] == 'hbm' else 'bf16_tflops_sustained: timed inside a long step'),
+                        note='avg launch duration from CUDA events on the launching stream inside the timed region; '
+                             'the recurrence is bound by serial-step latency, not by the tensor pipe (DESIGN.md)')
+    line = dict(metric=METRIC, value=value, unit='sequences/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype='bf16' if args.precision == 'bf16' else 'f32', data='synthetic',
+                config=dict(workload='config.json VAE (V=8192 D=512 R=1024 L=3), IAC-shaped synthetic sentencepiece batch, '
+                                     'seed 0, %d sequences per GPU (BASELINE configs[%d])' % (PER_GPU, 1 if world == 1 else 2),
+                            global_batch=gb, src_tokens=S_glob, tgt_rows=N_glob, max_len=int(full.shape[1]),
+                            parallelism='dp%d' % world, l2='no flush needed: one step streams >1 GB of activations and 0.68 GB of '
+                            'Adam state, far above the 126 MB L2'),
+                clocks=clocks, gpu_launches=int(launches),
+                e2e=dict(value=gb / (e2e_ms / 1e3), unit='sequences/s', ms_per_step=e2e_ms, h2d_bytes_per_step=int(h2d),
+                         d2h_bytes_per_step=d2h, timer='host perf_counter around K blocking argsim_train_step calls'),
+                roofline=roofline, kernels=kernels, phases_ms=phases,
+                step_tflops=round(fl['train'] / (ms * 1e-3) / 1e12, 3), step_frac_of_tensor_peak=round(fl['train'] / (ms * 1e-3) / 1e12 / pk['tf_sust'], 5),
+                last_step=dict(loss=st['loss'], loss_gen=st['loss_gen'], loss_kld=st['loss_kld']))
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline_leg()
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

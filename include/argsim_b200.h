@@ -43,7 +43,8 @@ typedef struct argsim_config {
     int32_t device;               /* CUDA device ordinal */
     int32_t nranks, rank;         /* data parallel world (1,0 = single GPU) */
     uint8_t nccl_id[128];         /* ncclUniqueId from argsim_nccl_unique_id on rank 0 (nranks>1) */
-    int32_t flags;                /* bit0: disable CUDA graphs; bit1: force SIMT GEMM */
+    int32_t flags;                /* bit2 (4): BF16 mode with the generic per-step GRU instead of the persistent
+                                     kernels; bit3 (8): record per-kernel CUDA-event timers (argsim_last_timings) */
 } argsim_config;
 
 /* per-step scalars; sums are over the GLOBAL batch when nranks>1 */
@@ -123,9 +124,23 @@ int  argsim_last_timings(argsim_handle*, int32_t cap, const char** names, float*
 int  argsim_test_gemm(int32_t device, int32_t impl, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
                       const float* A, const float* B, const float* bias_or_null, float alpha,
                       int32_t accumulate, float* C_inout, float* ms_or_null);
-/* stand-alone timing of the bandwidth kernels on synthetic device data (bench/profiles) */
+/* stand-alone timing of one hot kernel on synthetic device data with an L2 flush between
+ * iterations (bench.py roofline / profiles).  which: "softmax_ce" | "adam" | "embed_gather" |
+ * "logits_gemm".  Returns the mean ms per launch and the algorithmic bytes / flops per launch. */
 int  argsim_bench_kernel(argsim_handle*, const char* which, int64_t rows, int32_t iters,
-                         float* ms, double* algo_bytes);
+                         float* ms, double* algo_bytes, double* algo_flops);
+/* host-only (no GPU needed): the index pipeline of one batch -- trim (util_tf.py:40-57), length
+ * sort, packed layout, lead/gold/mask construction (model.py:91-95) and the boolean_mask row
+ * order (model.py:161,174).  Every output may be NULL.  keep: (b,T_tgt) uint8 or NULL (= keep all).
+ * Outputs: len_src/len_tgt (b); counts[4] = {S, N, Tmax_src, Tmax_dec}; ids_src (S); lead, gold,
+ * ref_row (N); enc_last (b); perm_src, perm_dec (b). Capacities are the caller's responsibility
+ * (S <= b*T_src, N <= b*(T_tgt+1)). */
+int  argsim_plan_batch(const int32_t* src, const int32_t* tgt, int32_t b, int32_t T_src, int32_t T_tgt,
+                       int32_t bos, int32_t eos, const uint8_t* keep, int32_t* len_src, int32_t* len_tgt,
+                       int64_t counts[4], int32_t* ids_src, int32_t* lead, int32_t* gold, int32_t* ref_row,
+                       int32_t* enc_last, int32_t* perm_src, int32_t* perm_dec, char* err, int32_t err_cap);
+/* host-only: src/model.py:75-80 evaluated in fp32 */
+void argsim_schedule(int64_t step, float accelerate, float learn_rate, float* keepwd, float* anneal, float* update);
 
 #ifdef __cplusplus
 }

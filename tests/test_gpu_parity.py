@@ -1,0 +1,165 @@
+"""-m gpu: the CUDA path, called through the C ABI, against the CPU oracle (oracle/vae_oracle.py)
+on the same seeded inputs.  fp32 validation mode: ELBO terms within 1e-3 relative (north_star);
+index work bit exact.  The oracle is a restatement (TF cannot run here): parity is against it."""
+import numpy as np
+import pytest
+
+from conftest import SMALL, ragged_batch
+from oracle import vae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(cfg, precision, seed=0, flags=0):
+    from argsim_b200 import _lib
+    h = _lib.Handle(precision=precision, flags=flags, **cfg)
+    P = O.init_params(cfg, seed=seed, dtype=np.float64, bias_scale=0.1)
+    h.set_params({k: v.astype(np.float32) for k, v in P.items()})
+    return h, P
+
+
+def _inject(cfg, tgt, seed):
+    rng = np.random.default_rng(seed)
+    keep = (rng.random(tgt.shape) < 0.7).astype(np.uint8)
+    eps = rng.standard_normal((tgt.shape[0], cfg['dim_rep'])).astype(np.float32)
+    return keep, eps
+
+
+def _oracle_keep(keep, tgt, eos):
+    """(b,T) batch-major mask -> the oracle's (t-1, b) time-major mask over the trimmed length"""
+    tmax = int((tgt != eos).sum(1).max())
+    return keep[:, :tmax].T
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-12)
+
+
+def test_fp32_forward_losses_match_oracle():
+    from argsim_b200 import _lib
+    cfg = dict(SMALL)
+    h, P = _mk(cfg, _lib.FP32_VALIDATE)
+    src = ragged_batch(7, 13, cfg['dim_tgt'], 1)
+    tgt = ragged_batch(7, 11, cfg['dim_tgt'], 2)
+    o, _ = O.forward(P, cfg, src, tgt, 'valid', step=0)
+    e = h.eval_step(src, tgt, want_pred=True)
+    assert e['loss_gen_samp'].shape == o['loss_gen_samp'].shape
+    np.testing.assert_allclose(e['loss_gen_samp'], o['loss_gen_samp'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(e['loss_kld_samp'], o['loss_kld_samp'], rtol=1e-4, atol=1e-6)
+    np.testing.assert_array_equal(e['pred'], o['pred'])              # index work: bit exact
+    np.testing.assert_array_equal(e['errt_samp'], o['errt_samp'])
+    mu = h.embed(src)
+    np.testing.assert_allclose(mu, o['mu'], rtol=1e-4, atol=1e-5)
+
+
+def test_fp32_train_step_losses_and_grads_match_oracle():
+    from argsim_b200 import _lib
+    cfg = dict(SMALL)
+    h, P = _mk(cfg, _lib.FP32_VALIDATE)
+    src = ragged_batch(6, 12, cfg['dim_tgt'], 3)
+    tgt = ragged_batch(6, 9, cfg['dim_tgt'], 4)
+    keep, eps = _inject(cfg, tgt, 5)
+    step = 12345
+    h.step = step
+    o, cache = O.forward(P, cfg, src, tgt, 'train', step=step, keep=_oracle_keep(keep, tgt, cfg['eos']), eps=eps.astype(np.float64))
+    G = O.backward(P, cfg, cache)
+    st = h.grad_step(src, tgt, keep=keep, eps=eps)
+    assert st['n_tokens'] == len(o['labels'])
+    assert rel(st['loss_gen'], o['loss_gen']) < 1e-3
+    assert rel(st['loss_kld'], o['loss_kld']) < 1e-3
+    assert rel(st['loss'], o['loss']) < 1e-3
+    assert abs(st['errt'] - o['errt']) < 1e-6
+    assert rel(st['rate_anneal'], o['rate_anneal']) < 1e-6 and rel(st['rate_update'], o['rate_update']) < 1e-6
+    assert h.step == step  # grad_step does not advance
+    for k in P:
+        g = h.get_grad(k)
+        scale = np.abs(G[k]).max() + 1e-12
+        err = np.abs(g - G[k]).max() / scale
+        assert err < 2e-4, (k, err)
+
+
+def test_fp32_multi_step_adam_tracks_oracle():
+    from argsim_b200 import _lib
+    cfg = dict(SMALL)
+    h, P = _mk(cfg, _lib.FP32_VALIDATE)
+    M = {k: np.zeros_like(v) for k, v in P.items()}
+    V = {k: np.zeros_like(v) for k, v in P.items()}
+    for it in range(4):
+        src = ragged_batch(5, 10, cfg['dim_tgt'], 10 + it)
+        keep, eps = _inject(cfg, src, 20 + it)
+        o, _ = O.train_step(P, M, V, cfg, src, src, it, _oracle_keep(keep, src, cfg['eos']), eps.astype(np.float64))
+        st = h.train_step(src, src, keep=keep, eps=eps)
+        assert st['step'] == it + 1
+        for name, ref in (('loss', o['loss']), ('loss_gen', o['loss_gen']), ('loss_kld', o['loss_kld'])):
+            assert rel(st[name], ref) < 1e-3, (it, name, st[name], ref)
+    for k in P:
+        p = h.get_param(k)
+        assert np.abs(p - P[k]).max() < 2e-4, k   # 4 Adam steps move every weight by <= 4e-3
+        m, v = h.get_opt_state(k)
+        np.testing.assert_allclose(m, M[k], rtol=5e-3, atol=1e-7)
+
+
+def test_edge_cases_len1_b1_and_contract_errors():
+    from argsim_b200 import _lib
+    cfg = dict(SMALL)
+    h, P = _mk(cfg, _lib.FP32_VALIDATE)
+    src = np.array([[7]], np.int32)               # b=1, len 1, no padding column at all
+    o, _ = O.forward(P, cfg, src, src, 'valid')
+    e = h.eval_step(src, src)
+    np.testing.assert_allclose(e['loss_gen_samp'], o['loss_gen_samp'], rtol=1e-4, atol=1e-5)
+    src = np.array([[7, 1, 1, 1], [9, 8, 7, 6], [5, 1, 1, 1]], np.int32)
+    o, _ = O.forward(P, cfg, src, src, 'valid')
+    e = h.eval_step(src, src)
+    np.testing.assert_allclose(e['loss_gen_samp'], o['loss_gen_samp'], rtol=1e-4, atol=1e-5)
+    with pytest.raises(RuntimeError):             # empty row: len_src must be >= 1 (model.py:135 would index -1)
+        h.eval_step(np.array([[1, 1], [4, 5]], np.int32), np.array([[1, 1], [4, 5]], np.int32))
+    with pytest.raises(RuntimeError):             # eos inside a sequence violates trim()'s contract
+        h.eval_step(np.array([[4, 1, 5]], np.int32), np.array([[4, 1, 5]], np.int32))
+    with pytest.raises(RuntimeError):             # id out of range
+        h.eval_step(np.array([[4, 999]], np.int32), np.array([[4, 5]], np.int32))
+
+
+def test_philox_keep_mask_matches_numpy_restatement():
+    """library-drawn word dropout (no injected mask) == argsim_b200.rng.keep_mask fed back as injection"""
+    from argsim_b200 import _lib, rng
+    cfg = dict(SMALL)
+    h, P = _mk(cfg, _lib.FP32_VALIDATE)
+    h2, _ = _mk(cfg, _lib.FP32_VALIDATE)
+    src = ragged_batch(6, 12, cfg['dim_tgt'], 7)
+    eps = np.random.default_rng(0).standard_normal((6, cfg['dim_rep'])).astype(np.float32)
+    for hh in (h, h2):
+        hh.set_seed(1234)
+        hh.step = 5000
+    kw = _lib.schedule(5000, cfg['accelerate'], cfg['learn_rate'])['rate_keepwd']
+    keep = rng.keep_mask(6, src.shape[1], kw, 1234, 5000)
+    assert 0 < keep.mean() < 1
+    a = h.grad_step(src, src, keep=None, eps=eps)
+    b = h2.grad_step(src, src, keep=keep, eps=eps)
+    assert a['loss_gen'] == b['loss_gen']
+
+
+def test_decode_and_checkpoint_roundtrip(tmp_path):
+    from argsim_b200 import _lib
+    cfg = dict(SMALL)
+    h, P = _mk(cfg, _lib.FP32_VALIDATE)
+    z = np.random.default_rng(3).standard_normal((4, cfg['dim_rep'])).astype(np.float32)
+    ref = O.decode_greedy({k: v.astype(np.float32) for k, v in P.items()}, cfg, z, steps=6)
+    s = h.decode_init(z)
+    x = np.full(4, cfg['bos'], np.int32)
+    ys = []
+    for _ in range(6):
+        x, s = h.decode_step(x, s)
+        if np.all(x == cfg['eos']):
+            break
+        ys.append(x)
+    np.testing.assert_array_equal(np.stack(ys, 1), ref)
+    src = ragged_batch(3, 8, cfg['dim_tgt'], 9)
+    h.train_step(src, src)
+    path = str(tmp_path / 'ckpt.bin')
+    h.save(path)
+    h2 = _lib.Handle(precision=_lib.FP32_VALIDATE, **cfg)
+    h2.load(path)
+    assert h2.step == 1
+    for k in P:
+        np.testing.assert_array_equal(h.get_param(k), h2.get_param(k))
+        np.testing.assert_array_equal(h.get_opt_state(k)[1], h2.get_opt_state(k)[1])

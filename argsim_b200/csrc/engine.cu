@@ -16,6 +16,14 @@
 
 static inline size_t align_up(size_t n, size_t a) { return (n + a - 1) / a * a; }
 
+// Blocking copy ordered on the engine's own stream.  st[0] is created cudaStreamNonBlocking, so the
+// legacy default stream used by plain cudaMemcpy is NOT ordered against the kernels launched on it
+// (a pageable H2D cudaMemcpy may even return before its DMA lands).
+void Engine::copy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, kind, st[0]));
+    CUDA_CHECK(cudaStreamSynchronize(st[0]));
+}
+
 // ------------------------------------------------------------------------------------------
 // construction: parameter table in backward-completion order (== allreduce bucket order)
 // ------------------------------------------------------------------------------------------
@@ -159,7 +167,7 @@ void Engine::init_params(uint64_t seed_) {
             uni(dst, pi.n, sqrtf(6.0f / (float)(pi.shape[0] + pi.shape[1])));
         }
     }
-    CUDA_CHECK(cudaMemcpy(p, host.data(), nflat * sizeof(float), cudaMemcpyHostToDevice));
+    copy_sync(p, host.data(), nflat * sizeof(float), cudaMemcpyHostToDevice);
     CUDA_CHECK(cudaMemset(m, 0, nflat * sizeof(float)));
     CUDA_CHECK(cudaMemset(v, 0, nflat * sizeof(float)));
     refresh_shadow(0, nflat);
@@ -169,17 +177,17 @@ void Engine::init_params(uint64_t seed_) {
 
 void Engine::set_param(const std::string& name, const float* src) {
     const ParamInfo& pi = pinfo(name);
-    CUDA_CHECK(cudaMemcpy(p + pi.off, src, pi.n * sizeof(float), cudaMemcpyHostToDevice));
+    copy_sync(p + pi.off, src, pi.n * sizeof(float), cudaMemcpyHostToDevice);
     refresh_shadow(pi.off, pi.n);
     CUDA_CHECK(cudaStreamSynchronize(st[0]));
 }
 void Engine::get_flat(const float* flat, const std::string& name, float* dst) {
     const ParamInfo& pi = pinfo(name);
-    CUDA_CHECK(cudaMemcpy(dst, flat + pi.off, pi.n * sizeof(float), cudaMemcpyDeviceToHost));
+    copy_sync(dst, flat + pi.off, pi.n * sizeof(float), cudaMemcpyDeviceToHost);
 }
 void Engine::set_flat(float* flat, const std::string& name, const float* src) {
     const ParamInfo& pi = pinfo(name);
-    CUDA_CHECK(cudaMemcpy(flat + pi.off, src, pi.n * sizeof(float), cudaMemcpyHostToDevice));
+    copy_sync(flat + pi.off, src, pi.n * sizeof(float), cudaMemcpyHostToDevice);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -223,14 +231,14 @@ void Engine::gather_embed(const int* ids, long long n, const Mat& out) {
 void Engine::gru_fwd(GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact) {
     if (arena.dry) return;
     kbegin(ndir == 2 ? "k:gru_fwd_enc" : "k:gru_fwd_dec");
-    if (use_mma) gru_mma_fwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0]);
+    if (use_mma && gru_mma_fits(mma, ndir, P.b)) gru_mma_fwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0]);
     else gru_generic_fwd(dirs, ndir, P, H, gru_work, st);
     kend();
 }
 void Engine::gru_bwd(GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact) {
     if (arena.dry) return;
     kbegin(ndir == 2 ? "k:gru_bwd_enc" : "k:gru_bwd_dec");
-    if (use_mma) gru_mma_bwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0]);
+    if (use_mma && gru_mma_fits(mma, ndir, P.b)) gru_mma_bwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0]);
     else gru_generic_bwd(dirs, ndir, P, H, gru_work, st);
     kend();
 }
@@ -760,7 +768,7 @@ void Engine::decode_init(const float* z, int b, float* state) {
     float *dz, *dh;
     CUDA_CHECK(cudaMalloc(&dz, sizeof(float) * b * R));
     CUDA_CHECK(cudaMalloc(&dh, sizeof(float) * b * H));
-    CUDA_CHECK(cudaMemcpy(dz, z, sizeof(float) * b * R, cudaMemcpyHostToDevice));
+    copy_sync(dz, z, sizeof(float) * b * R, cudaMemcpyHostToDevice);
     const ParamInfo& k = pinfo("latent/ex/kernel");
     gemm_simt(dz, R, 0, p + k.off, D, 1, dh, H, b, D, R, 1.f, p + pinfo("latent/ex/bias").off, 0, nullptr, st[0]);
     for (int l = 0; l < L; ++l)
@@ -809,9 +817,9 @@ void Engine::save(const char* path) {
     FILE* f = fopen(path, "wb");
     if (!f) throw std::runtime_error(std::string("cannot open for writing: ") + path);
     std::vector<float> hp(nflat), hm(nflat), hv(nflat);
-    CUDA_CHECK(cudaMemcpy(hp.data(), p, nflat * sizeof(float), cudaMemcpyDeviceToHost));
-    CUDA_CHECK(cudaMemcpy(hm.data(), m, nflat * sizeof(float), cudaMemcpyDeviceToHost));
-    CUDA_CHECK(cudaMemcpy(hv.data(), v, nflat * sizeof(float), cudaMemcpyDeviceToHost));
+    copy_sync(hp.data(), p, nflat * sizeof(float), cudaMemcpyDeviceToHost);
+    copy_sync(hm.data(), m, nflat * sizeof(float), cudaMemcpyDeviceToHost);
+    copy_sync(hv.data(), v, nflat * sizeof(float), cudaMemcpyDeviceToHost);
     const char magic[8] = {'A', 'R', 'G', 'S', 'I', 'M', '0', '1'};
     fwrite(magic, 1, 8, f);
     int64_t hdr[2] = {step, (int64_t)params.size()};
@@ -853,9 +861,9 @@ void Engine::load(const char* path) {
             fread(hv.data() + pi.off, sizeof(float), pi.n, f) != pi.n) { fclose(f); throw std::runtime_error("truncated checkpoint"); }
     }
     fclose(f);
-    CUDA_CHECK(cudaMemcpy(p, hp.data(), nflat * sizeof(float), cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaMemcpy(m, hm.data(), nflat * sizeof(float), cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaMemcpy(v, hv.data(), nflat * sizeof(float), cudaMemcpyHostToDevice));
+    copy_sync(p, hp.data(), nflat * sizeof(float), cudaMemcpyHostToDevice);
+    copy_sync(m, hm.data(), nflat * sizeof(float), cudaMemcpyHostToDevice);
+    copy_sync(v, hv.data(), nflat * sizeof(float), cudaMemcpyHostToDevice);
     refresh_shadow(0, nflat);
     CUDA_CHECK(cudaStreamSynchronize(st[0]));
     step = hdr[0];

@@ -63,6 +63,7 @@ public:
     void get_flat(const float* flat, const std::string& name, float* dst);
     void set_flat(float* flat, const std::string& name, const float* src);
     void refresh_shadow(size_t off, size_t n);
+    void copy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind);
 
     // --- steps (host buffers in/out, blocking) ---
     void train_step(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt, const uint8_t* keep, const float* eps,

@@ -1,9 +1,589 @@
-// placeholder until the persistent recurrence lands
+// gru_mma.cu -- persistent GRU recurrence for H = 512 (bf16 operands, fp32 state and gates).
+//
+// The recurrence is bound by serial-step latency, not by flops: per step and direction-layer it
+// is a (rows x 512) x (512 x 1536) product that cannot start before the previous step finished.
+// Design (DESIGN.md "recurrence"):
+//   * a GROUP of 16 CTAs owns one (direction, batch-slice); CTA c owns hidden units [32c, 32c+32),
+//     i.e. 96 rows of R.  Its R slice (96 x 512 bf16 = 96 KB) is loaded ONCE into registers as
+//     mma.sync A-fragments (96 registers per thread) and stays there for the whole sequence --
+//     no shared-memory or L2 re-read of weights per step.
+//   * forward:  gh[96 x n] = R_own[96 x 512] . h^T[512 x n]  needs the whole h of the previous step:
+//     every CTA publishes its 32 new units per row through an L2-resident "LL" buffer (8-byte words =
+//     two bf16 + a 32-bit step tag, so data and flag arrive in ONE store: no fence, no separate flag).
+//   * backward: dh_prev[n x 512] = dgh[n x 1536] . R is computed by the dual decomposition: CTA c
+//     multiplies its OWN 96 dgh columns (local, no gather) with R_own^T[512 x 96] and scatters the
+//     512 partial sums to their owner CTAs through the same LL mechanism (reduce-scatter), so the
+//     bytes exchanged per step equal the forward's instead of 3x.
+//   * rows of a slice are processed in chunks of 16 (two n=8 MMA tiles); fp32 h state lives in smem.
+//   * groups are independent (no grid-wide barrier); the launch is cooperative only to guarantee
+//     that the 16 CTAs that wait on each other are co-resident.
+// Tensor-core instruction: mma.sync.m16n8k16 (bf16 -> fp32).  tcgen05 is the wrong tool here: its
+// minimum M = 128 tile and shared-memory operand reads (>= 96 KB per step) cost more than the whole
+// register-stationary step; the batched GEMMs around the recurrence use tcgen05 (gemm_tc.cu).
 #include "kernels.h"
 #include "plan.h"
-struct GruMmaCtx { int dev; };
-GruMmaCtx* gru_mma_create(int device) { return new GruMmaCtx{device}; }
-void gru_mma_destroy(GruMmaCtx* c) { delete c; }
-bool gru_mma_supported(int) { return false; }
-void gru_mma_fwd(GruMmaCtx*, const GruFwdArgs*, int, const SeqPlan&, const int*, const int*, int, cudaStream_t) { throw std::runtime_error("gru_mma not built"); }
-void gru_mma_bwd(GruMmaCtx*, const GruBwdArgs*, int, const SeqPlan&, const int*, const int*, int, cudaStream_t) { throw std::runtime_error("gru_mma not built"); }
+#include <cooperative_groups.h>
+
+namespace {
+
+constexpr int HH = 512;
+constexpr int CL = 16;
+constexpr int UN = 32;
+constexpr int NTH = 256;
+constexpr int CH = 16;
+constexpr int HS_LD = HH + 8;
+constexpr int RED_LD = 100;
+constexpr int GS_LD = 96 + 8;
+constexpr int MAX_BSL = 128;
+
+struct FwdDirP {
+    const float* gx; const bf16* R; const float* bR; const float* h0;
+    float* hs_f; bf16* hs_h; float* cache;
+    int ld_gx, ld_hs, reverse;
+};
+struct FwdP {
+    FwdDirP dir[2];
+    const int* off; const int* nact;
+    unsigned long long* xbuf;
+    int ndir, nslices, b, Tmax, bslr;
+    unsigned tag_base;
+};
+struct BwdDirP {
+    const float* dhs; const float* hs_f; const bf16* hs_h; const float* h0; const float* cache; const bf16* R;
+    float* dgx_f; bf16* dgx_h; float* dgh_f; bf16* dgh_h; float* hp_f; bf16* hp_h; float* dh0;
+    int ld_dhs, ld_hs, ld_dg, ld_hp, reverse;
+};
+struct BwdP {
+    BwdDirP dir[2];
+    const int* off; const int* nact;
+    unsigned long long* ybuf;
+    int ndir, nslices, b, Tmax, bslr;
+    unsigned tag_base;
+};
+
+__device__ __forceinline__ void ll_store(unsigned long long* p, uint32_t data, uint32_t tag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load2(const unsigned long long* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 ll_load1(const unsigned long long* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const bf16* p) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t bf16_bits(float x) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x)); }
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ int slice_rows(int nat, int sl, int ns) { return nat > sl ? (nat - sl + ns - 1) / ns : 0; }
+// a peer that never shows up must not hang the GPU: ~2 s, then trap
+#define POLL_GUARD(t0) if (clock64() - (t0) > 4000000000LL) __trap()
+
+// =========================================================================================
+// forward
+// =========================================================================================
+__global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ FwdP P) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    bf16* Hs = reinterpret_cast<bf16*>(sm);                                   // [bslr][HS_LD]  h_{t-1}, all 512 units
+    float* red = reinterpret_cast<float*>(sm + (size_t)P.bslr * HS_LD * 2);  // [4][CH][RED_LD] k-quarter partial sums
+    float* hst = red + 4 * CH * RED_LD;                                       // [bslr][UN]     fp32 state of the own units
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = blockIdx.x / CL, c = blockIdx.x % CL;
+    const int ns = P.nslices, d = grp / ns, sl = grp % ns;
+    const FwdDirP& A = P.dir[d];
+    const int kq = warp & 3, mh = warp >> 2, g4 = lane >> 2, q4 = lane & 3;
+
+    // ---- R slice -> registers (A fragments): local row lr = gate*32 + unit  <->  R row gate*H + 32c + unit
+    uint32_t a[3][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 3; ++mt) {
+        const int lr0 = (3 * mh + mt) * 16 + g4, lr1 = lr0 + 8;
+        const bf16* r0 = A.R + (size_t)((lr0 >> 5) * HH + UN * c + (lr0 & 31)) * HH;
+        const bf16* r1 = A.R + (size_t)((lr1 >> 5) * HH + UN * c + (lr1 & 31)) * HH;
+#pragma unroll
+        for (int kt = 0; kt < 8; ++kt) {
+            const int k0 = 128 * kq + 16 * kt + 2 * q4;
+            a[mt][kt][0] = *reinterpret_cast<const uint32_t*>(r0 + k0);
+            a[mt][kt][1] = *reinterpret_cast<const uint32_t*>(r1 + k0);
+            a[mt][kt][2] = *reinterpret_cast<const uint32_t*>(r0 + k0 + 8);
+            a[mt][kt][3] = *reinterpret_cast<const uint32_t*>(r1 + k0 + 8);
+        }
+    }
+    const int col = UN * c + lane;
+    const float bRr = A.bR[col], bRu = A.bR[HH + col], bRn = A.bR[2 * HH + col];
+    const int nloc = slice_rows(P.b, sl, ns);
+    for (int i = tid; i < nloc * UN; i += NTH) {
+        const int jl = i >> 5, u = i & 31;
+        hst[i] = A.h0 ? A.h0[(size_t)(jl * ns + sl) * HH + UN * c + u] : 0.f;
+    }
+    const size_t xpar = (size_t)P.bslr * (HH / 2);
+    unsigned long long* X = P.xbuf + (size_t)grp * 2 * xpar;
+    __syncthreads();
+
+    int na_prev = 0;
+    bool first = true;
+    for (int k = 0; k < P.Tmax; ++k) {
+        const int t = A.reverse ? P.Tmax - 1 - k : k;
+        const int na = slice_rows(P.nact[t], sl, ns);
+        if (na == 0) {
+            if (A.reverse) continue;
+            break;
+        }
+        // ---------------- h_{prev} of every active row, all 512 units -> Hs
+        if (first) {
+            for (int i = tid; i < na * (HH / 2); i += NTH) {
+                const int jl = i / (HH / 2), kk = (i % (HH / 2)) * 2;
+                float v0 = 0.f, v1 = 0.f;
+                if (A.h0) {
+                    const float* hp = A.h0 + (size_t)(jl * ns + sl) * HH + kk;
+                    v0 = hp[0]; v1 = hp[1];
+                }
+                *reinterpret_cast<__nv_bfloat162*>(Hs + jl * HS_LD + kk) = __floats2bfloat162_rn(v0, v1);
+            }
+            first = false;
+        } else {
+            const int npoll = min(na, na_prev);
+            const unsigned tag = P.tag_base + (unsigned)(k - 1);
+            const unsigned long long* Xr = X + (size_t)((k - 1) & 1) * xpar;
+            const int nvec = npoll * (HH / 4);
+            constexpr int U = 8;
+            for (int base = 0; base < nvec; base += NTH * U) {
+                uint4 x[U];
+                bool ok;
+                const long long t0 = clock64();
+                do {
+                    ok = true;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int v = base + u * NTH + tid;
+                        if (v < nvec) x[u] = ll_load2(Xr + (size_t)(v / (HH / 4)) * (HH / 2) + 2 * (v % (HH / 4)));
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int v = base + u * NTH + tid;
+                        if (v < nvec && (x[u].y != tag || x[u].w != tag)) ok = false;
+                    }
+                    POLL_GUARD(t0);
+                } while (!ok);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int v = base + u * NTH + tid;
+                    if (v < nvec) *reinterpret_cast<uint2*>(Hs + (v / (HH / 4)) * HS_LD + 4 * (v % (HH / 4))) = make_uint2(x[u].x, x[u].z);
+                }
+            }
+            // rows that join at this step (reverse direction): zero initial state
+            for (int i = tid; i < (na - npoll) * (HH / 2); i += NTH) {
+                const int jl = npoll + i / (HH / 2), kk = (i % (HH / 2)) * 2;
+                *reinterpret_cast<uint32_t*>(Hs + jl * HS_LD + kk) = 0u;
+            }
+        }
+        __syncthreads();
+
+        const unsigned tagw = P.tag_base + (unsigned)k;
+        unsigned long long* Xw = X + (size_t)(k & 1) * xpar;
+        const long long row_base = P.off[t];
+        for (int ch = 0; ch * CH < na; ++ch) {
+            const int nrows = min(CH, na - ch * CH);
+            // gx of the two rows this thread finishes (independent of h: issued before the MMAs)
+            float gxv[2][3];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = 2 * warp + e;
+                gxv[e][0] = gxv[e][1] = gxv[e][2] = 0.f;
+                if (n < nrows) {
+                    const float* gp = A.gx + (size_t)(row_base + (long long)(ch * CH + n) * ns + sl) * A.ld_gx + col;
+                    gxv[e][0] = gp[0]; gxv[e][1] = gp[HH]; gxv[e][2] = gp[2 * HH];
+                }
+            }
+            float acc[3][2][4];
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+#pragma unroll
+            for (int kt2 = 0; kt2 < 4; ++kt2) {
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4(b0, b1, b2, b3, Hs + (ch * CH + nt * 8 + (lane & 7)) * HS_LD + 128 * kq + 32 * kt2 + 8 * (lane >> 3));
+#pragma unroll
+                    for (int mt = 0; mt < 3; ++mt) {
+                        mma16816(acc[mt][nt], a[mt][2 * kt2], b0, b1);
+                        mma16816(acc[mt][nt], a[mt][2 * kt2 + 1], b2, b3);
+                    }
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < 3; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    float* rp = red + (kq * CH + nt * 8 + 2 * q4) * RED_LD + (3 * mh + mt) * 16 + g4;
+                    rp[0] = acc[mt][nt][0]; rp[RED_LD] = acc[mt][nt][1];
+                    rp[8] = acc[mt][nt][2]; rp[RED_LD + 8] = acc[mt][nt][3];
+                }
+            __syncthreads();
+            // ---------------- gates: lane = unit, warp -> rows 2w, 2w+1
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = 2 * warp + e;
+                if (n < nrows) {
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float* rb = red + (q * CH + n) * RED_LD;
+                        s0 += rb[lane]; s1 += rb[32 + lane]; s2 += rb[64 + lane];
+                    }
+                    const float r = sigm(gxv[e][0] + s0 + bRr);
+                    const float z = sigm(gxv[e][1] + s1 + bRu);
+                    const float qq = s2 + bRn;
+                    const float nn = tanhf(gxv[e][2] + r * qq);
+                    const int jl = ch * CH + n;
+                    const float hp = hst[jl * UN + lane];
+                    const float h = (1.f - z) * nn + z * hp;
+                    hst[jl * UN + lane] = h;
+                    const size_t row = (size_t)(row_base + (long long)jl * ns + sl);
+                    const __nv_bfloat16 hb16 = __float2bfloat16(h);
+                    if (A.hs_h) A.hs_h[row * A.ld_hs + col] = hb16;
+                    if (A.hs_f) A.hs_f[row * A.ld_hs + col] = h;
+                    if (A.cache) {
+                        float* cp = A.cache + row * 4 * HH + col;
+                        cp[0] = r; cp[HH] = z; cp[2 * HH] = nn; cp[3 * HH] = qq;
+                    }
+                    const uint32_t hb = (uint32_t)__bfloat16_as_ushort(hb16);
+                    const uint32_t ob = __shfl_down_sync(0xffffffffu, hb, 1);
+                    if (!(lane & 1)) ll_store(Xw + (size_t)jl * (HH / 2) + (col >> 1), hb | (ob << 16), tagw);
+                }
+            }
+            __syncthreads();
+        }
+        na_prev = na;
+    }
+}
+
+// =========================================================================================
+// backward (BPTT)
+// =========================================================================================
+__device__ __forceinline__ size_t yidx(int par, int dest, int src, int pair, int ul, int npair) {
+    return ((((size_t)par * CL + dest) * CL + src) * npair + pair) * UN + ul;
+}
+
+__global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ BwdP P) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    bf16* Gs = reinterpret_cast<bf16*>(sm);                               // [CH][GS_LD]  own dgh columns of the chunk
+    float* cs = reinterpret_cast<float*>(sm + CH * GS_LD * 2);           // [bslr][UN]   d*u carried to the next step
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = blockIdx.x / CL, c = blockIdx.x % CL;
+    const int ns = P.nslices, d = grp / ns, sl = grp % ns;
+    const BwdDirP& A = P.dir[d];
+    const int g4 = lane >> 2, q4 = lane & 3;
+    const int npair = P.bslr / 2;
+
+    // ---- R_own^T -> registers: A[m = out unit o][k = local gate row lr] = R[grow(lr)][o]
+    uint32_t a[4][6][4];
+#pragma unroll
+    for (int kt = 0; kt < 6; ++kt) {
+        const int lr0 = 16 * kt + 2 * q4;
+        const unsigned short* R0 = reinterpret_cast<const unsigned short*>(A.R) + (size_t)((lr0 >> 5) * HH + UN * c + (lr0 & 31)) * HH;
+        const unsigned short* R1 = R0 + HH;                                   // lr0 + 1 (same gate: lr0 is even)
+        const int lr8 = lr0 + 8;
+        const unsigned short* R8 = reinterpret_cast<const unsigned short*>(A.R) + (size_t)((lr8 >> 5) * HH + UN * c + (lr8 & 31)) * HH;
+        const unsigned short* R9 = R8 + HH;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const int o0 = 64 * warp + 16 * mt + g4, o1 = o0 + 8;
+            a[mt][kt][0] = (uint32_t)R0[o0] | ((uint32_t)R1[o0] << 16);
+            a[mt][kt][1] = (uint32_t)R0[o1] | ((uint32_t)R1[o1] << 16);
+            a[mt][kt][2] = (uint32_t)R8[o0] | ((uint32_t)R9[o0] << 16);
+            a[mt][kt][3] = (uint32_t)R8[o1] | ((uint32_t)R9[o1] << 16);
+        }
+    }
+    const int col = UN * c + lane;
+    const int nloc = slice_rows(P.b, sl, ns);
+    for (int i = tid; i < nloc * UN; i += NTH) cs[i] = 0.f;
+    const size_t ypar = (size_t)CL * CL * npair * UN;
+    unsigned long long* Y = P.ybuf + (size_t)grp * 2 * ypar;
+    __syncthreads();
+
+    int na_prev = 0;
+    bool first = true;
+    int k_last = -1;
+    for (int k = 0; k < P.Tmax; ++k) {
+        const int t = A.reverse ? k : P.Tmax - 1 - k;
+        const int na = slice_rows(P.nact[t], sl, ns);
+        if (na == 0) {
+            if (A.reverse) break;
+            continue;
+        }
+        const int ncarry = first ? 0 : min(na, na_prev);
+        // h_{prev} source: the step processed BEFORE t in the forward pass
+        const int th = A.reverse ? t + 1 : t - 1;
+        int nhp = 0;
+        long long hp_base = 0;
+        bool hp_from_h0 = false;
+        if (th >= 0 && th < P.Tmax) {
+            nhp = min(na, slice_rows(P.nact[th], sl, ns));
+            hp_base = P.off[th];
+        } else if (!A.reverse && A.h0) {
+            nhp = na;
+            hp_from_h0 = true;
+        }
+        const unsigned tagr = P.tag_base + (unsigned)(k - 1), tagw = P.tag_base + (unsigned)k;
+        const int parr = (k - 1) & 1, parw = k & 1;
+        const long long row_base = P.off[t];
+        for (int ch = 0; ch * CH < na; ++ch) {
+            const int nrows = min(CH, na - ch * CH);
+            // ---- reduce-scatter receive: partial sums of R^T.dgh for my unit, rows (2w, 2w+1), from all 16 CTAs
+            float pin[2] = {0.f, 0.f};
+            if (ch * CH + 2 * warp < ncarry) {
+                uint2 w[CL];
+                bool ok;
+                const long long t0 = clock64();
+                do {
+                    ok = true;
+#pragma unroll
+                    for (int s = 0; s < CL; ++s) w[s] = ll_load1(Y + yidx(parr, c, s, ch * 8 + warp, lane, npair));
+#pragma unroll
+                    for (int s = 0; s < CL; ++s)
+                        if (w[s].y != tagr) ok = false;
+                    POLL_GUARD(t0);
+                } while (!ok);
+#pragma unroll
+                for (int s = 0; s < CL; ++s) {
+                    pin[0] += bf16_lo(w[s].x);
+                    pin[1] += bf16_hi(w[s].x);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = 2 * warp + e;
+                float dr = 0.f, du = 0.f, dnr = 0.f;
+                if (n < nrows) {
+                    const int jl = ch * CH + n;
+                    const size_t row = (size_t)(row_base + (long long)jl * ns + sl);
+                    const float carry = cs[jl * UN + lane] + (jl < ncarry ? pin[e] : 0.f);
+                    const float dd = carry + A.dhs[row * A.ld_dhs + col];
+                    const float* cp = A.cache + row * 4 * HH + col;
+                    const float r = cp[0], z = cp[HH], nn = cp[2 * HH], qq = cp[3 * HH];
+                    float hp = 0.f;
+                    if (jl < nhp) {
+                        if (hp_from_h0) {
+                            hp = A.h0[(size_t)(jl * ns + sl) * HH + col];
+                        } else {
+                            const size_t rh = (size_t)(hp_base + (long long)jl * ns + sl);
+                            hp = A.hs_f ? A.hs_f[rh * A.ld_hs + col] : __bfloat162float(A.hs_h[rh * A.ld_hs + col]);
+                        }
+                    }
+                    const float dn = dd * (1.f - z) * (1.f - nn * nn);
+                    du = dd * (hp - nn) * z * (1.f - z);
+                    dr = dn * qq * r * (1.f - r);
+                    dnr = dn * r;
+                    cs[jl * UN + lane] = dd * z;
+                    const size_t o = row * A.ld_dg + col;
+                    if (A.dgx_f) { A.dgx_f[o] = dr; A.dgx_f[o + HH] = du; A.dgx_f[o + 2 * HH] = dn; }
+                    if (A.dgx_h) { A.dgx_h[o] = __float2bfloat16(dr); A.dgx_h[o + HH] = __float2bfloat16(du); A.dgx_h[o + 2 * HH] = __float2bfloat16(dn); }
+                    if (A.dgh_f) { A.dgh_f[o] = dr; A.dgh_f[o + HH] = du; A.dgh_f[o + 2 * HH] = dnr; }
+                    if (A.dgh_h) { A.dgh_h[o] = __float2bfloat16(dr); A.dgh_h[o + HH] = __float2bfloat16(du); A.dgh_h[o + 2 * HH] = __float2bfloat16(dnr); }
+                    if (A.hp_f) A.hp_f[row * A.ld_hp + col] = hp;
+                    if (A.hp_h) A.hp_h[row * A.ld_hp + col] = __float2bfloat16(hp);
+                }
+                bf16* gp = Gs + n * GS_LD + lane;
+                gp[0] = __float2bfloat16(dr); gp[32] = __float2bfloat16(du); gp[64] = __float2bfloat16(dnr);
+            }
+            __syncthreads();
+            // ---- partial^T[512 x 16] = R_own^T[512 x 96] . dgh_own^T[96 x 16]; this warp: out units 64w..64w+63
+            float acc[4][2][4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+#pragma unroll
+            for (int kt2 = 0; kt2 < 3; ++kt2) {
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4(b0, b1, b2, b3, Gs + (nt * 8 + (lane & 7)) * GS_LD + 32 * kt2 + 8 * (lane >> 3));
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) {
+                        mma16816(acc[mt][nt], a[mt][2 * kt2], b0, b1);
+                        mma16816(acc[mt][nt], a[mt][2 * kt2 + 1], b2, b3);
+                    }
+                }
+            }
+            // ---- reduce-scatter send: (rows 2q, 2q+1) packed as two bf16 + tag, to the owner of each out unit
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const int o0 = 64 * warp + 16 * mt + g4, o1 = o0 + 8;
+                    const int pair = ch * 8 + nt * 4 + q4;
+                    ll_store(Y + yidx(parw, o0 >> 5, c, pair, o0 & 31, npair), bf16_bits(acc[mt][nt][0]) | (bf16_bits(acc[mt][nt][1]) << 16), tagw);
+                    ll_store(Y + yidx(parw, o1 >> 5, c, pair, o1 & 31, npair), bf16_bits(acc[mt][nt][2]) | (bf16_bits(acc[mt][nt][3]) << 16), tagw);
+                }
+            __syncthreads();
+        }
+        na_prev = na;
+        first = false;
+        k_last = k;
+    }
+    // ---- gradient wrt the initial state (decoder: d ex(z)); the last BPTT step of a forward GRU is t = 0
+    if (A.dh0 && !A.reverse && k_last >= 0) {
+        const unsigned tagr = P.tag_base + (unsigned)k_last;
+        const int parr = k_last & 1;
+        for (int ch = 0; ch * CH < na_prev; ++ch) {
+            if (ch * CH + 2 * warp >= na_prev) continue;
+            uint2 w[CL];
+            bool ok;
+            const long long t0 = clock64();
+            do {
+                ok = true;
+#pragma unroll
+                for (int s = 0; s < CL; ++s) w[s] = ll_load1(Y + yidx(parr, c, s, ch * 8 + warp, lane, npair));
+#pragma unroll
+                for (int s = 0; s < CL; ++s)
+                    if (w[s].y != tagr) ok = false;
+                POLL_GUARD(t0);
+            } while (!ok);
+            float pin[2] = {0.f, 0.f};
+#pragma unroll
+            for (int s = 0; s < CL; ++s) {
+                pin[0] += bf16_lo(w[s].x);
+                pin[1] += bf16_hi(w[s].x);
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int jl = ch * CH + 2 * warp + e;
+                if (jl < na_prev) A.dh0[(size_t)(jl * ns + sl) * HH + col] += cs[jl * UN + lane] + pin[e];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+struct GruMmaCtx {
+    int device = 0, num_sms = 148;
+    unsigned launch_id = 1;
+    unsigned long long* xbuf = nullptr;
+    size_t xcap = 0;
+    unsigned long long* ybuf = nullptr;
+    size_t ycap = 0;
+    bool attr_set = false;
+};
+
+GruMmaCtx* gru_mma_create(int device) {
+    GruMmaCtx* c = new GruMmaCtx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BSL * HS_LD * 2 + 4 * CH * RED_LD * 4 + MAX_BSL * UN * 4));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, CH * GS_LD * 2 + MAX_BSL * UN * 4));
+    return c;
+}
+void gru_mma_destroy(GruMmaCtx* c) {
+    if (!c) return;
+    cudaFree(c->xbuf);
+    cudaFree(c->ybuf);
+    delete c;
+}
+bool gru_mma_supported(int H) { return H == HH; }
+
+static void pick_slices(const GruMmaCtx* c, int ndir, int b, int* ns, int* bslr) {
+    const int max_groups = std::max(1, c->num_sms / CL);
+    int s = std::max(1, std::min(max_groups / ndir, (b + CH - 1) / CH));
+    int per = (b + s - 1) / s;
+    *ns = s;
+    *bslr = (per + CH - 1) / CH * CH;
+}
+bool gru_mma_fits(const GruMmaCtx* c, int ndir, int b) {
+    int ns, bslr;
+    pick_slices(c, ndir, b, &ns, &bslr);
+    return ndir * CL <= c->num_sms && bslr <= MAX_BSL;
+}
+
+void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& Pl, const int* d_off, const int* d_nact, int H,
+                 cudaStream_t s) {
+    if (H != HH) throw std::runtime_error("gru_mma: H must be 512");
+    if (Pl.Tmax >= 4096) throw std::runtime_error("gru_mma: more than 4095 steps");
+    FwdP P;
+    int ns, bslr;
+    pick_slices(c, ndir, Pl.b, &ns, &bslr);
+    if (bslr > MAX_BSL) throw std::runtime_error("gru_mma: batch too large for the persistent kernel");
+    for (int d = 0; d < ndir; ++d) {
+        const GruFwdArgs& a = dirs[d];
+        if (!a.R_h) throw std::runtime_error("gru_mma: bf16 weights missing");
+        if (a.h0 && a.reverse) throw std::runtime_error("gru_mma: h0 is only supported for forward directions");
+        P.dir[d] = FwdDirP{a.gx, a.R_h, a.bR, a.h0, a.hs_f, a.hs_h, a.cache, a.ld_gx, a.ld_hs, a.reverse};
+    }
+    if (ndir == 1) P.dir[1] = P.dir[0];
+    const int groups = ndir * ns;
+    const size_t need = (size_t)groups * 2 * bslr * (HH / 2);
+    if (need > c->xcap) {
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        cudaFree(c->xbuf);
+        CUDA_CHECK(cudaMalloc(&c->xbuf, need * 8));
+        CUDA_CHECK(cudaMemset(c->xbuf, 0, need * 8));
+        CUDA_CHECK(cudaDeviceSynchronize());
+        c->xcap = need;
+    }
+    P.off = d_off; P.nact = d_nact; P.xbuf = c->xbuf;
+    P.ndir = ndir; P.nslices = ns; P.b = Pl.b; P.Tmax = Pl.Tmax; P.bslr = bslr;
+    P.tag_base = (c->launch_id++) << 12;
+    if (c->launch_id >= (1u << 20)) c->launch_id = 1;
+    const size_t smem = (size_t)bslr * HS_LD * 2 + 4 * CH * RED_LD * 4 + (size_t)bslr * UN * 4;
+    void* args[] = {&P};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gru_mma_fwd, dim3(groups * CL), dim3(NTH), args, smem, s));
+    COUNT_LAUNCH();
+}
+
+void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& Pl, const int* d_off, const int* d_nact, int H,
+                 cudaStream_t s) {
+    if (H != HH) throw std::runtime_error("gru_mma: H must be 512");
+    if (Pl.Tmax >= 4096) throw std::runtime_error("gru_mma: more than 4095 steps");
+    BwdP P;
+    int ns, bslr;
+    pick_slices(c, ndir, Pl.b, &ns, &bslr);
+    if (bslr > MAX_BSL) throw std::runtime_error("gru_mma: batch too large for the persistent kernel");
+    for (int d = 0; d < ndir; ++d) {
+        const GruBwdArgs& a = dirs[d];
+        if (!a.R_h) throw std::runtime_error("gru_mma: bf16 weights missing");
+        P.dir[d] = BwdDirP{a.dhs, a.hs_f, a.hs_h, a.h0, a.cache, a.R_h, a.dgx_f, a.dgx_h, a.dgh_f, a.dgh_h, a.hp_f, a.hp_h, a.dh0,
+                           a.ld_dhs, a.ld_hs, a.ld_dg, a.ld_hp, a.reverse};
+    }
+    if (ndir == 1) P.dir[1] = P.dir[0];
+    const int groups = ndir * ns;
+    const size_t need = (size_t)groups * 2 * CL * CL * (bslr / 2) * UN;
+    if (need > c->ycap) {
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        cudaFree(c->ybuf);
+        CUDA_CHECK(cudaMalloc(&c->ybuf, need * 8));
+        CUDA_CHECK(cudaMemset(c->ybuf, 0, need * 8));
+        CUDA_CHECK(cudaDeviceSynchronize());
+        c->ycap = need;
+    }
+    P.off = d_off; P.nact = d_nact; P.ybuf = c->ybuf;
+    P.ndir = ndir; P.nslices = ns; P.b = Pl.b; P.Tmax = Pl.Tmax; P.bslr = bslr;
+    P.tag_base = (c->launch_id++) << 12;
+    if (c->launch_id >= (1u << 20)) c->launch_id = 1;
+    const size_t smem = (size_t)CH * GS_LD * 2 + (size_t)bslr * UN * 4;
+    void* args[] = {&P};
+    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gru_mma_bwd, dim3(groups * CL), dim3(NTH), args, smem, s));
+    COUNT_LAUNCH();
+}

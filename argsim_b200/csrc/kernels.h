@@ -96,6 +96,7 @@ struct GruMmaCtx;
 GruMmaCtx* gru_mma_create(int device);
 void gru_mma_destroy(GruMmaCtx*);
 bool gru_mma_supported(int H);
+bool gru_mma_fits(const GruMmaCtx*, int ndir, int b);   // batch small enough for the resident-state kernel
 void gru_mma_fwd(GruMmaCtx*, const GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
                  int H, cudaStream_t s);
 void gru_mma_bwd(GruMmaCtx*, const GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,

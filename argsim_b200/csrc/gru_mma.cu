@@ -23,6 +23,7 @@
 #include "kernels.h"
 #include "plan.h"
 #include <cooperative_groups.h>
+#include <vector>
 
 namespace {
 
@@ -47,6 +48,7 @@ struct FwdP {
     unsigned long long* xbuf;
     int ndir, nslices, b, Tmax, bslr;
     unsigned tag_base;
+    long long* prof;   // debug: per-phase clock totals of thread 0 of every CTA (8 slots each) or null
 };
 struct BwdDirP {
     const float* dhs; const float* hs_f; const bf16* hs_h; const float* h0; const float* cache; const bf16* R;
@@ -59,6 +61,7 @@ struct BwdP {
     unsigned long long* ybuf;
     int ndir, nslices, b, Tmax, bslr;
     unsigned tag_base;
+    long long* prof;
 };
 
 __device__ __forceinline__ void ll_store(unsigned long long* p, uint32_t data, uint32_t tag) {
@@ -84,13 +87,25 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// volatile asm: keeps its program position relative to ldmatrix / other volatile asm
+__device__ __forceinline__ float ld_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ uint32_t bf16_bits(float x) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16(x)); }
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
-__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// tanh(x) = 2 sigm(2x) - 1 with the fast exp / divide (abs error ~1e-7; exact limits at +-inf)
+__device__ __forceinline__ float tanh_fast(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
 __device__ __forceinline__ int slice_rows(int nat, int sl, int ns) { return nat > sl ? (nat - sl + ns - 1) / ns : 0; }
 // a peer that never shows up must not hang the GPU: ~2 s, then trap
 #define POLL_GUARD(t0) if (clock64() - (t0) > 4000000000LL) __trap()
+#define PROF_MARK(i) do { if (P.prof && tid == 0) { const long long now_ = clock64(); pacc[i] += now_ - plast; plast = now_; } } while (0)
 
 // =========================================================================================
 // forward
@@ -100,7 +115,11 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
     bf16* Hs = reinterpret_cast<bf16*>(sm);                                   // [bslr][HS_LD]  h_{t-1}, all 512 units
     float* red = reinterpret_cast<float*>(sm + (size_t)P.bslr * HS_LD * 2);  // [4][CH][RED_LD] k-quarter partial sums
     float* hst = red + 4 * CH * RED_LD;                                       // [bslr][UN]     fp32 state of the own units
+    int* s_nact = reinterpret_cast<int*>(hst + (size_t)P.bslr * UN);          // [Tmax]   step tables: a global load per
+    int* s_off = s_nact + P.Tmax;                                             // [Tmax+1] step would sit on the critical path
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < P.Tmax; i += NTH) s_nact[i] = slice_rows(P.nact[i], blockIdx.x / CL % P.nslices, P.nslices);
+    for (int i = tid; i <= P.Tmax; i += NTH) s_off[i] = P.off[i];
     const int grp = blockIdx.x / CL, c = blockIdx.x % CL;
     const int ns = P.nslices, d = grp / ns, sl = grp % ns;
     const FwdDirP& A = P.dir[d];
@@ -135,12 +154,33 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
 
     int na_prev = 0;
     bool first = true;
+    bool have_next = false;
+    float gxn[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long plast = clock64();
     for (int k = 0; k < P.Tmax; ++k) {
         const int t = A.reverse ? P.Tmax - 1 - k : k;
-        const int na = slice_rows(P.nact[t], sl, ns);
+        const int na = s_nact[t];
         if (na == 0) {
             if (A.reverse) continue;
             break;
+        }
+        PROF_MARK(0);
+        const long long row_base = s_off[t];
+        // gx of chunk 0 (independent of h) was loaded one step ahead into gxn; the first active step loads it here
+        float gx0[2][3];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int n = warp + 8 * e;
+            if (have_next) {
+                gx0[e][0] = gxn[e][0]; gx0[e][1] = gxn[e][1]; gx0[e][2] = gxn[e][2];
+            } else {
+                gx0[e][0] = gx0[e][1] = gx0[e][2] = 0.f;
+                if (n < na) {
+                    const float* gp = A.gx + (size_t)(row_base + (long long)n * ns + sl) * A.ld_gx + UN * c + lane;
+                    gx0[e][0] = gp[0]; gx0[e][1] = gp[HH]; gx0[e][2] = gp[2 * HH];
+                }
+            }
         }
         // ---------------- h_{prev} of every active row, all 512 units -> Hs
         if (first) {
@@ -190,20 +230,21 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
                 *reinterpret_cast<uint32_t*>(Hs + jl * HS_LD + kk) = 0u;
             }
         }
+        PROF_MARK(1);   // poll + Hs fill (thread 0's share)
         __syncthreads();
-
+        PROF_MARK(2);   // barrier 1 (waiting for the slowest poller)
         const unsigned tagw = P.tag_base + (unsigned)k;
         unsigned long long* Xw = X + (size_t)(k & 1) * xpar;
-        const long long row_base = P.off[t];
         for (int ch = 0; ch * CH < na; ++ch) {
             const int nrows = min(CH, na - ch * CH);
-            // gx of the two rows this thread finishes (independent of h: issued before the MMAs)
+            const int ntl = nrows > 8 ? 2 : 1;   // n=8 MMA tiles that hold live rows (warp-uniform)
+            // gx of the rows this thread finishes (row n -> warp n & 7; independent of h: issued before the MMAs)
             float gxv[2][3];
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int n = 2 * warp + e;
-                gxv[e][0] = gxv[e][1] = gxv[e][2] = 0.f;
-                if (n < nrows) {
+                const int n = warp + 8 * e;
+                gxv[e][0] = gx0[e][0]; gxv[e][1] = gx0[e][1]; gxv[e][2] = gx0[e][2];
+                if (ch > 0 && n < nrows) {
                     const float* gp = A.gx + (size_t)(row_base + (long long)(ch * CH + n) * ns + sl) * A.ld_gx + col;
                     gxv[e][0] = gp[0]; gxv[e][1] = gp[HH]; gxv[e][2] = gp[2 * HH];
                 }
@@ -219,6 +260,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
             for (int kt2 = 0; kt2 < 4; ++kt2) {
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
+                    if (nt >= ntl) continue;
                     uint32_t b0, b1, b2, b3;
                     ldmatrix_x4(b0, b1, b2, b3, Hs + (ch * CH + nt * 8 + (lane & 7)) * HS_LD + 128 * kq + 32 * kt2 + 8 * (lane >> 3));
 #pragma unroll
@@ -228,19 +270,57 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
                     }
                 }
             }
+            // next step's gx (chunk 0) -> registers.  Loads return IN ORDER through L1TEX, so they are issued only
+            // after this step's ldmatrix (they would stall them) and were made L2 hits by the prefetch.global.L2
+            // issued two steps ago; they complete under the HMMAs / the partial-sum barrier.
+            if (ch == 0) {
+                have_next = false;
+                if (k + 1 < P.Tmax) {
+                    const int tn = A.reverse ? t - 1 : t + 1;
+                    const int nan = s_nact[tn];
+                    if (nan > 0) {
+                        have_next = true;
+                        const long long rbn = s_off[tn];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int n = warp + 8 * e;
+                            gxn[e][0] = gxn[e][1] = gxn[e][2] = 0.f;
+                            if (n < nan) {
+                                const float* gp = A.gx + (size_t)(rbn + (long long)n * ns + sl) * A.ld_gx + UN * c + lane;
+                                gxn[e][0] = ld_f32(gp); gxn[e][1] = ld_f32(gp + HH); gxn[e][2] = ld_f32(gp + 2 * HH);
+                            }
+                        }
+                    }
+                }
+            }
 #pragma unroll
             for (int mt = 0; mt < 3; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
+                    if (nt >= ntl) continue;
                     float* rp = red + (kq * CH + nt * 8 + 2 * q4) * RED_LD + (3 * mh + mt) * 16 + g4;
                     rp[0] = acc[mt][nt][0]; rp[RED_LD] = acc[mt][nt][1];
                     rp[8] = acc[mt][nt][2]; rp[RED_LD + 8] = acc[mt][nt][3];
                 }
+            PROF_MARK(3);   // MMA + partial stores
             __syncthreads();
-            // ---------------- gates: lane = unit, warp -> rows 2w, 2w+1
+            PROF_MARK(4);   // barrier 2
+            // gx rows of the step after next -> L2.  A prefetch costs its issuing warp ~100 cycles, so it is done by
+            // the warps that have no row to finish in this chunk (all of them idle otherwise until barrier 3)
+            if (ch == 0 && warp >= nrows && k + 2 < P.Tmax) {
+                const int tn = A.reverse ? t - 2 : t + 2;
+                const int nan = s_nact[tn];
+                const long long rbn = s_off[tn];
+                const int nidle = NTH / 32 - nrows;
+                for (int n = warp - nrows; n < nan; n += nidle) {
+                    const float* gp = A.gx + (size_t)(rbn + (long long)n * ns + sl) * A.ld_gx + UN * c;
+                    if (lane < 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + lane * HH));
+                }
+            }
+            // ---------------- gates: lane = unit, warp -> rows w, w+8
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int n = 2 * warp + e;
+                const int n = warp + 8 * e;
                 if (n < nrows) {
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -251,7 +331,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
                     const float r = sigm(gxv[e][0] + s0 + bRr);
                     const float z = sigm(gxv[e][1] + s1 + bRu);
                     const float qq = s2 + bRn;
-                    const float nn = tanhf(gxv[e][2] + r * qq);
+                    const float nn = tanh_fast(gxv[e][2] + r * qq);
                     const int jl = ch * CH + n;
                     const float hp = hst[jl * UN + lane];
                     const float h = (1.f - z) * nn + z * hp;
@@ -269,10 +349,15 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
                     if (!(lane & 1)) ll_store(Xw + (size_t)jl * (HH / 2) + (col >> 1), hb | (ob << 16), tagw);
                 }
             }
+            PROF_MARK(5);   // gates + stores
             __syncthreads();
+            PROF_MARK(6);   // barrier 3
         }
         na_prev = na;
+        PROF_MARK(7);
     }
+    if (P.prof && tid == 0)
+        for (int i = 0; i < 8; ++i) P.prof[blockIdx.x * 8 + i] = pacc[i];
 }
 
 // =========================================================================================
@@ -286,7 +371,15 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
     extern __shared__ __align__(16) unsigned char sm[];
     bf16* Gs = reinterpret_cast<bf16*>(sm);                               // [CH][GS_LD]  own dgh columns of the chunk
     float* cs = reinterpret_cast<float*>(sm + CH * GS_LD * 2);           // [bslr][UN]   d*u carried to the next step
+    int* s_nact = reinterpret_cast<int*>(cs + (size_t)P.bslr * UN);     // [Tmax], [Tmax+1]: step tables in smem
+    int* s_off = s_nact + P.Tmax;
+    // cp.async landing zone for the NEXT step's gate inputs of chunk 0 (dhs, r, u, n, q: fp32; h_prev: bf16),
+    // double buffered by step parity: their HBM latency is paid one step ahead, off the serial chain
+    float* stg = reinterpret_cast<float*>(s_off + P.Tmax + 1 + ((P.Tmax & 1) ? 0 : 1));   // [2][CH][5][UN], 8-byte aligned
+    bf16* stgh = reinterpret_cast<bf16*>(stg + 2 * CH * 5 * UN);                            // [2][CH][UN]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < P.Tmax; i += NTH) s_nact[i] = slice_rows(P.nact[i], blockIdx.x / CL % P.nslices, P.nslices);
+    for (int i = tid; i <= P.Tmax; i += NTH) s_off[i] = P.off[i];
     const int grp = blockIdx.x / CL, c = blockIdx.x % CL;
     const int ns = P.nslices, d = grp / ns, sl = grp % ns;
     const BwdDirP& A = P.dir[d];
@@ -321,14 +414,18 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
 
     int na_prev = 0;
     bool first = true;
+    bool staged = false;      // chunk 0 of the current step was prefetched into stg[k & 1]
     int k_last = -1;
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long plast = clock64();
     for (int k = 0; k < P.Tmax; ++k) {
         const int t = A.reverse ? k : P.Tmax - 1 - k;
-        const int na = slice_rows(P.nact[t], sl, ns);
+        const int na = s_nact[t];
         if (na == 0) {
             if (A.reverse) break;
             continue;
         }
+        PROF_MARK(0);
         const int ncarry = first ? 0 : min(na, na_prev);
         // h_{prev} source: the step processed BEFORE t in the forward pass
         const int th = A.reverse ? t + 1 : t - 1;
@@ -336,58 +433,126 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
         long long hp_base = 0;
         bool hp_from_h0 = false;
         if (th >= 0 && th < P.Tmax) {
-            nhp = min(na, slice_rows(P.nact[th], sl, ns));
-            hp_base = P.off[th];
+            nhp = min(na, s_nact[th]);
+            hp_base = s_off[th];
         } else if (!A.reverse && A.h0) {
             nhp = na;
             hp_from_h0 = true;
         }
         const unsigned tagr = P.tag_base + (unsigned)(k - 1), tagw = P.tag_base + (unsigned)k;
         const int parr = (k - 1) & 1, parw = k & 1;
-        const long long row_base = P.off[t];
+        const long long row_base = s_off[t];
         for (int ch = 0; ch * CH < na; ++ch) {
             const int nrows = min(CH, na - ch * CH);
-            // ---- reduce-scatter receive: partial sums of R^T.dgh for my unit, rows (2w, 2w+1), from all 16 CTAs
+            const int ntl = nrows > 8 ? 2 : 1;
+            // ---- reduce-scatter receive: partial sums of R^T.dgh for my unit and rows (w, w+8) from all 16 CTAs.
+            // A word carries rows (2p, 2p+1) of one source; row n lives in pair n>>1, half n&1.
             float pin[2] = {0.f, 0.f};
-            if (ch * CH + 2 * warp < ncarry) {
-                uint2 w[CL];
-                bool ok;
-                const long long t0 = clock64();
-                do {
-                    ok = true;
 #pragma unroll
-                    for (int s = 0; s < CL; ++s) w[s] = ll_load1(Y + yidx(parr, c, s, ch * 8 + warp, lane, npair));
+            for (int e = 0; e < 2; ++e) {
+                const int n = warp + 8 * e;
+                if (n < nrows && ch * CH + n < ncarry) {
+                    const int pair = ch * 8 + (n >> 1);
+                    uint2 w[CL];
+                    bool ok;
+                    const long long t0 = clock64();
+                    const unsigned long long* yb = Y + yidx(parr, c, 0, pair, lane, npair);
+                    const size_t ystr = (size_t)npair * UN;   // stride between sources
+                    do {
+                        ok = true;
 #pragma unroll
-                    for (int s = 0; s < CL; ++s)
-                        if (w[s].y != tagr) ok = false;
-                    POLL_GUARD(t0);
-                } while (!ok);
+                        for (int s = 0; s < CL; ++s) w[s] = ll_load1(yb + s * ystr);
 #pragma unroll
-                for (int s = 0; s < CL; ++s) {
-                    pin[0] += bf16_lo(w[s].x);
-                    pin[1] += bf16_hi(w[s].x);
+                        for (int s = 0; s < CL; ++s)
+                            if (w[s].y != tagr) ok = false;
+                        POLL_GUARD(t0);
+                    } while (!ok);
+#pragma unroll
+                    for (int s = 0; s < CL; ++s) pin[e] += (n & 1) ? bf16_hi(w[s].x) : bf16_lo(w[s].x);
+                }
+            }
+            PROF_MARK(1);   // reduce-scatter receive
+            // ---- prefetch the NEXT step's chunk-0 gate inputs (issued after the poll: the L1TEX queue is in order)
+            bool staged_next = false;
+            if (ch == 0 && k + 1 < P.Tmax && A.hs_h) {
+                const int tq = A.reverse ? t + 1 : t - 1;
+                const int naq = s_nact[tq];
+                if (naq > 0) {
+                    staged_next = true;
+                    const int thq = A.reverse ? tq + 1 : tq - 1;
+                    const int nhq = (thq >= 0 && thq < P.Tmax) ? min(naq, s_nact[thq]) : 0;
+                    const long long rbq = s_off[tq], rbh = (thq >= 0 && thq <= P.Tmax) ? s_off[thq] : 0;
+                    const int pq = (k + 1) & 1;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int n = warp + 8 * e;
+                        if (n < naq) {
+                            const size_t rq = (size_t)(rbq + (long long)n * ns + sl);
+                            float* d = stg + ((pq * CH + n) * 5) * UN + lane;
+                            cp_async4(d, A.dhs + rq * A.ld_dhs + col);
+                            const float* cq = A.cache + rq * 4 * HH + col;
+                            cp_async4(d + UN, cq); cp_async4(d + 2 * UN, cq + HH);
+                            cp_async4(d + 3 * UN, cq + 2 * HH); cp_async4(d + 4 * UN, cq + 3 * HH);
+                            if (n < nhq && !(lane & 1))
+                                cp_async4(stgh + (pq * CH + n) * UN + lane, A.hs_h + (size_t)(rbh + (long long)n * ns + sl) * A.ld_hs + col);
+                        }
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (ch == 0 && staged) {
+                // everything but the group just committed (= this step's inputs, issued one step ago) has landed
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                __syncwarp();
+            }
+            // gate inputs of the BPTT step after next -> L2 (by the warps without a row in this chunk), so that the
+            // cp.async staging issued next step hits L2 and does not hold up the in-order L1TEX queue
+            if (ch == 0 && warp >= nrows && k + 2 < P.Tmax) {
+                const int tn = A.reverse ? t + 2 : t - 2;
+                const int nan = s_nact[tn];
+                const long long rbn = s_off[tn];
+                const int thn = A.reverse ? tn + 1 : tn - 1;
+                const long long rbh = (thn >= 0 && thn < P.Tmax) ? s_off[thn] : -1;
+                const int nidle = NTH / 32 - nrows;
+                for (int n = warp - nrows; n < nan; n += nidle) {
+                    const size_t rown = (size_t)(rbn + (long long)n * ns + sl);
+                    if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cache + rown * 4 * HH + UN * c + lane * HH));
+                    if (lane == 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.dhs + rown * A.ld_dhs + UN * c));
+                    if (lane == 5 && rbh >= 0 && A.hs_h && n < s_nact[thn])
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.hs_h + (size_t)(rbh + (long long)n * ns + sl) * A.ld_hs + UN * c));
                 }
             }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int n = 2 * warp + e;
+                const int n = warp + 8 * e;
+                if (e >= ntl) continue;
                 float dr = 0.f, du = 0.f, dnr = 0.f;
                 if (n < nrows) {
                     const int jl = ch * CH + n;
                     const size_t row = (size_t)(row_base + (long long)jl * ns + sl);
                     const float carry = cs[jl * UN + lane] + (jl < ncarry ? pin[e] : 0.f);
-                    const float dd = carry + A.dhs[row * A.ld_dhs + col];
-                    const float* cp = A.cache + row * 4 * HH + col;
-                    const float r = cp[0], z = cp[HH], nn = cp[2 * HH], qq = cp[3 * HH];
-                    float hp = 0.f;
-                    if (jl < nhp) {
-                        if (hp_from_h0) {
-                            hp = A.h0[(size_t)(jl * ns + sl) * HH + col];
-                        } else {
-                            const size_t rh = (size_t)(hp_base + (long long)jl * ns + sl);
-                            hp = A.hs_f ? A.hs_f[rh * A.ld_hs + col] : __bfloat162float(A.hs_h[rh * A.ld_hs + col]);
+                    float dhv, r, z, nn, qq, hp = 0.f;
+                    if (ch == 0 && staged) {
+                        const float* d = stg + (((k & 1) * CH + n) * 5) * UN + lane;
+                        dhv = d[0]; r = d[UN]; z = d[2 * UN]; nn = d[3 * UN]; qq = d[4 * UN];
+                        if (jl < nhp) {
+                            if (hp_from_h0) hp = A.h0[(size_t)(jl * ns + sl) * HH + col];
+                            else hp = __bfloat162float(stgh[((k & 1) * CH + n) * UN + lane]);
+                        }
+                    } else {
+                        dhv = A.dhs[row * A.ld_dhs + col];
+                        const float* cp = A.cache + row * 4 * HH + col;
+                        r = cp[0]; z = cp[HH]; nn = cp[2 * HH]; qq = cp[3 * HH];
+                        if (jl < nhp) {
+                            if (hp_from_h0) {
+                                hp = A.h0[(size_t)(jl * ns + sl) * HH + col];
+                            } else {
+                                const size_t rh = (size_t)(hp_base + (long long)jl * ns + sl);
+                                hp = A.hs_f ? A.hs_f[rh * A.ld_hs + col] : __bfloat162float(A.hs_h[rh * A.ld_hs + col]);
+                            }
                         }
                     }
+                    const float dd = carry + dhv;
                     const float dn = dd * (1.f - z) * (1.f - nn * nn);
                     du = dd * (hp - nn) * z * (1.f - z);
                     dr = dn * qq * r * (1.f - r);
@@ -404,7 +569,9 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
                 bf16* gp = Gs + n * GS_LD + lane;
                 gp[0] = __float2bfloat16(dr); gp[32] = __float2bfloat16(du); gp[64] = __float2bfloat16(dnr);
             }
+            PROF_MARK(2);   // gate gradients (global loads + stores)
             __syncthreads();
+            PROF_MARK(3);   // barrier 1
             // ---- partial^T[512 x 16] = R_own^T[512 x 96] . dgh_own^T[96 x 16]; this warp: out units 64w..64w+63
             float acc[4][2][4];
 #pragma unroll
@@ -417,6 +584,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
             for (int kt2 = 0; kt2 < 3; ++kt2) {
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
+                    if (nt >= ntl) continue;
                     uint32_t b0, b1, b2, b3;
                     ldmatrix_x4(b0, b1, b2, b3, Gs + (nt * 8 + (lane & 7)) * GS_LD + 32 * kt2 + 8 * (lane >> 3));
 #pragma unroll
@@ -426,50 +594,60 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
                     }
                 }
             }
+            PROF_MARK(4);   // MMA
             // ---- reduce-scatter send: (rows 2q, 2q+1) packed as two bf16 + tag, to the owner of each out unit
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
+                    if (nt >= ntl) continue;
                     const int o0 = 64 * warp + 16 * mt + g4, o1 = o0 + 8;
                     const int pair = ch * 8 + nt * 4 + q4;
                     ll_store(Y + yidx(parw, o0 >> 5, c, pair, o0 & 31, npair), bf16_bits(acc[mt][nt][0]) | (bf16_bits(acc[mt][nt][1]) << 16), tagw);
                     ll_store(Y + yidx(parw, o1 >> 5, c, pair, o1 & 31, npair), bf16_bits(acc[mt][nt][2]) | (bf16_bits(acc[mt][nt][3]) << 16), tagw);
                 }
+            PROF_MARK(5);   // send
             __syncthreads();
+            PROF_MARK(6);   // barrier 2
+            if (ch == 0) staged = staged_next;
         }
         na_prev = na;
         first = false;
         k_last = k;
+        PROF_MARK(7);
     }
+    if (P.prof && tid == 0)
+        for (int i = 0; i < 8; ++i) P.prof[blockIdx.x * 8 + i] = pacc[i];
     // ---- gradient wrt the initial state (decoder: d ex(z)); the last BPTT step of a forward GRU is t = 0
     if (A.dh0 && !A.reverse && k_last >= 0) {
         const unsigned tagr = P.tag_base + (unsigned)k_last;
         const int parr = k_last & 1;
         for (int ch = 0; ch * CH < na_prev; ++ch) {
-            if (ch * CH + 2 * warp >= na_prev) continue;
-            uint2 w[CL];
-            bool ok;
-            const long long t0 = clock64();
-            do {
-                ok = true;
-#pragma unroll
-                for (int s = 0; s < CL; ++s) w[s] = ll_load1(Y + yidx(parr, c, s, ch * 8 + warp, lane, npair));
-#pragma unroll
-                for (int s = 0; s < CL; ++s)
-                    if (w[s].y != tagr) ok = false;
-                POLL_GUARD(t0);
-            } while (!ok);
-            float pin[2] = {0.f, 0.f};
-#pragma unroll
-            for (int s = 0; s < CL; ++s) {
-                pin[0] += bf16_lo(w[s].x);
-                pin[1] += bf16_hi(w[s].x);
-            }
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int jl = ch * CH + 2 * warp + e;
-                if (jl < na_prev) A.dh0[(size_t)(jl * ns + sl) * HH + col] += cs[jl * UN + lane] + pin[e];
+                const int n = warp + 8 * e;
+                const int jl = ch * CH + n;
+                if (jl >= na_prev) continue;
+                const int pair = ch * 8 + (n >> 1);
+                float pin = 0.f;
+#pragma unroll
+                for (int s0 = 0; s0 < CL; s0 += 8) {
+                    uint2 w[8];
+                    bool ok;
+                    const long long t0 = clock64();
+                    do {
+                        ok = true;
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) w[s] = ll_load1(Y + yidx(parr, c, s0 + s, pair, lane, npair));
+#pragma unroll
+                        for (int s = 0; s < 8; ++s)
+                            if (w[s].y != tagr) ok = false;
+                        POLL_GUARD(t0);
+                    } while (!ok);
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) pin += (n & 1) ? bf16_hi(w[s].x) : bf16_lo(w[s].x);
+                }
+                A.dh0[(size_t)(jl * ns + sl) * HH + col] += cs[jl * UN + lane] + pin;
             }
         }
     }
@@ -485,6 +663,7 @@ struct GruMmaCtx {
     unsigned long long* ybuf = nullptr;
     size_t ycap = 0;
     bool attr_set = false;
+    long long* prof = nullptr;   // ARGSIM_GRU_PROF=1: per-phase clocks, printed to stderr after every launch
 };
 
 GruMmaCtx* gru_mma_create(int device) {
@@ -493,8 +672,9 @@ GruMmaCtx* gru_mma_create(int device) {
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
-    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BSL * HS_LD * 2 + 4 * CH * RED_LD * 4 + MAX_BSL * UN * 4));
-    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, CH * GS_LD * 2 + MAX_BSL * UN * 4));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BSL * HS_LD * 2 + 4 * CH * RED_LD * 4 + MAX_BSL * UN * 4 + 2 * 4096 * 4 + 4));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, CH * GS_LD * 2 + MAX_BSL * UN * 4 + 2 * 4096 * 4 + 8 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2));
+    if (getenv("ARGSIM_GRU_PROF")) CUDA_CHECK(cudaMalloc(&c->prof, 160 * 8 * sizeof(long long)));
     return c;
 }
 void gru_mma_destroy(GruMmaCtx* c) {
@@ -504,6 +684,21 @@ void gru_mma_destroy(GruMmaCtx* c) {
     delete c;
 }
 bool gru_mma_supported(int H) { return H == HH; }
+
+static void dump_prof(GruMmaCtx* c, const char* what, int nblocks, int steps, cudaStream_t s) {
+    if (!c->prof) return;
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    std::vector<long long> h(nblocks * 8);
+    CUDA_CHECK(cudaMemcpy(h.data(), c->prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    double avg[8] = {0};
+    for (int b = 0; b < nblocks; ++b)
+        for (int i = 0; i < 8; ++i) avg[i] += (double)h[b * 8 + i] / nblocks;
+    fprintf(stderr, "[gru_prof] %s blocks=%d steps=%d cycles/step:", what, nblocks, steps);
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " p%d=%.0f", i, avg[i] / steps);
+    fprintf(stderr, "  | block0:");
+    for (int i = 0; i < 8; ++i) fprintf(stderr, " %.0f", (double)h[i] / steps);
+    fprintf(stderr, "\n");
+}
 
 static void pick_slices(const GruMmaCtx* c, int ndir, int b, int* ns, int* bslr) {
     const int max_groups = std::max(1, c->num_sms / CL);
@@ -546,11 +741,13 @@ void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& 
     P.off = d_off; P.nact = d_nact; P.xbuf = c->xbuf;
     P.ndir = ndir; P.nslices = ns; P.b = Pl.b; P.Tmax = Pl.Tmax; P.bslr = bslr;
     P.tag_base = (c->launch_id++) << 12;
+    P.prof = c->prof;
     if (c->launch_id >= (1u << 20)) c->launch_id = 1;
-    const size_t smem = (size_t)bslr * HS_LD * 2 + 4 * CH * RED_LD * 4 + (size_t)bslr * UN * 4;
+    const size_t smem = (size_t)bslr * HS_LD * 2 + 4 * CH * RED_LD * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Pl.Tmax + 1) * 4;
     void* args[] = {&P};
     CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gru_mma_fwd, dim3(groups * CL), dim3(NTH), args, smem, s));
     COUNT_LAUNCH();
+    dump_prof(c, ndir == 2 ? "fwd_enc" : "fwd_dec", groups * CL, Pl.Tmax, s);
 }
 
 void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& Pl, const int* d_off, const int* d_nact, int H,
@@ -581,9 +778,11 @@ void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& 
     P.off = d_off; P.nact = d_nact; P.ybuf = c->ybuf;
     P.ndir = ndir; P.nslices = ns; P.b = Pl.b; P.Tmax = Pl.Tmax; P.bslr = bslr;
     P.tag_base = (c->launch_id++) << 12;
+    P.prof = c->prof;
     if (c->launch_id >= (1u << 20)) c->launch_id = 1;
-    const size_t smem = (size_t)CH * GS_LD * 2 + (size_t)bslr * UN * 4;
+    const size_t smem = (size_t)CH * GS_LD * 2 + (size_t)bslr * UN * 4 + (size_t)(2 * Pl.Tmax + 2) * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2;
     void* args[] = {&P};
     CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gru_mma_bwd, dim3(groups * CL), dim3(NTH), args, smem, s));
     COUNT_LAUNCH();
+    dump_prof(c, ndir == 2 ? "bwd_enc" : "bwd_dec", groups * CL, Pl.Tmax, s);
 }

@@ -1,0 +1,149 @@
+"""CPU: pins the oracle (oracle/vae_oracle.py) against everything the reference publishes for the hot
+path and against an independent torch-CPU autograd build of the same graph.
+The reference has no tests and cannot run here (no TensorFlow), so numerical parity of the graph itself
+is UNPINNED; what is pinned: schedule table, init bound, docstring shapes, GRU cell vs torch.nn.GRU."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import SMALL, ragged_batch
+from oracle import vae_oracle as O
+from oracle import vae_torch as T
+
+
+def test_schedule_table_docs_log_org_21_28():
+    """docs/log.org:21-28: rate 0..5 -> keepwd % (sigmoid) and anneal % (tanh) columns."""
+    keep = [50.00, 73.11, 88.08, 95.26, 98.20, 99.33]
+    anneal = [0.00, 76.16, 96.40, 99.51, 99.93, 99.99]
+    for rate, k, a in zip(range(6), keep, anneal):
+        s = O.schedule(rate * 10000, accelerate=1e-4, learn_rate=1e-3, dtype=np.float64)
+        assert round(float(s['rate_keepwd']) * 100, 2) == k
+        assert round(float(s['rate_anneal']) * 100, 2) == a
+    # the code (model.py:80) and the paper (paper.tex:351) agree on lr/(1+sqrt(rate)); first step: 1e-3
+    assert O.schedule(0)['rate_update'] == np.float32(1e-3)
+    assert abs(float(O.schedule(10000, dtype=np.float64)['rate_update']) - 5e-4) < 1e-12
+
+
+def test_init_bound_model_py_109():
+    P = O.init_params(dict(dim_tgt=8192, dim_emb=512, dim_rep=64, rnn_layers=1), seed=0)
+    b = (6 / (8192 / 512 + 1)) ** 0.5
+    assert abs(b - 0.594) < 1e-3                      # docs/log.org:86-88
+    E = P['embed/embedding']
+    assert E.shape == (8192, 512) and np.abs(E).max() <= b and np.abs(E).max() > 0.99 * b
+    assert all(np.all(v == 0) for k, v in P.items() if k.endswith(('bias', 'bW', 'bR')))
+
+
+def test_param_count_matches_survey():
+    n = sum(int(np.prod(s)) for s in O.param_shapes(dim_tgt=8192, dim_emb=512, dim_rep=1024, rnn_layers=3).values())
+    assert n == 24410112
+
+
+def test_trim_and_decoder_io_docstrings():
+    """util_tf.py:40-52 (shapes / dtypes) and model.py:97-106 (lead has bos, gold has eos, mask has len+1)."""
+    x = np.array([[5, 6, 7, 1, 1], [8, 1, 1, 1, 1], [3, 4, 1, 1, 1]], np.int32)
+    xt, m, n = O.trim(np.ascontiguousarray(x.T), 1)
+    assert xt.shape == (3, 3) and m.dtype == bool and n.dtype == np.int32 and n.tolist() == [3, 1, 2]
+    lead, gold, msk = O.decoder_io(xt, m, bos=2, eos=1)
+    assert lead.shape == gold.shape == msk.shape == (4, 3)
+    assert lead[0].tolist() == [2, 2, 2] and gold[-1].tolist() == [1, 1, 1]
+    assert msk.sum(0).tolist() == [4, 2, 3]
+    assert gold[msk].tolist() == [5, 8, 3, 6, 1, 4, 7, 1, 1]      # boolean_mask: time-major row order
+    keep = np.array([[1, 1, 0], [0, 1, 1], [1, 1, 1]])
+    lead2, _, _ = O.decoder_io(xt, m, 2, 1, keep)
+    assert lead2[1].tolist() == [5, 8, 0] and lead2[0].tolist() == [2, 2, 2]   # dropped -> unk(0); bos never dropped
+
+
+def test_gru_cell_matches_torch_library_gru():
+    rng = np.random.default_rng(0)
+    T_, b, I, H = 7, 3, 5, 4
+    x = rng.standard_normal((T_, b, I)); h0 = rng.standard_normal((b, H))
+    W = rng.standard_normal((3 * H, I)); R = rng.standard_normal((3 * H, H))
+    bW = rng.standard_normal(3 * H); bR = rng.standard_normal(3 * H)
+    hs, _ = O.gru_forward(x, h0, W, R, bW, bR)
+    g = torch.nn.GRU(I, H).double()
+    with torch.no_grad():
+        g.weight_ih_l0.copy_(torch.tensor(W)); g.weight_hh_l0.copy_(torch.tensor(R))
+        g.bias_ih_l0.copy_(torch.tensor(bW)); g.bias_hh_l0.copy_(torch.tensor(bR))
+        ref, _ = g(torch.tensor(x), torch.tensor(h0)[None])
+    np.testing.assert_allclose(hs, ref.numpy(), atol=1e-12)
+
+
+def _setup(seed=0, L=2):
+    cfg = dict(SMALL, dim_tgt=64, dim_emb=16, dim_rep=24, rnn_layers=L)
+    P = O.init_params(cfg, seed=seed, bias_scale=0.2)
+    src = ragged_batch(4, 7, cfg['dim_tgt'], seed + 1)
+    tgt = ragged_batch(4, 6, cfg['dim_tgt'], seed + 2)
+    rng = np.random.default_rng(seed + 3)
+    tmax = int((tgt != 1).sum(1).max())
+    keep = (rng.random((tmax, 4)) < 0.7).astype(np.int64)
+    eps = rng.standard_normal((4, cfg['dim_rep']))
+    return cfg, P, src, tgt, keep, eps
+
+
+def test_forward_and_analytic_backward_match_torch_autograd():
+    cfg, P, src, tgt, keep, eps = _setup()
+    o, cache = O.forward(P, cfg, src, tgt, 'train', step=7000, keep=keep, eps=eps)
+    G = O.backward(P, cfg, cache)
+    Pt = T.to_torch(P, torch.float64, requires_grad=True)
+    ot = T.forward(Pt, cfg, src, tgt, 'train', step=7000, keep=keep, eps=eps)
+    for k in ('loss', 'loss_gen', 'loss_kld'):
+        assert abs(float(ot[k]) - float(o[k])) < 1e-5 * abs(float(o[k])), k   # anneal is fp32 in both
+    np.testing.assert_allclose(ot['logits'].detach().numpy(), o['logits'], atol=1e-10)
+    ot['loss'].backward()
+    for k in P:
+        np.testing.assert_allclose(Pt[k].grad.numpy(), G[k], atol=2e-7 * max(1.0, np.abs(G[k]).max()), err_msg=k)
+
+
+def test_backward_finite_differences():
+    cfg, P, src, tgt, keep, eps = _setup(seed=5, L=1)
+    o, cache = O.forward(P, cfg, src, tgt, 'train', step=9000, keep=keep, eps=eps)
+    G = O.backward(P, cfg, cache)
+    rng = np.random.default_rng(0)
+    for k in ('embed/embedding', 'encode/rnn1/bwd/R', 'latent/lv/kernel', 'decode/rnn/l0/bR', 'decode/out/kernel'):
+        idx = tuple(rng.integers(0, s) for s in P[k].shape)
+        if k == 'embed/embedding':
+            idx = (int(src[0, 0]), idx[1])
+        h = 1e-6
+        old = P[k][idx]
+        P[k][idx] = old + h
+        lp = O.forward(P, cfg, src, tgt, 'train', step=9000, keep=keep, eps=eps)[0]['loss']
+        P[k][idx] = old - h
+        lm = O.forward(P, cfg, src, tgt, 'train', step=9000, keep=keep, eps=eps)[0]['loss']
+        P[k][idx] = old
+        fd = (lp - lm) / (2 * h)
+        assert abs(fd - G[k][idx]) < 1e-6 + 1e-4 * abs(fd), (k, fd, G[k][idx])
+
+
+def test_tf_adam_form_and_torch_port_agree():
+    cfg, P, src, tgt, keep, eps = _setup(seed=9)
+    Pt = T.to_torch(P, torch.float64, requires_grad=True)
+    M = {k: np.zeros_like(v) for k, v in P.items()}; V = {k: np.zeros_like(v) for k, v in P.items()}
+    Mt = {k: torch.zeros_like(v) for k, v in Pt.items()}; Vt = {k: torch.zeros_like(v) for k, v in Pt.items()}
+    for it in range(3):
+        O.train_step(P, M, V, cfg, src, tgt, it, keep, eps)
+        T.train_step(Pt, Mt, Vt, cfg, src, tgt, it, keep, eps)
+    for k in P:
+        np.testing.assert_allclose(Pt[k].detach().numpy(), P[k], atol=1e-7, err_msg=k)
+    # epsilon sits OUTSIDE the bias-corrected sqrt (TF-1), unlike torch.optim.Adam
+    p = {'w': np.array([1.0])}; g = {'w': np.array([1e-9])}; m = {'w': np.zeros(1)}; v = {'w': np.zeros(1)}
+    O.adam_tf(p, g, m, v, 1, 1e-3)
+    lr_t = 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    assert abs(p['w'][0] - (1.0 - lr_t * 1e-10 / (np.sqrt(1e-21) + 1e-8))) < 1e-15
+
+
+def test_valid_mode_is_mean_and_padding_invariant():
+    """z = mu outside training (model.py:152-155); extra eos columns change nothing (trim)."""
+    cfg, P, src, tgt, _, _ = _setup(seed=11)
+    o, _ = O.forward(P, cfg, src, tgt, 'valid')
+    assert np.array_equal(o['z'], o['mu'])
+    pad = lambda x: np.concatenate([x, np.ones((len(x), 3), np.int32)], 1)
+    o2, _ = O.forward(P, cfg, pad(src), pad(tgt), 'valid')
+    np.testing.assert_allclose(o2['loss'], o['loss'], rtol=1e-12)
+    assert o2['logits'].shape == o['logits'].shape
+
+
+def test_decode_greedy_shapes():
+    cfg, P, *_ = _setup(seed=13)
+    z = np.random.default_rng(0).standard_normal((3, cfg['dim_rep']))
+    y = O.decode_greedy(P, cfg, z, steps=5)
+    assert y.shape[0] == 3 and y.shape[1] <= 5 and y.dtype == np.int32

@@ -216,7 +216,7 @@ def gru_backward(dhs, dhT, cache, W, R):
 # the graph: src/model.py:75-189
 # --------------------------------------------------------------------------------------
 
-def forward(P, cfg, src, tgt, mode='valid', step=0, keep=None, eps=None, want_prob=False):
+def forward(P, cfg, src, tgt, mode='valid', step=0, keep=None, eps=None, want_prob=False, n_tokens_global=None, b_global=None):
     """P: canonical params (any float dtype).  src,tgt: int32 (b,T) eos-padded, batch-major.
     mode train: `keep` (t-1,b) 0/1 and `eps` (b,R) must be injected (TF's Philox streams
     cannot be reproduced).  Returns (Record-like dict, cache)."""
@@ -286,14 +286,16 @@ def forward(P, cfg, src, tgt, mode='valid', step=0, keep=None, eps=None, want_pr
         o.update(labels=labels,
                  errt_samp=(labels != o['pred']).astype(np.float32), loss_gen_samp=gen_samp,
                  loss_kld_samp=kld_samp)
-        o['errt'] = o['errt_samp'].mean()
-        o['loss_gen'] = gen_samp.mean()
-        o['loss_kld'] = kld_samp.mean()
+        n_norm = len(labels) if n_tokens_global is None else n_tokens_global
+        k_norm = kld_samp.size if b_global is None else b_global * kld_samp.shape[1]
+        o['errt'] = o['errt_samp'].sum() / n_norm
+        o['loss_gen'] = gen_samp.sum() / n_norm
+        o['loss_kld'] = kld_samp.sum() / k_norm
         o['loss'] = o['rate_anneal'] * o['loss_kld'] + o['loss_gen']
         cache = dict(E=E, lead=lead, src_tm=src_tm, len_src=len_src, msk_tgt=msk_tgt, labels=labels,
                      enc=enc_caches, dec=dec_caches, h=h, mu=mu, lv=lv, z=z, eps=eps, hd=hd, ho=ho,
                      logits=logits, lse=lse, scale=scale, hs_shape=hs.shape, emb_tgt_shape=emb_tgt.shape,
-                     mode=mode, anneal=o['rate_anneal'])
+                     mode=mode, anneal=o['rate_anneal'], n_norm=n_norm, k_norm=k_norm)
     return o, cache
 
 
@@ -307,7 +309,7 @@ def backward(P, cfg, cache):
     N = len(labels)
     dlog = np.exp(logits - lse[:, None])
     dlog[np.arange(N), labels] -= 1.0
-    dlog /= N
+    dlog /= cache['n_norm']
     ho, hd = cache['ho'], cache['hd']
     G['embed/embedding'] += scale * (dlog.T @ ho)
     dho = dlog @ (scale * E)
@@ -327,7 +329,7 @@ def backward(P, cfg, cache):
     G['latent/ex/kernel'] += z.T @ dhx
     G['latent/ex/bias'] += dhx.sum(0)
     dz = dhx @ P['latent/ex/kernel'].T
-    a = cache['anneal'] / mu.size
+    a = cache['anneal'] / cache['k_norm']
     dmu = dz + a * mu
     dlv = a * 0.5 * (np.exp(lv) - 1.0)
     if cache['mode'] == 'train':

@@ -1,0 +1,69 @@
+"""CPU, world_size 2 over gloo: the data-parallel host path.  Each rank takes its shard
+(argsim_b200.parallel.shard_batch), normalises with the GLOBAL counts and all-reduces (sum) losses and
+gradients -- exactly what the library does with NCCL -- and the result must equal the single-rank batch."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import SMALL, ragged_batch
+from oracle import vae_oracle as O
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    from argsim_b200 import parallel
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    cfg = dict(SMALL, dim_tgt=64, dim_emb=16, dim_rep=24, rnn_layers=2)
+    P = O.init_params(cfg, seed=0, bias_scale=0.1)
+    src = ragged_batch(10, 9, cfg['dim_tgt'], 1)
+    tgt = ragged_batch(10, 8, cfg['dim_tgt'], 2)
+    rng = np.random.default_rng(3)
+    keep = (rng.random(tgt.shape) < 0.7).astype(np.uint8)
+    eps = rng.standard_normal((10, cfg['dim_rep']))
+    s, t, rows, n_glob, b_glob = parallel.shard_batch(src, tgt, world, rank)
+    assert n_glob == int(((tgt != 1).sum(1) + 1).sum()) and b_glob == 10
+    kr = keep[rows][:, :t.shape[1]]
+    tmax = int((t != 1).sum(1).max())
+    o, cache = O.forward(P, cfg, s, t, 'train', step=5000, keep=kr[:, :tmax].T, eps=eps[rows], n_tokens_global=n_glob, b_global=b_glob)
+    G = O.backward(P, cfg, cache)
+    flat = torch.tensor(np.concatenate([G[k].ravel() for k in sorted(G)] + [[o['loss_gen'], o['loss_kld'], o['errt']]]))
+    dist.all_reduce(flat)      # the one collective of the data path: sum
+    rows_all = [None] * world
+    dist.all_gather_object(rows_all, rows.tolist())
+    if rank == 0:
+        assert sorted(sum(rows_all, [])) == list(range(10))      # shards partition the batch
+        tm = int((tgt != 1).sum(1).max())
+        of, cf = O.forward(P, cfg, src, tgt, 'train', step=5000, keep=keep[:, :tm].T, eps=eps)
+        Gf = O.backward(P, cfg, cf)
+        ref = np.concatenate([Gf[k].ravel() for k in sorted(Gf)] + [[of['loss_gen'], of['loss_kld'], of['errt']]])
+        q.put(float(np.abs(flat.numpy() - ref).max() / np.abs(ref).max()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shards_reduce_to_the_full_batch():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = q.get(timeout=120)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert err < 1e-10, err

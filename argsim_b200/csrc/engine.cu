@@ -48,6 +48,9 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     }
     use_mma = is_bf16 && gru_mma_supported(H) && !(c.flags & 4);
     for (auto& s : st) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& s : sw) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    if (const char* ev = getenv("ARGSIM_DEC_SEG")) dec_seg = atoi(ev);
+    if (L > 8) dec_seg = 0;
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_bucket, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
     if (use_mma) mma = gru_mma_create(c.device);
@@ -121,6 +124,8 @@ Engine::~Engine() {
     for (auto& k : ktimers) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
     cudaEventDestroy(ev_bucket); cudaEventDestroy(ev_comm);
     for (auto& s : st) if (s) cudaStreamDestroy(s);
+    for (auto& s : sw) if (s) cudaStreamDestroy(s);
+    for (auto& e : evpool) cudaEventDestroy(e);
 }
 
 const ParamInfo& Engine::pinfo(const std::string& name) const {
@@ -207,15 +212,29 @@ Mat Engine::both(long long rows, int cols) {
 }
 
 void Engine::gemm(const Mat& A, int a_mn, const Mat& B, int b_mn, const Mat& C, long long M, int N, long long K, float alpha,
-                  const float* bias, int accumulate) {
+                  const float* bias, int accumulate, cudaStream_t q) {
     if (arena.dry || M <= 0 || N <= 0) return;
+    if (!q) q = st[0];
     if (use_tc) {
         if (!A.h || !B.h) throw std::runtime_error("gemm: bf16 operand view missing (internal error)");
-        gemm_tc(A.h, A.ld, a_mn, B.h, B.ld, b_mn, C.f, C.h, C.ld, (int)M, N, (int)K, alpha, bias, accumulate, st[0]);
+        gemm_tc(A.h, A.ld, a_mn, B.h, B.ld, b_mn, C.f, C.h, C.ld, (int)M, N, (int)K, alpha, bias, accumulate, q);
     } else {
         if (!A.f || !B.f) throw std::runtime_error("gemm: fp32 operand view missing (internal error)");
-        gemm_simt(A.f, A.ld, a_mn, B.f, B.ld, b_mn, C.f, C.ld, (int)M, N, (int)K, alpha, bias, accumulate, C.h, st[0]);
+        gemm_simt(A.f, A.ld, a_mn, B.f, B.ld, b_mn, C.f, C.ld, (int)M, N, (int)K, alpha, bias, accumulate, C.h, q);
     }
+}
+
+cudaEvent_t Engine::next_event() {
+    if (evcount == evpool.size()) {
+        cudaEvent_t e;
+        CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        evpool.push_back(e);
+    }
+    return evpool[evcount++];
+}
+// the decoder's layers run as a wavefront over time segments when the persistent kernel is in use
+bool Engine::dec_wavefront(const SeqPlan& Dp) const {
+    return use_mma && L > 1 && dec_seg > 0 && Dp.Tmax > dec_seg && gru_mma_fits(mma, 1, Dp.b);
 }
 void Engine::colsum(const Mat& A, long long rows, int cols, float* out) {
     if (arena.dry) return;
@@ -379,7 +398,7 @@ void Engine::ensure_arena(int mode) {
 
 void Engine::run_device(int mode, bool apply_update) {
     ensure_arena(mode);
-    pcount = 0; kcount = 0;
+    pcount = 0; kcount = 0; evcount = 0;
     program(mode, apply_update);
 }
 
@@ -465,23 +484,69 @@ void Engine::program(int mode, bool apply_update) {
     std::vector<float*> decCache(L, nullptr);
     decY[0] = act(N, D);
     gather_embed(dp.ids_lead, N, decY[0]);
+    std::vector<Mat> decGX(L);
     for (int j = 0; j < L; ++j) {
-        const std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
-        Mat GX = f32(N, 3 * H);
-        gemm(decY[j], 0, pmat(pre + "W"), 0, GX, N, 3 * H, D, 1.f, p + pinfo(pre + "bW").off, 0);
-        Mat Y = act(N, H);
+        decGX[j] = f32(N, 3 * H);
+        decY[j + 1] = act(N, H);
         if (train) decCache[j] = (float*)arena.alloc(sizeof(float) * N * 4 * H);
+    }
+    auto dec_fwd_args = [&](int j) {
+        const std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
         GruFwdArgs a;
-        a.gx = GX.f; a.ld_gx = 3 * H;
+        a.gx = decGX[j].f; a.ld_gx = 3 * H;
         a.R_f = p + pinfo(pre + "R").off;
         a.R_h = ph ? ph + pinfo(pre + "R").off : nullptr;
         a.bR = p + pinfo(pre + "bR").off;
         a.h0 = hx_sorted.f;
-        a.hs_f = Y.f; a.hs_h = Y.h; a.ld_hs = H;
+        a.hs_f = decY[j + 1].f; a.hs_h = decY[j + 1].h; a.ld_hs = H;
         a.cache = decCache[j];
         a.reverse = 0;
-        gru_fwd(&a, 1, Dp, dp.dec_off, dp.dec_nact);
-        decY[j + 1] = Y;
+        return a;
+    };
+    const bool wave = dec_wavefront(Dp);
+    const int nseg = wave ? (Dp.Tmax + dec_seg - 1) / dec_seg : 1;
+    if (!wave) {
+        for (int j = 0; j < L; ++j) {
+            const std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
+            gemm(decY[j], 0, pmat(pre + "W"), 0, decGX[j], N, 3 * H, D, 1.f, p + pinfo(pre + "bW").off, 0);
+            GruFwdArgs a = dec_fwd_args(j);
+            gru_fwd(&a, 1, Dp, dp.dec_off, dp.dec_nact);
+        }
+    } else {
+        // Wavefront: layer l works on time segment s while layer l-1 already runs segment s+1 (one stream per
+        // layer, events between them).  The chain shrinks from L*T to about T + (L-1)*segment serial steps.
+        float* hT[8][2];
+        for (int j = 0; j < L; ++j)
+            for (int q = 0; q < 2; ++q) hT[j][q] = (float*)arena.alloc(sizeof(float) * b * H);
+        gemm(decY[0], 0, pmat("decode/rnn/l0/W"), 0, decGX[0], N, 3 * H, D, 1.f, p + pinfo("decode/rnn/l0/bW").off, 0);
+        if (!arena.dry) {
+            kbegin("k:gru_fwd_dec");
+            cudaEvent_t fork = next_event();
+            CUDA_CHECK(cudaEventRecord(fork, s));
+            for (int j = 0; j < L; ++j) CUDA_CHECK(cudaStreamWaitEvent(sw[j], fork, 0));
+            std::vector<cudaEvent_t> done(L * nseg);
+            for (int sg = 0; sg < nseg; ++sg) {
+                const int t0 = sg * dec_seg, tl = std::min(dec_seg, Dp.Tmax - t0);
+                const long long r0 = Dp.off[t0], nr = Dp.off[t0 + tl] - r0;
+                for (int j = 0; j < L; ++j) {
+                    cudaStream_t q = sw[j];
+                    const std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
+                    if (j > 0) {
+                        CUDA_CHECK(cudaStreamWaitEvent(q, done[(j - 1) * nseg + sg], 0));
+                        gemm(decY[j].rowslice(r0, nr), 0, pmat(pre + "W"), 0, decGX[j].rowslice(r0, nr), nr, 3 * H, D, 1.f,
+                             p + pinfo(pre + "bW").off, 0, q);
+                    }
+                    GruFwdArgs a = dec_fwd_args(j);
+                    if (sg > 0) a.h0 = hT[j][(sg - 1) & 1];
+                    a.hT = (sg + 1 < nseg) ? hT[j][sg & 1] : nullptr;
+                    gru_mma_fwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j);
+                    done[j * nseg + sg] = next_event();
+                    CUDA_CHECK(cudaEventRecord(done[j * nseg + sg], q));
+                }
+            }
+            for (int j = 0; j < L; ++j) CUDA_CHECK(cudaStreamWaitEvent(s, done[j * nseg + nseg - 1], 0));
+            kend();
+        }
     }
     Mat HO = act(N, D);
     gemm(decY[L], 0, pmat("decode/out/kernel"), 1, HO, N, D, D, 1.f, p + pinfo("decode/out/bias").off, 0);
@@ -536,14 +601,13 @@ void Engine::program(int mode, bool apply_update) {
     bucket_lo = pinfo("decode/out/bias").off + align_up(D, 64);
 
     // ---------------- backward: decoder GRUs (BPTT), dh0 of all layers sums into d ex(z)
-    Mat dGX = act(N, 3 * H), dGH = act(N, 3 * H), HP = act(N, H);
-    Mat dYn = f32(N, D);
     Mat dhx_sorted = f32(b, H);
     RUN(CUDA_CHECK(cudaMemsetAsync(dhx_sorted.f, 0, sizeof(float) * b * H, s)));
-    for (int j = L - 1; j >= 0; --j) {
+    Mat dYn = f32(N, D);
+    auto dec_bwd_args = [&](int j, const Mat& dhs, const Mat& dGX, const Mat& dGH, const Mat& HP, float* dh0) {
         const std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
         GruBwdArgs a;
-        a.dhs = dY.f; a.ld_dhs = dY.ld;
+        a.dhs = dhs.f; a.ld_dhs = dhs.ld;
         a.hs_f = decY[j + 1].f; a.hs_h = decY[j + 1].h; a.ld_hs = H;
         a.h0 = hx_sorted.f;
         a.cache = decCache[j];
@@ -551,18 +615,80 @@ void Engine::program(int mode, bool apply_update) {
         a.R_h = ph ? ph + pinfo(pre + "R").off : nullptr;
         a.dgx_f = dGX.f; a.dgx_h = dGX.h; a.dgh_f = dGH.f; a.dgh_h = dGH.h; a.ld_dg = 3 * H;
         a.hp_f = HP.f; a.hp_h = HP.h; a.ld_hp = H;
-        a.dh0 = dhx_sorted.f;
+        a.dh0 = dh0;
         a.reverse = 0;
-        gru_bwd(&a, 1, Dp, dp.dec_off, dp.dec_nact);
+        return a;
+    };
+    auto dec_wgrad = [&](int j, const Mat& dGX, const Mat& dGH, const Mat& HP) {
+        const std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
         gemm(dGX, 1, decY[j], 1, gmat(pre + "W"), 3 * H, D, N, 1.f, nullptr, 1);
         gemm(dGH, 1, HP, 1, gmat(pre + "R"), 3 * H, H, N, 1.f, nullptr, 1);
         colsum(dGX, N, 3 * H, gptr(pre + "bW"));
         colsum(dGH, N, 3 * H, gptr(pre + "bR"));
-        gemm(dGX, 0, pmat(pre + "W"), 1, dYn, N, D, 3 * H, 1.f, nullptr, 0);
+    };
+    if (!wave) {
+        Mat dGX = act(N, 3 * H), dGH = act(N, 3 * H), HP = act(N, H);
+        for (int j = L - 1; j >= 0; --j) {
+            const std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
+            GruBwdArgs a = dec_bwd_args(j, dY, dGX, dGH, HP, dhx_sorted.f);
+            gru_bwd(&a, 1, Dp, dp.dec_off, dp.dec_nact);
+            dec_wgrad(j, dGX, dGH, HP);
+            gemm(dGX, 0, pmat(pre + "W"), 1, dYn, N, D, 3 * H, 1.f, nullptr, 0);
+            std::swap(dY, dYn);
+            const size_t end = pinfo(pre + "bR").off + align_up(3 * H, 64);
+            allreduce_bucket(bucket_lo, end);
+            bucket_lo = end;
+        }
+    } else {
+        // Wavefront in reverse: layer l's BPTT over segment s starts as soon as layer l+1 has produced the
+        // gradient of its inputs for that segment (dgrad GEMM per segment on layer l's stream).
+        std::vector<Mat> dGXl(L), dGHl(L), HPl(L), dYl(L);
+        float *dh0l[8], *carry[8][2];
+        for (int j = 0; j < L; ++j) {
+            dGXl[j] = act(N, 3 * H); dGHl[j] = act(N, 3 * H); HPl[j] = act(N, H);
+            dYl[j] = (j == L - 1) ? dY : f32(N, D);
+            dh0l[j] = (float*)arena.alloc(sizeof(float) * b * H * 3);
+            carry[j][0] = dh0l[j] + (size_t)b * H;
+            carry[j][1] = dh0l[j] + (size_t)2 * b * H;
+            RUN(CUDA_CHECK(cudaMemsetAsync(dh0l[j], 0, sizeof(float) * b * H * 3, s)));
+        }
+        if (!arena.dry) {
+            kbegin("k:gru_bwd_dec");
+            cudaEvent_t fork = next_event();
+            CUDA_CHECK(cudaEventRecord(fork, s));
+            for (int j = 0; j < L; ++j) CUDA_CHECK(cudaStreamWaitEvent(sw[j], fork, 0));
+            std::vector<cudaEvent_t> done(L * nseg);
+            for (int sg = nseg - 1; sg >= 0; --sg) {
+                const int t0 = sg * dec_seg, tl = std::min(dec_seg, Dp.Tmax - t0);
+                const long long r0 = Dp.off[t0], nr = Dp.off[t0 + tl] - r0;
+                for (int j = L - 1; j >= 0; --j) {
+                    cudaStream_t q = sw[j];
+                    if (j < L - 1) {
+                        const std::string up = "decode/rnn/l" + std::to_string(j + 1) + "/";
+                        CUDA_CHECK(cudaStreamWaitEvent(q, done[(j + 1) * nseg + sg], 0));
+                        gemm(dGXl[j + 1].rowslice(r0, nr), 0, pmat(up + "W"), 1, dYl[j].rowslice(r0, nr), nr, D, 3 * H, 1.f, nullptr, 0, q);
+                    }
+                    GruBwdArgs a = dec_bwd_args(j, dYl[j], dGXl[j], dGHl[j], HPl[j], dh0l[j]);
+                    a.dh_in = (sg + 1 < nseg) ? carry[j][(sg + 1) & 1] : nullptr;
+                    a.dh_out = (sg > 0) ? carry[j][sg & 1] : nullptr;
+                    gru_mma_bwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j);
+                    done[j * nseg + sg] = next_event();
+                    CUDA_CHECK(cudaEventRecord(done[j * nseg + sg], q));
+                }
+            }
+            for (int j = 0; j < L; ++j) CUDA_CHECK(cudaStreamWaitEvent(s, done[j * nseg + 0], 0));
+            kend();
+        }
+        for (int j = L - 1; j >= 0; --j) {
+            const std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
+            dec_wgrad(j, dGXl[j], dGHl[j], HPl[j]);
+            RUN(launch_row_scatter(dh0l[j], H, dhx_sorted.f, H, nullptr, b, H, 1, s));
+            const size_t end = pinfo(pre + "bR").off + align_up(3 * H, 64);
+            allreduce_bucket(bucket_lo, end);
+            bucket_lo = end;
+        }
+        gemm(dGXl[0], 0, pmat("decode/rnn/l0/W"), 1, dYn, N, D, 3 * H, 1.f, nullptr, 0);
         std::swap(dY, dYn);
-        const size_t end = pinfo(pre + "bR").off + align_up(3 * H, 64);
-        allreduce_bucket(bucket_lo, end);
-        bucket_lo = end;
     }
     // d emb_tgt -> IndexedSlices part of dE (model.py:111)
     RUN(launch_embed_scatter_add(dp.ids_lead, N, dY.f, D, D, gE.f, s));

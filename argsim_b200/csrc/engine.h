@@ -83,6 +83,12 @@ public:
 
 private:
     cudaStream_t st[3] = {nullptr, nullptr, nullptr};  // main, second GRU direction, comm
+    cudaStream_t sw[8] = {};                            // decoder wavefront: one stream per layer
+    std::vector<cudaEvent_t> evpool;
+    size_t evcount = 0;
+    cudaEvent_t next_event();
+    int dec_seg = 64;                                   // time steps per wavefront segment (0 = off)
+    bool dec_wavefront(const SeqPlan& Dp) const;
     cudaEvent_t ev_bucket = nullptr, ev_comm = nullptr;
     Arena arena;
     GruMmaCtx* mma = nullptr;
@@ -144,7 +150,7 @@ private:
     Mat f32(long long rows, int cols);
     Mat both(long long rows, int cols);
     void gemm(const Mat& A, int a_mn, const Mat& B, int b_mn, const Mat& C, long long M, int N, long long K, float alpha,
-              const float* bias, int accumulate);
+              const float* bias, int accumulate, cudaStream_t q = nullptr);
     void colsum(const Mat& A, long long rows, int cols, float* out);
     void gather_embed(const int* ids, long long n, const Mat& out);
     void gru_fwd(GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact);

@@ -40,26 +40,29 @@ constexpr int MAX_BSL = 128;
 struct FwdDirP {
     const float* gx; const bf16* R; const float* bR; const float* h0;
     float* hs_f; bf16* hs_h; float* cache;
+    float* hT;    // (b,H) fp32 state after the last step of the segment (sorted order) or null
     int ld_gx, ld_hs, reverse;
 };
 struct FwdP {
     FwdDirP dir[2];
     const int* off; const int* nact;
     unsigned long long* xbuf;
-    int ndir, nslices, b, Tmax, bslr;
+    int ndir, nslices, b, Ttot, t0, Tseg, bslr;   // steps [t0, t0+Tseg) of a plan with Ttot steps
     unsigned tag_base;
     long long* prof;   // debug: per-phase clock totals of thread 0 of every CTA (8 slots each) or null
 };
 struct BwdDirP {
     const float* dhs; const float* hs_f; const bf16* hs_h; const float* h0; const float* cache; const bf16* R;
     float* dgx_f; bf16* dgx_h; float* dgh_f; bf16* dgh_h; float* hp_f; bf16* hp_h; float* dh0;
+    const float* dh_in;   // (b,H) gradient wrt the state AFTER the segment's last step (from the later segment) or null
+    float* dh_out;        // (b,H) gradient wrt the state BEFORE the segment's first step, overwritten (t0 > 0) or null
     int ld_dhs, ld_hs, ld_dg, ld_hp, reverse;
 };
 struct BwdP {
     BwdDirP dir[2];
     const int* off; const int* nact;
     unsigned long long* ybuf;
-    int ndir, nslices, b, Tmax, bslr;
+    int ndir, nslices, b, Ttot, t0, Tseg, bslr;
     unsigned tag_base;
     long long* prof;
 };
@@ -105,6 +108,8 @@ __device__ __forceinline__ float tanh_fast(float x) { return __fdividef(2.0f, 1.
 __device__ __forceinline__ int slice_rows(int nat, int sl, int ns) { return nat > sl ? (nat - sl + ns - 1) / ns : 0; }
 // a peer that never shows up must not hang the GPU: ~2 s, then trap
 #define POLL_GUARD(t0) if (clock64() - (t0) > 4000000000LL) __trap()
+#define NA(t) s_nact[(t) - P.t0 + 1]
+#define OFF(t) s_off[(t) - P.t0 + 1]
 #define PROF_MARK(i) do { if (P.prof && tid == 0) { const long long now_ = clock64(); pacc[i] += now_ - plast; plast = now_; } } while (0)
 
 // =========================================================================================
@@ -115,11 +120,14 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
     bf16* Hs = reinterpret_cast<bf16*>(sm);                                   // [bslr][HS_LD]  h_{t-1}, all 512 units
     float* red = reinterpret_cast<float*>(sm + (size_t)P.bslr * HS_LD * 2);  // [4][CH][RED_LD] k-quarter partial sums
     float* hst = red + 4 * CH * RED_LD;                                       // [bslr][UN]     fp32 state of the own units
-    int* s_nact = reinterpret_cast<int*>(hst + (size_t)P.bslr * UN);          // [Tmax]   step tables: a global load per
-    int* s_off = s_nact + P.Tmax;                                             // [Tmax+1] step would sit on the critical path
+    int* s_nact = reinterpret_cast<int*>(hst + (size_t)P.bslr * UN);          // [Tseg+2] step tables: a global load per
+    int* s_off = s_nact + P.Tseg + 2;                                         // [Tseg+2] step would sit on the critical path
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < P.Tmax; i += NTH) s_nact[i] = slice_rows(P.nact[i], blockIdx.x / CL % P.nslices, P.nslices);
-    for (int i = tid; i <= P.Tmax; i += NTH) s_off[i] = P.off[i];
+    for (int i = tid; i < P.Tseg + 2; i += NTH) {
+        const int tt = P.t0 - 1 + i;
+        s_nact[i] = (tt >= 0 && tt < P.Ttot) ? slice_rows(P.nact[tt], blockIdx.x / CL % P.nslices, P.nslices) : 0;
+        s_off[i] = (tt >= 0 && tt <= P.Ttot) ? P.off[tt] : 0;
+    }
     const int grp = blockIdx.x / CL, c = blockIdx.x % CL;
     const int ns = P.nslices, d = grp / ns, sl = grp % ns;
     const FwdDirP& A = P.dir[d];
@@ -158,15 +166,15 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
     float gxn[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long plast = clock64();
-    for (int k = 0; k < P.Tmax; ++k) {
-        const int t = A.reverse ? P.Tmax - 1 - k : k;
-        const int na = s_nact[t];
+    for (int k = 0; k < P.Tseg; ++k) {
+        const int t = A.reverse ? P.t0 + P.Tseg - 1 - k : P.t0 + k;
+        const int na = NA(t);
         if (na == 0) {
             if (A.reverse) continue;
             break;
         }
         PROF_MARK(0);
-        const long long row_base = s_off[t];
+        const long long row_base = OFF(t);
         // gx of chunk 0 (independent of h) was loaded one step ahead into gxn; the first active step loads it here
         float gx0[2][3];
 #pragma unroll
@@ -275,12 +283,12 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
             // issued two steps ago; they complete under the HMMAs / the partial-sum barrier.
             if (ch == 0) {
                 have_next = false;
-                if (k + 1 < P.Tmax) {
+                if (k + 1 < P.Tseg) {
                     const int tn = A.reverse ? t - 1 : t + 1;
-                    const int nan = s_nact[tn];
+                    const int nan = NA(tn);
                     if (nan > 0) {
                         have_next = true;
-                        const long long rbn = s_off[tn];
+                        const long long rbn = OFF(tn);
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
                             const int n = warp + 8 * e;
@@ -307,10 +315,10 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
             PROF_MARK(4);   // barrier 2
             // gx rows of the step after next -> L2.  A prefetch costs its issuing warp ~100 cycles, so it is done by
             // the warps that have no row to finish in this chunk (all of them idle otherwise until barrier 3)
-            if (ch == 0 && warp >= nrows && k + 2 < P.Tmax) {
+            if (ch == 0 && warp >= nrows && k + 2 < P.Tseg) {
                 const int tn = A.reverse ? t - 2 : t + 2;
-                const int nan = s_nact[tn];
-                const long long rbn = s_off[tn];
+                const int nan = NA(tn);
+                const long long rbn = OFF(tn);
                 const int nidle = NTH / 32 - nrows;
                 for (int n = warp - nrows; n < nan; n += nidle) {
                     const float* gp = A.gx + (size_t)(rbn + (long long)n * ns + sl) * A.ld_gx + UN * c;
@@ -356,6 +364,13 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
         na_prev = na;
         PROF_MARK(7);
     }
+    if (A.hT) {   // state handed to the next time segment of this layer
+        __syncthreads();
+        for (int i = tid; i < nloc * UN; i += NTH) {
+            const int jl = i >> 5, u = i & 31;
+            A.hT[(size_t)(jl * ns + sl) * HH + UN * c + u] = hst[i];
+        }
+    }
     if (P.prof && tid == 0)
         for (int i = 0; i < 8; ++i) P.prof[blockIdx.x * 8 + i] = pacc[i];
 }
@@ -372,14 +387,17 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
     bf16* Gs = reinterpret_cast<bf16*>(sm);                               // [CH][GS_LD]  own dgh columns of the chunk
     float* cs = reinterpret_cast<float*>(sm + CH * GS_LD * 2);           // [bslr][UN]   d*u carried to the next step
     int* s_nact = reinterpret_cast<int*>(cs + (size_t)P.bslr * UN);     // [Tmax], [Tmax+1]: step tables in smem
-    int* s_off = s_nact + P.Tmax;
+    int* s_off = s_nact + P.Tseg + 2;
     // cp.async landing zone for the NEXT step's gate inputs of chunk 0 (dhs, r, u, n, q: fp32; h_prev: bf16),
     // double buffered by step parity: their HBM latency is paid one step ahead, off the serial chain
-    float* stg = reinterpret_cast<float*>(s_off + P.Tmax + 1 + ((P.Tmax & 1) ? 0 : 1));   // [2][CH][5][UN], 8-byte aligned
+    float* stg = reinterpret_cast<float*>(s_off + P.Tseg + 2);   // [2][CH][5][UN]
     bf16* stgh = reinterpret_cast<bf16*>(stg + 2 * CH * 5 * UN);                            // [2][CH][UN]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < P.Tmax; i += NTH) s_nact[i] = slice_rows(P.nact[i], blockIdx.x / CL % P.nslices, P.nslices);
-    for (int i = tid; i <= P.Tmax; i += NTH) s_off[i] = P.off[i];
+    for (int i = tid; i < P.Tseg + 2; i += NTH) {
+        const int tt = P.t0 - 1 + i;
+        s_nact[i] = (tt >= 0 && tt < P.Ttot) ? slice_rows(P.nact[tt], blockIdx.x / CL % P.nslices, P.nslices) : 0;
+        s_off[i] = (tt >= 0 && tt <= P.Ttot) ? P.off[tt] : 0;
+    }
     const int grp = blockIdx.x / CL, c = blockIdx.x % CL;
     const int ns = P.nslices, d = grp / ns, sl = grp % ns;
     const BwdDirP& A = P.dir[d];
@@ -407,7 +425,8 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
     }
     const int col = UN * c + lane;
     const int nloc = slice_rows(P.b, sl, ns);
-    for (int i = tid; i < nloc * UN; i += NTH) cs[i] = 0.f;
+    for (int i = tid; i < nloc * UN; i += NTH)
+        cs[i] = A.dh_in ? A.dh_in[(size_t)((i >> 5) * ns + sl) * HH + UN * c + (i & 31)] : 0.f;
     const size_t ypar = (size_t)CL * CL * npair * UN;
     unsigned long long* Y = P.ybuf + (size_t)grp * 2 * ypar;
     __syncthreads();
@@ -418,9 +437,9 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
     int k_last = -1;
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long plast = clock64();
-    for (int k = 0; k < P.Tmax; ++k) {
-        const int t = A.reverse ? k : P.Tmax - 1 - k;
-        const int na = s_nact[t];
+    for (int k = 0; k < P.Tseg; ++k) {
+        const int t = A.reverse ? P.t0 + k : P.t0 + P.Tseg - 1 - k;
+        const int na = NA(t);
         if (na == 0) {
             if (A.reverse) break;
             continue;
@@ -432,16 +451,16 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
         int nhp = 0;
         long long hp_base = 0;
         bool hp_from_h0 = false;
-        if (th >= 0 && th < P.Tmax) {
-            nhp = min(na, s_nact[th]);
-            hp_base = s_off[th];
+        if (th >= 0 && th < P.Ttot) {
+            nhp = min(na, NA(th));
+            hp_base = OFF(th);
         } else if (!A.reverse && A.h0) {
             nhp = na;
             hp_from_h0 = true;
         }
         const unsigned tagr = P.tag_base + (unsigned)(k - 1), tagw = P.tag_base + (unsigned)k;
         const int parr = (k - 1) & 1, parw = k & 1;
-        const long long row_base = s_off[t];
+        const long long row_base = OFF(t);
         for (int ch = 0; ch * CH < na; ++ch) {
             const int nrows = min(CH, na - ch * CH);
             const int ntl = nrows > 8 ? 2 : 1;
@@ -474,14 +493,14 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
             PROF_MARK(1);   // reduce-scatter receive
             // ---- prefetch the NEXT step's chunk-0 gate inputs (issued after the poll: the L1TEX queue is in order)
             bool staged_next = false;
-            if (ch == 0 && k + 1 < P.Tmax && A.hs_h) {
+            if (ch == 0 && k + 1 < P.Tseg && A.hs_h) {
                 const int tq = A.reverse ? t + 1 : t - 1;
-                const int naq = s_nact[tq];
+                const int naq = NA(tq);
                 if (naq > 0) {
                     staged_next = true;
                     const int thq = A.reverse ? tq + 1 : tq - 1;
-                    const int nhq = (thq >= 0 && thq < P.Tmax) ? min(naq, s_nact[thq]) : 0;
-                    const long long rbq = s_off[tq], rbh = (thq >= 0 && thq <= P.Tmax) ? s_off[thq] : 0;
+                    const int nhq = (thq >= 0 && thq < P.Ttot) ? min(naq, NA(thq)) : 0;
+                    const long long rbq = OFF(tq), rbh = (thq >= 0 && thq <= P.Ttot) ? OFF(thq) : 0;
                     const int pq = (k + 1) & 1;
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
@@ -507,18 +526,18 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
             }
             // gate inputs of the BPTT step after next -> L2 (by the warps without a row in this chunk), so that the
             // cp.async staging issued next step hits L2 and does not hold up the in-order L1TEX queue
-            if (ch == 0 && warp >= nrows && k + 2 < P.Tmax) {
+            if (ch == 0 && warp >= nrows && k + 2 < P.Tseg) {
                 const int tn = A.reverse ? t + 2 : t - 2;
-                const int nan = s_nact[tn];
-                const long long rbn = s_off[tn];
+                const int nan = NA(tn);
+                const long long rbn = OFF(tn);
                 const int thn = A.reverse ? tn + 1 : tn - 1;
-                const long long rbh = (thn >= 0 && thn < P.Tmax) ? s_off[thn] : -1;
+                const long long rbh = (thn >= 0 && thn < P.Ttot) ? OFF(thn) : -1;
                 const int nidle = NTH / 32 - nrows;
                 for (int n = warp - nrows; n < nan; n += nidle) {
                     const size_t rown = (size_t)(rbn + (long long)n * ns + sl);
                     if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cache + rown * 4 * HH + UN * c + lane * HH));
                     if (lane == 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.dhs + rown * A.ld_dhs + UN * c));
-                    if (lane == 5 && rbh >= 0 && A.hs_h && n < s_nact[thn])
+                    if (lane == 5 && rbh >= 0 && A.hs_h && n < NA(thn))
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.hs_h + (size_t)(rbh + (long long)n * ns + sl) * A.ld_hs + UN * c));
                 }
             }
@@ -619,7 +638,8 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
     if (P.prof && tid == 0)
         for (int i = 0; i < 8; ++i) P.prof[blockIdx.x * 8 + i] = pacc[i];
     // ---- gradient wrt the initial state (decoder: d ex(z)); the last BPTT step of a forward GRU is t = 0
-    if (A.dh0 && !A.reverse && k_last >= 0) {
+    float* const dh_dst = (P.t0 == 0) ? A.dh0 : A.dh_out;
+    if (dh_dst && !A.reverse && k_last >= 0) {
         const unsigned tagr = P.tag_base + (unsigned)k_last;
         const int parr = k_last & 1;
         for (int ch = 0; ch * CH < na_prev; ++ch) {
@@ -647,7 +667,9 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
 #pragma unroll
                     for (int s = 0; s < 8; ++s) pin += (n & 1) ? bf16_hi(w[s].x) : bf16_lo(w[s].x);
                 }
-                A.dh0[(size_t)(jl * ns + sl) * HH + col] += cs[jl * UN + lane] + pin;
+                const size_t di = (size_t)(jl * ns + sl) * HH + col;
+                const float val = cs[jl * UN + lane] + pin;
+                dh_dst[di] = (P.t0 == 0) ? dh_dst[di] + val : val;
             }
         }
     }
@@ -658,10 +680,11 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
 struct GruMmaCtx {
     int device = 0, num_sms = 148;
     unsigned launch_id = 1;
-    unsigned long long* xbuf = nullptr;
-    size_t xcap = 0;
-    unsigned long long* ybuf = nullptr;
-    size_t ycap = 0;
+    static constexpr int NSLOT = 4;
+    unsigned long long* xbuf[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+    size_t xcap[NSLOT] = {0, 0, 0, 0};
+    unsigned long long* ybuf[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+    size_t ycap[NSLOT] = {0, 0, 0, 0};
     bool attr_set = false;
     long long* prof = nullptr;   // ARGSIM_GRU_PROF=1: per-phase clocks, printed to stderr after every launch
 };
@@ -672,15 +695,18 @@ GruMmaCtx* gru_mma_create(int device) {
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
-    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BSL * HS_LD * 2 + 4 * CH * RED_LD * 4 + MAX_BSL * UN * 4 + 2 * 4096 * 4 + 4));
-    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, CH * GS_LD * 2 + MAX_BSL * UN * 4 + 2 * 4096 * 4 + 8 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BSL * HS_LD * 2 + 4 * CH * RED_LD * 4 + MAX_BSL * UN * 4 + 2 * 4100 * 4));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, CH * GS_LD * 2 + MAX_BSL * UN * 4 + 2 * 4100 * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2));
     if (getenv("ARGSIM_GRU_PROF")) CUDA_CHECK(cudaMalloc(&c->prof, 160 * 8 * sizeof(long long)));
     return c;
 }
 void gru_mma_destroy(GruMmaCtx* c) {
     if (!c) return;
-    cudaFree(c->xbuf);
-    cudaFree(c->ybuf);
+    for (int i = 0; i < GruMmaCtx::NSLOT; ++i) {
+        cudaFree(c->xbuf[i]);
+        cudaFree(c->ybuf[i]);
+    }
+    cudaFree(c->prof);
     delete c;
 }
 bool gru_mma_supported(int H) { return H == HH; }
@@ -713,76 +739,85 @@ bool gru_mma_fits(const GruMmaCtx* c, int ndir, int b) {
     return ndir * CL <= c->num_sms && bslr <= MAX_BSL;
 }
 
+// One launch = steps [t0, t0+Tseg) of the plan (Tseg < 0: all).  `slot` selects the LL exchange buffer: launches
+// that may run CONCURRENTLY (decoder wavefront: one stream per layer) must use different slots.
 void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& Pl, const int* d_off, const int* d_nact, int H,
-                 cudaStream_t s) {
+                 cudaStream_t s, int t0, int Tseg, int slot) {
     if (H != HH) throw std::runtime_error("gru_mma: H must be 512");
-    if (Pl.Tmax >= 4096) throw std::runtime_error("gru_mma: more than 4095 steps");
+    if (Tseg < 0) { t0 = 0; Tseg = Pl.Tmax; }
+    if (Tseg >= 4096) throw std::runtime_error("gru_mma: more than 4095 steps per launch");
+    if (slot < 0 || slot >= GruMmaCtx::NSLOT) throw std::runtime_error("gru_mma: bad slot");
     FwdP P;
     int ns, bslr;
-    pick_slices(c, ndir, Pl.b, &ns, &bslr);
+    // sequences alive in the segment: forward directions shrink with t, so the first step has the most
+    const int b_seg = (ndir == 1 && !dirs[0].reverse) ? Pl.nact[t0] : Pl.b;
+    pick_slices(c, ndir, b_seg, &ns, &bslr);
     if (bslr > MAX_BSL) throw std::runtime_error("gru_mma: batch too large for the persistent kernel");
     for (int d = 0; d < ndir; ++d) {
         const GruFwdArgs& a = dirs[d];
         if (!a.R_h) throw std::runtime_error("gru_mma: bf16 weights missing");
         if (a.h0 && a.reverse) throw std::runtime_error("gru_mma: h0 is only supported for forward directions");
-        P.dir[d] = FwdDirP{a.gx, a.R_h, a.bR, a.h0, a.hs_f, a.hs_h, a.cache, a.ld_gx, a.ld_hs, a.reverse};
+        P.dir[d] = FwdDirP{a.gx, a.R_h, a.bR, a.h0, a.hs_f, a.hs_h, a.cache, a.hT, a.ld_gx, a.ld_hs, a.reverse};
     }
     if (ndir == 1) P.dir[1] = P.dir[0];
     const int groups = ndir * ns;
     const size_t need = (size_t)groups * 2 * bslr * (HH / 2);
-    if (need > c->xcap) {
-        CUDA_CHECK(cudaStreamSynchronize(s));
-        cudaFree(c->xbuf);
-        CUDA_CHECK(cudaMalloc(&c->xbuf, need * 8));
-        CUDA_CHECK(cudaMemset(c->xbuf, 0, need * 8));
+    if (need > c->xcap[slot]) {
         CUDA_CHECK(cudaDeviceSynchronize());
-        c->xcap = need;
+        cudaFree(c->xbuf[slot]);
+        CUDA_CHECK(cudaMalloc(&c->xbuf[slot], need * 8));
+        CUDA_CHECK(cudaMemset(c->xbuf[slot], 0, need * 8));
+        CUDA_CHECK(cudaDeviceSynchronize());
+        c->xcap[slot] = need;
     }
-    P.off = d_off; P.nact = d_nact; P.xbuf = c->xbuf;
-    P.ndir = ndir; P.nslices = ns; P.b = Pl.b; P.Tmax = Pl.Tmax; P.bslr = bslr;
+    P.off = d_off; P.nact = d_nact; P.xbuf = c->xbuf[slot];
+    P.ndir = ndir; P.nslices = ns; P.b = b_seg; P.Ttot = Pl.Tmax; P.t0 = t0; P.Tseg = Tseg; P.bslr = bslr;
     P.tag_base = (c->launch_id++) << 12;
     P.prof = c->prof;
     if (c->launch_id >= (1u << 20)) c->launch_id = 1;
-    const size_t smem = (size_t)bslr * HS_LD * 2 + 4 * CH * RED_LD * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Pl.Tmax + 1) * 4;
+    const size_t smem = (size_t)bslr * HS_LD * 2 + 4 * CH * RED_LD * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4;
     void* args[] = {&P};
     CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gru_mma_fwd, dim3(groups * CL), dim3(NTH), args, smem, s));
     COUNT_LAUNCH();
-    dump_prof(c, ndir == 2 ? "fwd_enc" : "fwd_dec", groups * CL, Pl.Tmax, s);
+    dump_prof(c, ndir == 2 ? "fwd_enc" : "fwd_dec", groups * CL, Tseg, s);
 }
 
 void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& Pl, const int* d_off, const int* d_nact, int H,
-                 cudaStream_t s) {
+                 cudaStream_t s, int t0, int Tseg, int slot) {
     if (H != HH) throw std::runtime_error("gru_mma: H must be 512");
-    if (Pl.Tmax >= 4096) throw std::runtime_error("gru_mma: more than 4095 steps");
+    if (Tseg < 0) { t0 = 0; Tseg = Pl.Tmax; }
+    if (Tseg >= 4096) throw std::runtime_error("gru_mma: more than 4095 steps per launch");
+    if (slot < 0 || slot >= GruMmaCtx::NSLOT) throw std::runtime_error("gru_mma: bad slot");
     BwdP P;
     int ns, bslr;
-    pick_slices(c, ndir, Pl.b, &ns, &bslr);
+    const int b_seg = (ndir == 1 && !dirs[0].reverse) ? Pl.nact[t0] : Pl.b;
+    pick_slices(c, ndir, b_seg, &ns, &bslr);
     if (bslr > MAX_BSL) throw std::runtime_error("gru_mma: batch too large for the persistent kernel");
     for (int d = 0; d < ndir; ++d) {
         const GruBwdArgs& a = dirs[d];
         if (!a.R_h) throw std::runtime_error("gru_mma: bf16 weights missing");
         P.dir[d] = BwdDirP{a.dhs, a.hs_f, a.hs_h, a.h0, a.cache, a.R_h, a.dgx_f, a.dgx_h, a.dgh_f, a.dgh_h, a.hp_f, a.hp_h, a.dh0,
-                           a.ld_dhs, a.ld_hs, a.ld_dg, a.ld_hp, a.reverse};
+                           a.dh_in, a.dh_out, a.ld_dhs, a.ld_hs, a.ld_dg, a.ld_hp, a.reverse};
     }
     if (ndir == 1) P.dir[1] = P.dir[0];
     const int groups = ndir * ns;
     const size_t need = (size_t)groups * 2 * CL * CL * (bslr / 2) * UN;
-    if (need > c->ycap) {
-        CUDA_CHECK(cudaStreamSynchronize(s));
-        cudaFree(c->ybuf);
-        CUDA_CHECK(cudaMalloc(&c->ybuf, need * 8));
-        CUDA_CHECK(cudaMemset(c->ybuf, 0, need * 8));
+    if (need > c->ycap[slot]) {
         CUDA_CHECK(cudaDeviceSynchronize());
-        c->ycap = need;
+        cudaFree(c->ybuf[slot]);
+        CUDA_CHECK(cudaMalloc(&c->ybuf[slot], need * 8));
+        CUDA_CHECK(cudaMemset(c->ybuf[slot], 0, need * 8));
+        CUDA_CHECK(cudaDeviceSynchronize());
+        c->ycap[slot] = need;
     }
-    P.off = d_off; P.nact = d_nact; P.ybuf = c->ybuf;
-    P.ndir = ndir; P.nslices = ns; P.b = Pl.b; P.Tmax = Pl.Tmax; P.bslr = bslr;
+    P.off = d_off; P.nact = d_nact; P.ybuf = c->ybuf[slot];
+    P.ndir = ndir; P.nslices = ns; P.b = b_seg; P.Ttot = Pl.Tmax; P.t0 = t0; P.Tseg = Tseg; P.bslr = bslr;
     P.tag_base = (c->launch_id++) << 12;
     P.prof = c->prof;
     if (c->launch_id >= (1u << 20)) c->launch_id = 1;
-    const size_t smem = (size_t)CH * GS_LD * 2 + (size_t)bslr * UN * 4 + (size_t)(2 * Pl.Tmax + 2) * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2;
+    const size_t smem = (size_t)CH * GS_LD * 2 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2;
     void* args[] = {&P};
     CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gru_mma_bwd, dim3(groups * CL), dim3(NTH), args, smem, s));
     COUNT_LAUNCH();
-    dump_prof(c, ndir == 2 ? "bwd_enc" : "bwd_dec", groups * CL, Pl.Tmax, s);
+    dump_prof(c, ndir == 2 ? "bwd_enc" : "bwd_dec", groups * CL, Tseg, s);
 }

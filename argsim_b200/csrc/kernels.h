@@ -64,6 +64,7 @@ struct GruFwdArgs {
     int ld_hs;
     float* cache;         // (rows, 4H): r,u,n,q per row (training) or null
     int reverse;          // 1: runs t = Tmax-1 .. 0 (== tf.reverse_sequence o GRU o tf.reverse_sequence)
+    float* hT = nullptr;  // persistent kernels, time-segmented launches: (b,H) state after the segment, or null
 };
 struct GruBwdArgs {
     const float* dhs;     // (rows, ld_dhs) gradient wrt outputs (column offset applied)
@@ -85,6 +86,8 @@ struct GruBwdArgs {
     int ld_hp;
     float* dh0;           // (b,H) += gradient wrt h0 (sorted order), or null
     int reverse;
+    const float* dh_in = nullptr;   // time-segmented launches: gradient wrt the state after the segment (from the later one)
+    float* dh_out = nullptr;        // ... and wrt the state before it (overwritten; handed to the earlier segment)
 };
 struct SeqPlan;
 // generic path: one GEMM + one gate kernel per time step, fp32 (FP32_VALIDATE mode, any H)
@@ -97,7 +100,8 @@ GruMmaCtx* gru_mma_create(int device);
 void gru_mma_destroy(GruMmaCtx*);
 bool gru_mma_supported(int H);
 bool gru_mma_fits(const GruMmaCtx*, int ndir, int b);   // batch small enough for the resident-state kernel
+// steps [t0, t0+Tseg) (Tseg < 0: the whole plan); launches that may overlap in time need different slots (0..3)
 void gru_mma_fwd(GruMmaCtx*, const GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
-                 int H, cudaStream_t s);
+                 int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0);
 void gru_mma_bwd(GruMmaCtx*, const GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
-                 int H, cudaStream_t s);
+                 int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0);

@@ -99,80 +99,82 @@ def dist_setup(n):
     return 0, 1, 0, None
 
 
+class CpuPort:
+    """torch-CPU port of the reference graph (oracle/vae_torch.py) on the C1 batch.  The reference pads every
+    row to the batch maximum and runs cuDNN over all padded steps, so the cost of a step is proportional to the
+    number of TIME STEPS: a bounded sample is the same 64 rows truncated to their first T' tokens, and the
+    full-length rate is extrapolated as 64 / (t_sample * 512 / T')."""
+
+    def __init__(self):
+        import torch
+        from argsim_b200.synth import synth_batch
+        from oracle import vae_oracle as O
+        from oracle import vae_torch as T
+        self.T, self.torch = T, torch
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.full = synth_batch(PER_GPU, 'iac', CFG['dim_tgt'], seed=0)
+        self.tmax = self.full.shape[1]
+        self.P = T.to_torch(O.init_params(CFG, seed=0, dtype=np.float32), torch.float32, requires_grad=True)
+        self.M = {k: torch.zeros_like(v) for k, v in self.P.items()}
+        self.V = {k: torch.zeros_like(v) for k, v in self.P.items()}
+        rng = np.random.default_rng(0)
+        self.keep = (rng.random((self.tmax, PER_GPU)) < 0.5).astype(np.int64)
+        self.eps = rng.standard_normal((PER_GPU, CFG['dim_rep'])).astype(np.float32)
+        self.it = 0
+
+    def step(self, tprime):
+        sub = self.full[:, :tprime].copy()
+        t0 = time.perf_counter()
+        self.T.train_step(self.P, self.M, self.V, CFG, sub, sub, self.it, self.keep[:tprime], self.eps)
+        self.it += 1
+        return time.perf_counter() - t0
+
+    def pick(self, nsteps, budget_s):
+        """largest power-of-two truncation whose nsteps steps fit the budget (calibrated on T'=8)"""
+        self.step(8)
+        t8 = self.step(8)
+        tp = 8
+        while tp * 2 <= self.tmax and nsteps * t8 * (tp * 2 / 8.0) <= budget_s:
+            tp *= 2
+        return tp
+
+
 def reference_arm(args, rank, world):
-    """torch-CPU port of the reference graph on the host cores; bounded sample per step."""
+    """--impl reference: the CPU arm on the box's host cores, all threads, bounded sample per step."""
     if rank != 0:
         return
-    import torch
-    from argsim_b200.synth import synth_batch
-    from oracle import vae_oracle as O
-    from oracle import vae_torch as T
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    full = synth_batch(PER_GPU, 'iac', CFG['dim_tgt'], seed=0)
-    nrow = int(os.environ.get('ARGSIM_REF_ROWS', 8))
-    # bounded sample: the first rows of the C1 batch whose longest row is the batch's longest (keeps s = 512)
-    order = np.argsort(-(full != 1).sum(1), kind='stable')[:nrow]
-    sub = full[np.sort(order)]
-    sub = sub[:, :int((sub != 1).sum(1).max())]
-    P0 = O.init_params(CFG, seed=0, dtype=np.float32)
-    P = T.to_torch(P0, torch.float32, requires_grad=True)
-    M = {k: torch.zeros_like(v) for k, v in P.items()}
-    V = {k: torch.zeros_like(v) for k, v in P.items()}
-    rng = np.random.default_rng(0)
-    tmax = sub.shape[1]
-    keep = (rng.random((tmax, nrow)) < 0.5).astype(np.int64)
-    eps = rng.standard_normal((nrow, CFG['dim_rep'])).astype(np.float32)
-    times = []
-    for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        T.train_step(P, M, V, CFG, sub, sub, it, keep, eps)
-        dt = time.perf_counter() - t0
-        if it >= args.warmup:
-            times.append(dt)
+    port = CpuPort()
+    tp = port.pick(args.steps + args.warmup, float(os.environ.get('ARGSIM_REF_BUDGET_S', 150)))
+    times = [port.step(tp) for _ in range(args.warmup + args.steps)][args.warmup:]
     ms = 1e3 * float(np.mean(times))
-    val = nrow / (ms / 1e3)
+    ms_full = ms * port.tmax / tp
+    val = PER_GPU / (ms_full / 1e3)
+    sample = ('the 64-row C1 batch truncated to its first %d of %d time steps per step (padded graph: cost ~ time steps); '
+              'value extrapolated x%d/%d; %d steps of fwd+bwd+Adam, torch-CPU fp32' % (tp, port.tmax, tp, port.tmax, args.steps))
     line = dict(metric=METRIC, value=val, unit='sequences/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                ms_per_step=ms_full, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                 impl='reference',
-                config=dict(workload='config.json VAE, IAC-shaped synthetic batch (seed 0), %d longest of 64 rows per step' % nrow,
-                            global_batch=nrow, note='TF reference cannot run (no TensorFlow; CudnnGRU has no CPU kernel): '
-                            'torch-CPU port of the same padded graph, oracle/vae_torch.py'),
-                cpu_baseline=dict(value=val, unit='sequences/s', cores=cores, kind='port',
-                                  sample='%d longest rows of the 64-row C1 batch (max len %d), %d steps' % (nrow, tmax, args.steps)),
+                config=dict(workload='config.json VAE (V=8192 D=512 R=1024 L=3), IAC-shaped synthetic sentencepiece batch, '
+                                     'seed 0, 64 sequences (BASELINE configs[0])', global_batch=PER_GPU,
+                            measured_ms_per_sample_step=ms, sample_time_steps=tp,
+                            note='the TF reference cannot run (no TensorFlow; CudnnGRU has no CPU kernel): torch-CPU port of '
+                                 'the same padded graph (oracle/vae_torch.py), library GRU + MKL GEMMs'),
+                cpu_baseline=dict(value=val, unit='sequences/s', cores=port.cores, kind='port', sample=sample),
                 e2e=dict(value=val, unit='sequences/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline_leg():
-    """rank 0, N=1: the torch-CPU port timed on a bounded sample of the same workload."""
-    import torch
-    from argsim_b200.synth import synth_batch
-    from oracle import vae_oracle as O
-    from oracle import vae_torch as T
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    full = synth_batch(PER_GPU, 'iac', CFG['dim_tgt'], seed=0)
-    nrow = 8
-    order = np.argsort(-(full != 1).sum(1), kind='stable')[:nrow]
-    sub = full[np.sort(order)]
-    sub = sub[:, :int((sub != 1).sum(1).max())]
-    P = T.to_torch(O.init_params(CFG, seed=0, dtype=np.float32), torch.float32, requires_grad=True)
-    M = {k: torch.zeros_like(v) for k, v in P.items()}
-    V = {k: torch.zeros_like(v) for k, v in P.items()}
-    rng = np.random.default_rng(0)
-    keep = (rng.random((sub.shape[1], nrow)) < 0.5).astype(np.int64)
-    eps = rng.standard_normal((nrow, CFG['dim_rep'])).astype(np.float32)
-    T.train_step(P, M, V, CFG, sub[:2, :32], sub[:2, :32], 0, keep[:32, :2], eps[:2])  # warm the thread pool
-    t0 = time.perf_counter()
-    nstep = 0
-    while nstep < 2 or (time.perf_counter() - t0 < 10 and nstep < 8):
-        T.train_step(P, M, V, CFG, sub, sub, nstep, keep, eps)
-        nstep += 1
-    dt = (time.perf_counter() - t0) / nstep
-    return dict(value=nrow / dt, unit='sequences/s', cores=cores, kind='port',
-                sample='%d longest rows of the 64-row C1 batch (max len %d), %d steps of fwd+bwd+Adam in torch-CPU fp32 '
-                       '(TF reference not runnable)' % (nrow, sub.shape[1], nstep))
+    """rank 0, N=1: the same port timed for ~20 s next to the GPU number."""
+    port = CpuPort()
+    tp = port.pick(3, 20.0)
+    times = [port.step(tp) for _ in range(3)][1:]
+    ms_full = 1e3 * float(np.mean(times)) * port.tmax / tp
+    return dict(value=PER_GPU / (ms_full / 1e3), unit='sequences/s', cores=port.cores, kind='port',
+                sample='the 64-row C1 batch truncated to its first %d of %d time steps (padded graph: cost ~ time steps), '
+                       'extrapolated x%d/%d; 2 timed steps of fwd+bwd+Adam in torch-CPU fp32 (TF reference not runnable)'
+                       % (tp, port.tmax, tp, port.tmax))
 
 
 def main():

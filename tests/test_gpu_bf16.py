@@ -94,3 +94,35 @@ def test_persistent_recurrence_matches_generic(b, tmax):
             bad[k] = (round(float(cos), 4), round(float(ratio), 4))
     assert not bad, bad
     np.testing.assert_allclose(hm.embed(src), hg.embed(src), rtol=0, atol=2e-2)
+
+
+@pytest.mark.parametrize('seg,b,tmax', [(8, 40, 37), (5, 130, 21), (16, 16, 16)])
+def test_decoder_wavefront_matches_generic(monkeypatch, seg, b, tmax):
+    """decoder layers as a wavefront over time segments (state / gradient hand-over between segment launches,
+    one stream per layer) against the per-step generic GRU"""
+    from argsim_b200 import _lib
+    cfg = dict(dim_tgt=1024, dim_emb=512, dim_rep=256, rnn_layers=3, accelerate=1e-4, learn_rate=1e-3, bos=2, eos=1)
+    hg, P = _mk(cfg, _lib.BF16, flags=4)
+    monkeypatch.setenv('ARGSIM_DEC_SEG', str(seg))
+    hm, _ = _mk(cfg, _lib.BF16, flags=0)
+    src = ragged_batch(b, tmax, cfg['dim_tgt'], 70 + b)
+    tgt = ragged_batch(b, tmax, cfg['dim_tgt'], 71 + b)
+    keep, eps = _inject(cfg, tgt, 72)
+    for h in (hg, hm):
+        h.step = 15000
+    a = hg.grad_step(src, tgt, keep=keep, eps=eps)
+    m = hm.grad_step(src, tgt, keep=keep, eps=eps)
+    for name in ('loss', 'loss_gen', 'loss_kld'):
+        assert rel(m[name], a[name]) < 2e-3, (name, m[name], a[name])
+    bad = {}
+    for k in P:
+        g, r = hm.get_grad(k).astype(np.float64).ravel(), hg.get_grad(k).astype(np.float64).ravel()
+        if np.linalg.norm(r) < 1e-12:
+            continue
+        cos = g @ r / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30)
+        ratio = np.linalg.norm(g) / np.linalg.norm(r)
+        if not (cos > 0.998 and abs(ratio - 1) < 0.02):
+            bad[k] = (round(float(cos), 4), round(float(ratio), 4))
+    assert not bad, bad
+    e1, e2 = hm.eval_step(src, tgt), hg.eval_step(src, tgt)
+    assert rel(e1['loss_gen_samp'].mean(), e2['loss_gen_samp'].mean()) < 2e-3

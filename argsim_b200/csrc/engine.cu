@@ -877,7 +877,7 @@ void Engine::eval_step(const int32_t* src, const int32_t* tgt, int b, int Ts, in
     if (lkld) memcpy(lkld, hk, (size_t)b * R * sizeof(float));
 }
 
-void Engine::embed(const int32_t* src, int b, int T, float* mu_out) {
+void Engine::embed_one(const int32_t* src, int b, int T, float* mu_out) {
     DropoutSpec drop;
     last = StepArgs();
     stage(src, nullptr, b, T, 0, 0, drop, nullptr);
@@ -887,6 +887,37 @@ void Engine::embed(const int32_t* src, int b, int T, float* mu_out) {
                                  (size_t)R * sizeof(float), b, cudaMemcpyDeviceToHost, st[0]));
     CUDA_CHECK(cudaStreamSynchronize(st[0]));
     collect_timings();
+}
+
+// Rows are independent in 'infer' mode, so a batch larger than the persistent recurrence holds resident
+// (4 slices x 128 rows) is processed as length-sorted micro-batches: each one's step count is its own longest
+// row, not the batch maximum (eval_embed*.py feed 128 rows per call; BASELINE configs[3] feeds 4096).
+void Engine::embed(const int32_t* src, int b, int T, float* mu_out) {
+    const int cap = 512;
+    if (!use_mma || b <= cap) {
+        embed_one(src, b, T, mu_out);
+        return;
+    }
+    std::vector<int> len(b), order(b);
+    for (int i = 0; i < b; ++i) {
+        int n = 0;
+        for (int t = 0; t < T; ++t) n += (src[(size_t)i * T + t] != cfg.eos);
+        len[i] = n;
+        order[i] = i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return len[x] > len[y]; });
+    std::vector<int32_t> rows;
+    std::vector<float> out;
+    for (int i0 = 0; i0 < b; i0 += cap) {
+        const int n = std::min(cap, b - i0);
+        const int Tm = std::max(1, len[order[i0]]);     // longest row of this micro-batch (sorted descending)
+        rows.assign((size_t)n * Tm, cfg.eos);
+        for (int r = 0; r < n; ++r) memcpy(rows.data() + (size_t)r * Tm, src + (size_t)order[i0 + r] * T, sizeof(int32_t) * std::min(Tm, T));
+        // a row with eos inside its first Tm tokens keeps it and fails the trim() contract check, as it must
+        out.resize((size_t)n * R);
+        embed_one(rows.data(), n, Tm, out.data());
+        for (int r = 0; r < n; ++r) memcpy(mu_out + (size_t)order[i0 + r] * R, out.data() + (size_t)r * R, sizeof(float) * R);
+    }
 }
 
 // decode(), model.py:204-219: fp32 SIMT path (host-driven single steps, batch <= a few hundred)

@@ -71,6 +71,7 @@ public:
     void eval_step(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt, float* errt, float* lgen, int64_t cap,
                    float* lkld, int64_t* n_rows, int32_t* pred);
     void embed(const int32_t* src, int b, int T, float* mu_out);
+    void embed_one(const int32_t* src, int b, int T, float* mu_out);
     void decode_init(const float* z, int b, float* state);
     void decode_step(const int32_t* lead, int b, float* state, int32_t* pred);
     void bench_resident(int iters, float* ms);

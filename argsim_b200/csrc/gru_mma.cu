@@ -49,6 +49,7 @@ struct FwdP {
     unsigned long long* xbuf;
     int ndir, nslices, b, Ttot, t0, Tseg, bslr;   // steps [t0, t0+Tseg) of a plan with Ttot steps
     unsigned tag_base;
+    int variant;       // bit0: gx loaded one step ahead into registers; bit1: L2 prefetch two steps ahead by idle warps
     long long* prof;   // debug: per-phase clock totals of thread 0 of every CTA (8 slots each) or null
 };
 struct BwdDirP {
@@ -64,6 +65,7 @@ struct BwdP {
     unsigned long long* ybuf;
     int ndir, nslices, b, Ttot, t0, Tseg, bslr;
     unsigned tag_base;
+    int variant;       // bit0: cp.async staging one step ahead; bit1: L2 prefetch two steps ahead by idle warps
     long long* prof;
 };
 
@@ -175,7 +177,8 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
         }
         PROF_MARK(0);
         const long long row_base = OFF(t);
-        // gx of chunk 0 (independent of h) was loaded one step ahead into gxn; the first active step loads it here
+        const bool had_next = have_next;
+        // gx of chunk 0 (independent of h) was loaded one step ahead into gxn; otherwise it is loaded at chunk start
         float gx0[2][3];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -183,11 +186,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
             if (have_next) {
                 gx0[e][0] = gxn[e][0]; gx0[e][1] = gxn[e][1]; gx0[e][2] = gxn[e][2];
             } else {
-                gx0[e][0] = gx0[e][1] = gx0[e][2] = 0.f;
-                if (n < na) {
-                    const float* gp = A.gx + (size_t)(row_base + (long long)n * ns + sl) * A.ld_gx + UN * c + lane;
-                    gx0[e][0] = gp[0]; gx0[e][1] = gp[HH]; gx0[e][2] = gp[2 * HH];
-                }
+                gx0[e][0] = gx0[e][1] = gx0[e][2] = 0.f;   // loaded at the start of chunk 0 (after the poll)
             }
         }
         // ---------------- h_{prev} of every active row, all 512 units -> Hs
@@ -252,7 +251,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
             for (int e = 0; e < 2; ++e) {
                 const int n = warp + 8 * e;
                 gxv[e][0] = gx0[e][0]; gxv[e][1] = gx0[e][1]; gxv[e][2] = gx0[e][2];
-                if (ch > 0 && n < nrows) {
+                if (!(P.variant & 4) && (ch > 0 || !had_next) && n < nrows) {
                     const float* gp = A.gx + (size_t)(row_base + (long long)(ch * CH + n) * ns + sl) * A.ld_gx + col;
                     gxv[e][0] = gp[0]; gxv[e][1] = gp[HH]; gxv[e][2] = gp[2 * HH];
                 }
@@ -278,12 +277,24 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
                     }
                 }
             }
+            // this step's gx, issued behind the ldmatrix: loads return in order through L1TEX, so an L2-latency load
+            // issued in front of them would hold them up; here it completes under the HMMA tail and barrier 2
+            if (P.variant & 4) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = warp + 8 * e;
+                    if ((ch > 0 || !had_next) && n < nrows) {
+                        const float* gp = A.gx + (size_t)(row_base + (long long)(ch * CH + n) * ns + sl) * A.ld_gx + col;
+                        gxv[e][0] = ld_f32(gp); gxv[e][1] = ld_f32(gp + HH); gxv[e][2] = ld_f32(gp + 2 * HH);
+                    }
+                }
+            }
             // next step's gx (chunk 0) -> registers.  Loads return IN ORDER through L1TEX, so they are issued only
             // after this step's ldmatrix (they would stall them) and were made L2 hits by the prefetch.global.L2
             // issued two steps ago; they complete under the HMMAs / the partial-sum barrier.
             if (ch == 0) {
                 have_next = false;
-                if (k + 1 < P.Tseg) {
+                if ((P.variant & 1) && k + 1 < P.Tseg) {
                     const int tn = A.reverse ? t - 1 : t + 1;
                     const int nan = NA(tn);
                     if (nan > 0) {
@@ -315,7 +326,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
             PROF_MARK(4);   // barrier 2
             // gx rows of the step after next -> L2.  A prefetch costs its issuing warp ~100 cycles, so it is done by
             // the warps that have no row to finish in this chunk (all of them idle otherwise until barrier 3)
-            if (ch == 0 && warp >= nrows && k + 2 < P.Tseg) {
+            if ((P.variant & 2) && ch == 0 && warp >= nrows && k + 2 < P.Tseg) {
                 const int tn = A.reverse ? t - 2 : t + 2;
                 const int nan = NA(tn);
                 const long long rbn = OFF(tn);
@@ -493,7 +504,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
             PROF_MARK(1);   // reduce-scatter receive
             // ---- prefetch the NEXT step's chunk-0 gate inputs (issued after the poll: the L1TEX queue is in order)
             bool staged_next = false;
-            if (ch == 0 && k + 1 < P.Tseg && A.hs_h) {
+            if ((P.variant & 1) && ch == 0 && k + 1 < P.Tseg && A.hs_h) {
                 const int tq = A.reverse ? t + 1 : t - 1;
                 const int naq = NA(tq);
                 if (naq > 0) {
@@ -526,7 +537,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
             }
             // gate inputs of the BPTT step after next -> L2 (by the warps without a row in this chunk), so that the
             // cp.async staging issued next step hits L2 and does not hold up the in-order L1TEX queue
-            if (ch == 0 && warp >= nrows && k + 2 < P.Tseg) {
+            if ((P.variant & 2) && ch == 0 && warp >= nrows && k + 2 < P.Tseg) {
                 const int tn = A.reverse ? t + 2 : t - 2;
                 const int nan = NA(tn);
                 const long long rbn = OFF(tn);
@@ -686,6 +697,7 @@ struct GruMmaCtx {
     unsigned long long* ybuf[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
     size_t ycap[NSLOT] = {0, 0, 0, 0};
     bool attr_set = false;
+    int variant_fwd = 2, variant_bwd = 3;
     long long* prof = nullptr;   // ARGSIM_GRU_PROF=1: per-phase clocks, printed to stderr after every launch
 };
 
@@ -697,6 +709,7 @@ GruMmaCtx* gru_mma_create(int device) {
     c->num_sms = prop.multiProcessorCount;
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BSL * HS_LD * 2 + 4 * CH * RED_LD * 4 + MAX_BSL * UN * 4 + 2 * 4100 * 4));
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, CH * GS_LD * 2 + MAX_BSL * UN * 4 + 2 * 4100 * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2));
+    if (const char* v = getenv("ARGSIM_GRU_VARIANT")) { c->variant_fwd = atoi(v) & 7; c->variant_bwd = (atoi(v) >> 3) & 7; }
     if (getenv("ARGSIM_GRU_PROF")) CUDA_CHECK(cudaMalloc(&c->prof, 160 * 8 * sizeof(long long)));
     return c;
 }
@@ -774,6 +787,7 @@ void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& 
     P.ndir = ndir; P.nslices = ns; P.b = b_seg; P.Ttot = Pl.Tmax; P.t0 = t0; P.Tseg = Tseg; P.bslr = bslr;
     P.tag_base = (c->launch_id++) << 12;
     P.prof = c->prof;
+    P.variant = c->variant_fwd;
     if (c->launch_id >= (1u << 20)) c->launch_id = 1;
     const size_t smem = (size_t)bslr * HS_LD * 2 + 4 * CH * RED_LD * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4;
     void* args[] = {&P};
@@ -814,6 +828,7 @@ void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& 
     P.ndir = ndir; P.nslices = ns; P.b = b_seg; P.Ttot = Pl.Tmax; P.t0 = t0; P.Tseg = Tseg; P.bslr = bslr;
     P.tag_base = (c->launch_id++) << 12;
     P.prof = c->prof;
+    P.variant = c->variant_bwd;
     if (c->launch_id >= (1u << 20)) c->launch_id = 1;
     const size_t smem = (size_t)CH * GS_LD * 2 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2;
     void* args[] = {&P};

@@ -126,3 +126,17 @@ def test_decoder_wavefront_matches_generic(monkeypatch, seg, b, tmax):
     assert not bad, bad
     e1, e2 = hm.eval_step(src, tgt), hg.eval_step(src, tgt)
     assert rel(e1['loss_gen_samp'].mean(), e2['loss_gen_samp'].mean()) < 2e-3
+
+
+def test_embed_microbatches_large_batch():
+    """b > 512 is embedded as length-sorted micro-batches: same rows, same order, same values as small calls"""
+    from argsim_b200 import _lib
+    cfg = dict(dim_tgt=1024, dim_emb=512, dim_rep=256, rnn_layers=2, accelerate=1e-4, learn_rate=1e-3, bos=2, eos=1)
+    h, P = _mk(cfg, _lib.BF16)
+    src = ragged_batch(1100, 19, cfg['dim_tgt'], 80)
+    big = h.embed(src)
+    assert big.shape == (1100, cfg['dim_rep'])
+    for i0 in (0, 300, 900):
+        np.testing.assert_allclose(big[i0:i0 + 100], h.embed(src[i0:i0 + 100]), rtol=0, atol=2e-2)
+    ov, _ = O.forward(P, cfg, src[:24], src[:24], 'valid')
+    assert np.abs(big[:24] - ov['mu']).max() / np.abs(ov['mu']).max() < 2e-2

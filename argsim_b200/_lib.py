@@ -64,6 +64,8 @@ SIGNATURES = {
     'argsim_last_timings': (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), _f32p]),
     'argsim_test_gemm': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p,
                                    _f32p, _f32p, C.c_float, C.c_int32, _f32p, _f32p]),
+    'argsim_test_softmax_ce': (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, _f32p, _i32p, C.c_float, C.c_int32, _f32p,
+                                         _f32p, _f32p, _i32p, C.POINTER(C.c_double)]),
     'argsim_bench_kernel': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, _f32p, C.POINTER(C.c_double),
                                       C.POINTER(C.c_double)]),
     'argsim_plan_batch': (C.c_int, [_i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _u8p, _i32p,
@@ -163,6 +165,23 @@ def test_gemm(impl, A, B, a_mn=0, b_mn=0, bias=None, alpha=1.0, C0=None, device=
     if rc != 0:
         raise RuntimeError(lib().argsim_last_error(None).decode())
     return out, ms.value
+
+
+def test_softmax_ce(logits, labels=None, gscale=1.0, bf16=True, write_grad=True, device=0):
+    """runs the fused softmax-CE kernel once on host data; returns dict(grad, loss_samp, err_samp, pred, stats)."""
+    logits = np.ascontiguousarray(logits, np.float32)
+    n, V = logits.shape
+    lab = None if labels is None else np.ascontiguousarray(labels, np.int32)
+    grad = np.zeros_like(logits)
+    loss = np.zeros(n, np.float32)
+    err = np.zeros(n, np.float32)
+    pred = np.zeros(n, np.int32)
+    stats = (C.c_double * 2)()
+    rc = lib().argsim_test_softmax_ce(device, int(bf16), n, V, _p(logits, _f32p), _p(lab, _i32p), gscale, int(write_grad),
+                                      _p(grad, _f32p), _p(loss, _f32p), _p(err, _f32p), _p(pred, _i32p), stats)
+    if rc != 0:
+        raise RuntimeError(lib().argsim_last_error(None).decode())
+    return dict(grad=grad, loss_samp=loss, err_samp=err, pred=pred, stats=np.array(stats[:]))
 
 
 class Handle:

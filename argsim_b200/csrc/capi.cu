@@ -231,6 +231,48 @@ int argsim_test_gemm(int32_t device, int32_t impl, int32_t M, int32_t N, int32_t
     return 0;
 }
 
+int argsim_test_softmax_ce(int32_t device, int32_t bf16_mode, int64_t n, int32_t V, const float* logits, const int32_t* labels,
+                           float gscale, int32_t write_grad, float* grad_out, float* loss_samp, float* err_samp, int32_t* pred,
+                           double stats[2]) {
+    try {
+        CUDA_CHECK(cudaSetDevice(device));
+        const size_t nl = (size_t)n * V;
+        float *dl, *dls, *der;
+        int *dlab = nullptr, *dpred;
+        double* dst;
+        bf16* dh = nullptr;
+        CUDA_CHECK(cudaMalloc(&dl, std::max<size_t>(nl, 1) * 4));
+        CUDA_CHECK(cudaMalloc(&dls, std::max<size_t>(n, 1) * 4)); CUDA_CHECK(cudaMalloc(&der, std::max<size_t>(n, 1) * 4));
+        CUDA_CHECK(cudaMalloc(&dpred, std::max<size_t>(n, 1) * 4)); CUDA_CHECK(cudaMalloc(&dst, 16));
+        CUDA_CHECK(cudaMemset(dst, 0, 16));
+        CUDA_CHECK(cudaMemcpy(dl, logits, nl * 4, cudaMemcpyHostToDevice));
+        if (labels) {
+            CUDA_CHECK(cudaMalloc(&dlab, std::max<size_t>(n, 1) * 4));
+            CUDA_CHECK(cudaMemcpy(dlab, labels, (size_t)n * 4, cudaMemcpyHostToDevice));
+        }
+        if (bf16_mode) {
+            CUDA_CHECK(cudaMalloc(&dh, std::max<size_t>(nl, 1) * 2));
+            launch_cast_bf16(dl, dh, (long long)nl, 0);
+            launch_ce_bf16(dh, V, dlab, n, V, gscale, write_grad, dls, der, dpred, dst, 0);
+            launch_cast_f32(dh, dl, (long long)nl, 0);
+        } else {
+            launch_ce_f32(dl, V, dlab, n, V, gscale, write_grad, dls, der, dpred, dst, 0);
+        }
+        CUDA_CHECK(cudaDeviceSynchronize());
+        if (grad_out) CUDA_CHECK(cudaMemcpy(grad_out, dl, nl * 4, cudaMemcpyDeviceToHost));
+        if (loss_samp) CUDA_CHECK(cudaMemcpy(loss_samp, dls, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        if (err_samp) CUDA_CHECK(cudaMemcpy(err_samp, der, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        if (pred) CUDA_CHECK(cudaMemcpy(pred, dpred, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        if (stats) CUDA_CHECK(cudaMemcpy(stats, dst, 16, cudaMemcpyDeviceToHost));
+        cudaFree(dl); cudaFree(dls); cudaFree(der); cudaFree(dpred); cudaFree(dst); cudaFree(dlab); cudaFree(dh);
+    } catch (const std::exception& ex) {
+        g_create_err = ex.what();
+        cudaGetLastError();
+        return -2;
+    }
+    return 0;
+}
+
 int argsim_bench_kernel(argsim_handle* h, const char* which, int64_t rows, int32_t iters, float* ms, double* algo_bytes,
                         double* algo_flops) {
     API_BEGIN(h)

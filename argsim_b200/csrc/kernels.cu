@@ -284,6 +284,124 @@ __global__ void __launch_bounds__(256) k_ce(T* __restrict__ logits, int ld, cons
         }
     }
 }
+
+// Register-resident fast path for bf16 logits (V = NV * 2048): every thread keeps its NV 16-byte vectors PACKED in
+// registers (16 * NV bytes per thread, so 6 rows are resident per SM at V = 8192 and their loads overlap the math of
+// the others); a row is read from HBM once and written once, no shared-memory staging pass.  Instruction budget per
+// element (the kernel is issue-bound long before it is HBM-bound if written naively): packed bf16x2 max (0.5),
+// packed equality for the argmax (0.5), unpack + FFMA + MUFU.EX2 + FADD + pack of exp(x - max) (4.5), unpack + FMUL +
+// pack of the gradient (2.5).  exp() is evaluated ONCE per element (MUFU runs 16/clk/SM: twice would cost 1024
+// cycles per row against a 1456-cycle HBM budget); it is kept as bf16 between the two passes, so the gradient is
+// rounded twice (<= 1 bf16 ulp); the loss uses the fp32 sum.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <int NV, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_ce_reg(bf16* __restrict__ logits, int ld, const int* __restrict__ labels, float gscale,
+                                                      int write_grad, float* __restrict__ loss_samp, float* __restrict__ err_samp,
+                                                      int* __restrict__ pred, double* __restrict__ stats) {
+    __shared__ float red_v[8];
+    __shared__ int red_i[8];
+    const long long r = blockIdx.x;
+    uint4* g4 = reinterpret_cast<uint4*>(logits + r * ld);
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t w[NV][4];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const uint4 v = g4[j * 256 + tid];
+        w[j][0] = v.x; w[j][1] = v.y; w[j][2] = v.z; w[j][3] = v.w;
+    }
+    const int lab = labels ? labels[r] : -1;
+    // the thread that holds the label element finishes the row (loss, error flag, label gradient in fp32)
+    const bool owner = lab >= 0 ? ((lab >> 3) & 255) == tid : tid == 0;
+    float x_lab = 0.f;
+    if (owner && lab >= 0) x_lab = __bfloat162float(logits[r * ld + lab]);   // read before the row is overwritten
+    // ---- max (packed bf16x2)
+    __nv_bfloat162 m2 = *reinterpret_cast<const __nv_bfloat162*>(&w[0][0]);
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m2 = __hmax2(m2, *reinterpret_cast<const __nv_bfloat162*>(&w[j][q]));
+    const float mt = fmaxf(__low2float(m2), __high2float(m2));
+    float mx = mt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red_v[wid] = mx;
+    __syncthreads();
+    mx = red_v[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red_v[i]);
+    __syncthreads();
+    // ---- argmax (ties -> lowest index, like tf.argmax): only the threads whose own maximum is the row maximum look
+    int mi = 0x7fffffff;
+    if (mt == mx) {
+        const __nv_bfloat162 mx2 = __float2bfloat162_rn(mx);   // exact: mx is one of the bf16 inputs
+#pragma unroll
+        for (int j = NV - 1; j >= 0; --j)
+#pragma unroll
+            for (int q = 3; q >= 0; --q) {   // descending, so the last hit is the lowest index
+                const unsigned eq = __heq2_mask(*reinterpret_cast<const __nv_bfloat162*>(&w[j][q]), mx2);
+                if (eq) mi = (j * 256 + tid) * 8 + 2 * q + ((eq & 0xffffu) ? 0 : 1);
+            }
+    }
+    // ---- exp(x - max) once per element, fp32 sum; kept packed as bf16 for the gradient pass
+    constexpr float L2E = 1.4426950408889634f;
+    const float nmx = -mx * L2E;
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(w[j][q] << 16), L2E, nmx));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(w[j][q] & 0xffff0000u), L2E, nmx));
+            sum0 += e0;
+            sum1 += e1;
+            const __nv_bfloat162 pk = __floats2bfloat162_rn(e0, e1);
+            w[j][q] = *reinterpret_cast<const uint32_t*>(&pk);
+        }
+    float sum = warp_sum(sum0 + sum1);
+    mi = __reduce_min_sync(0xffffffffu, mi);
+    if (lane == 0) { red_v[wid] = sum; red_i[wid] = mi; }
+    __syncthreads();
+    sum = 0.f;
+    mi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sum += red_v[i]; mi = min(mi, red_i[i]); }
+    const float inv = gscale / sum;
+    if (write_grad) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const __nv_bfloat162 pk = __floats2bfloat162_rn(__uint_as_float(w[j][q] << 16) * inv,
+                                                                 __uint_as_float(w[j][q] & 0xffff0000u) * inv);
+                w[j][q] = *reinterpret_cast<const uint32_t*>(&pk);
+            }
+            g4[j * 256 + tid] = make_uint4(w[j][0], w[j][1], w[j][2], w[j][3]);
+        }
+    }
+    if (owner) {
+        if (pred) pred[r] = mi;
+        if (lab >= 0) {
+            const float loss = logf(sum) + mx - x_lab;
+            const float err = (mi != lab) ? 1.f : 0.f;
+            if (loss_samp) loss_samp[r] = loss;
+            if (err_samp) err_samp[r] = err;
+            atomicAdd(stats + 0, (double)loss);
+            atomicAdd(stats + 1, (double)err);
+            // label element: softmax - 1 from the fp32 exp (same thread stored the vector above: program order)
+            if (write_grad) logits[r * ld + lab] = __float2bfloat16(ex2_approx(fmaf(x_lab, L2E, nmx)) * inv - gscale);
+        }
+    }
+}
+template <int NV, int MINB>
+static void launch_ce_reg(bf16* logits, int ld, const int* labels, long long n, float gscale, int write_grad, float* loss_samp,
+                          float* err_samp, int* pred, double* stats, cudaStream_t s) {
+    k_ce_reg<NV, MINB><<<(unsigned)n, 256, 0, s>>>(logits, ld, labels, gscale, write_grad, loss_samp, err_samp, pred, stats);
+    COUNT_LAUNCH();
+}
 template <typename T>
 static void launch_ce(T* logits, int ld, const int* labels, long long n, int V, float gscale, int write_grad,
                       float* loss_samp, float* err_samp, int* pred, double* stats, cudaStream_t s) {
@@ -303,6 +421,16 @@ void launch_ce_f32(float* logits, int ld, const int* labels, long long n, int V,
 }
 void launch_ce_bf16(bf16* logits, int ld, const int* labels, long long n, int V, float gscale, int write_grad,
                     float* loss_samp, float* err_samp, int* pred, double* stats, cudaStream_t s) {
+    if (n > 0 && V % 2048 == 0 && ld % 8 == 0 && ((uintptr_t)logits & 15) == 0 && !getenv("ARGSIM_CE_SMEM")) {
+        switch (V / 2048) {
+            case 1: return launch_ce_reg<1, 8>(logits, ld, labels, n, gscale, write_grad, loss_samp, err_samp, pred, stats, s);
+            case 2: return launch_ce_reg<2, 6>(logits, ld, labels, n, gscale, write_grad, loss_samp, err_samp, pred, stats, s);
+            case 4: return launch_ce_reg<4, 5>(logits, ld, labels, n, gscale, write_grad, loss_samp, err_samp, pred, stats, s);
+            case 8: return launch_ce_reg<8, 3>(logits, ld, labels, n, gscale, write_grad, loss_samp, err_samp, pred, stats, s);
+            case 16: return launch_ce_reg<16, 2>(logits, ld, labels, n, gscale, write_grad, loss_samp, err_samp, pred, stats, s);
+            default: break;
+        }
+    }
     launch_ce<bf16>(logits, ld, labels, n, V, gscale, write_grad, loss_samp, err_samp, pred, stats, s);
 }
 
@@ -404,6 +532,17 @@ void launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s) {
     if (n <= 0) return;
     int blocks = (int)std::min<long long>(cdiv(n, 256), 148LL * 16);
     k_cast_bf16<<<blocks, 256, 0, s>>>(in, out, n);
+    COUNT_LAUNCH();
+}
+__global__ void __launch_bounds__(256) k_cast_f32(const bf16* __restrict__ in, float* __restrict__ out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = __bfloat162float(in[i]);
+}
+void launch_cast_f32(const bf16* in, float* out, long long n, cudaStream_t s) {
+    if (n <= 0) return;
+    int blocks = (int)std::min<long long>(cdiv(n, 256), 148LL * 16);
+    k_cast_f32<<<blocks, 256, 0, s>>>(in, out, n);
     COUNT_LAUNCH();
 }
 __global__ void __launch_bounds__(256) k_fill(float* p, long long n, float v) {

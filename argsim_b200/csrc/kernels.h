@@ -30,6 +30,7 @@ void launch_adam(float* p, const float* g, float* m, float* v, bf16* shadow, lon
 void launch_colsum_f32(const float* in, int ld, long long rows, int cols, float* out, cudaStream_t s);
 void launch_colsum_bf16(const bf16* in, int ld, long long rows, int cols, float* out, cudaStream_t s);
 void launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s);
+void launch_cast_f32(const bf16* in, float* out, long long n, cudaStream_t s);
 // dst[dst_idx[i],:] += (or =) src[i,:]
 void launch_row_scatter(const float* in, int ld_in, float* out, int ld_out, const int* dst_idx, int n, int cols,
                         int accumulate, cudaStream_t s);

@@ -124,6 +124,13 @@ int  argsim_last_timings(argsim_handle*, int32_t cap, const char** names, float*
 int  argsim_test_gemm(int32_t device, int32_t impl, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
                       const float* A, const float* B, const float* bias_or_null, float alpha,
                       int32_t accumulate, float* C_inout, float* ms_or_null);
+/* unit-test hook for the fused softmax cross-entropy kernel (model.py:170-181 + its gradient): host fp32 logits
+ * (n,V) are copied to the device (rounded to bf16 when bf16_mode), the kernel runs once, and the in-place gradient
+ * (softmax - onehot) * gscale, per-row loss / error flag / argmax and the two fp64 sums {loss, errors} come back.
+ * labels may be NULL (argmax only); any output may be NULL. */
+int  argsim_test_softmax_ce(int32_t device, int32_t bf16_mode, int64_t n, int32_t V, const float* logits,
+                            const int32_t* labels_or_null, float gscale, int32_t write_grad, float* grad_out,
+                            float* loss_samp, float* err_samp, int32_t* pred, double stats[2]);
 /* stand-alone timing of one hot kernel on synthetic device data with an L2 flush between
  * iterations (bench.py roofline / profiles).  which: "softmax_ce" | "adam" | "embed_gather" |
  * "logits_gemm".  Returns the mean ms per launch and the algorithmic bytes / flops per launch. */

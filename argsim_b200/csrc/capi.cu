@@ -210,11 +210,14 @@ int argsim_test_gemm(int32_t device, int32_t impl, int32_t M, int32_t N, int32_t
             CUDA_CHECK(cudaMalloc(&hA, na * 2)); CUDA_CHECK(cudaMalloc(&hB, nb * 2));
             launch_cast_bf16(dA, hA, (long long)na, 0);
             launch_cast_bf16(dB, hB, (long long)nb, 0);
+            bf16* hC = nullptr;
+            if (impl == 2) CUDA_CHECK(cudaMalloc(&hC, nc * 2));   // bf16 output (activation-typed C)
             CUDA_CHECK(cudaEventRecord(e0, 0));
-            gemm_tc(hA, lda, a_mn, hB, ldb, b_mn, dC, nullptr, N, M, N, K, alpha, dbias, accumulate, 0);
+            gemm_tc(hA, lda, a_mn, hB, ldb, b_mn, impl == 2 ? nullptr : dC, hC, N, M, N, K, alpha, dbias, impl == 2 ? 0 : accumulate, 0);
             CUDA_CHECK(cudaEventRecord(e1, 0));
+            if (hC) launch_cast_f32(hC, dC, (long long)nc, 0);
             CUDA_CHECK(cudaDeviceSynchronize());
-            cudaFree(hA); cudaFree(hB);
+            cudaFree(hA); cudaFree(hB); cudaFree(hC);
         }
         CUDA_CHECK(cudaDeviceSynchronize());
         float ms = 0.f;

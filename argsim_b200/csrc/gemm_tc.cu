@@ -9,6 +9,16 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2..5 = epilogue (TMEM lane group = warp_id % 4).
+//
+// Two kernels share the operand pipeline:
+//   k_gemm_tc2 (default): PERSISTENT, one CTA per SM walking (m-tile, n-tile, k-split) work units; 128 x 256 tiles
+//     (96 B/clk of shared-memory operand reads per MMA instead of the 128 B/clk a 128 x 128 tile needs -- the port
+//     limit); the fp32 accumulator is DOUBLE BUFFERED in TMEM (2 x 256 columns) so the epilogue of unit i runs under
+//     the MMAs of unit i+1; the epilogue goes TMEM -> registers -> 128B-swizzled shared memory -> TMA store
+//     (cp.async.bulk.tensor, or cp.reduce.async.bulk.tensor .add for accumulate / split-K), so global writes are
+//     full 128-byte lines issued by the copy engine instead of 16-byte-per-row scattered stores.
+//   k_gemm_tc (v1): one 128 x 128 tile per CTA, direct stores; kept for outputs that want fp32 AND bf16 copies or are
+//     not 16-byte aligned, and as the A/B baseline (ARGSIM_GEMM_V1=1).
 #include "kernels.h"
 #include <cuda.h>
 #include <mutex>
@@ -265,6 +275,279 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
 }
 
+
+// ============================================================================================
+// v2: persistent, 128 x 256 tiles, double-buffered TMEM accumulator, TMA-store epilogue
+// ============================================================================================
+namespace v2 {
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SLAB_BYTES = 32 * 128;                 // 32 rows x 128 B: one epilogue warp's TMA-store box
+constexpr int EPI_BYTES = 4 * 2 * SLAB_BYTES;        // 4 epilogue warps x 2 slabs
+constexpr int BIAS_BYTES = BN * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + BIAS_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
+constexpr int TMEM_COLS = 512;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1, int reduce) {
+    if (reduce)
+        asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+// MN-major tiles are stored as [mn-block of 64][64 k-rows][64 mn] so LBO = 64 k-rows * 128 B
+template <int MN_MAJOR>
+__device__ __forceinline__ uint64_t make_desc2(uint32_t saddr) {
+    const uint64_t lbo = MN_MAJOR ? (uint64_t)((BK * 128) >> 4) : 1ull;
+    const uint64_t sbo = 1024 >> 4;
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+template <int A_MN, int B_MN>
+__device__ __forceinline__ uint32_t make_idesc2() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)A_MN << 15) | ((uint32_t)B_MN << 16) | ((uint32_t)(BN >> 3) << 17) |
+           ((uint32_t)(BM >> 4) << 24);
+}
+
+struct Work {
+    int tiles_m, tiles_n, splits, kb_per_split, nkb_total;
+    __device__ __forceinline__ int count() const { return tiles_m * tiles_n * splits; }
+    __device__ __forceinline__ void decode(int u, int& m0, int& n0, int& kb0, int& nkb, int& split) const {
+        const int mt = u % tiles_m, rest = u / tiles_m;   // m fastest: CTAs running together share the B (weight) tile in L2
+        const int nt = rest % tiles_n;
+        split = rest / tiles_n;
+        m0 = mt * BM; n0 = nt * BN;
+        kb0 = split * kb_per_split;
+        nkb = min(nkb_total, kb0 + kb_per_split) - kb0;
+    }
+};
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+           const __grid_constant__ CUtensorMap tmC, int M, int N, float alpha, const float* __restrict__ bias, int out_bf16,
+           int reduce, const Work W) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t epi_base = base + STAGES * STAGE_BYTES;
+    const uint32_t bias_base = epi_base + EPI_BYTES;
+    const uint32_t bar_base = bias_base + BIAS_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nunits = W.count();
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);   // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+                int m0, n0, kb0, nkb, split;
+                W.decode(u, m0, n0, kb0, nkb, split);
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                    const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+                    const int k = (kb0 + i) * BK;
+                    if (!A_MN) {
+                        tma_load_2d(sa, &tmA, k, m0, full_bar(s));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, m0 + 64 * j, k, full_bar(s));
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sb, &tmB, k, n0, full_bar(s));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, n0 + 64 * j, k, full_bar(s));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc2<A_MN, B_MN>();
+            uint32_t it = 0, tl = 0;
+            for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++tl) {
+                int m0, n0, kb0, nkb, split;
+                W.decode(u, m0, n0, kb0, nkb, split);
+                const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+                mbar_wait(tempty_bar(acc), aph ^ 1u);   // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + acc * BN;
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+                    for (int k16 = 0; k16 < BK / 16; ++k16) {
+                        const uint64_t da = make_desc2<A_MN>(sa + (A_MN ? k16 * 2048 : k16 * 32));
+                        const uint64_t db = make_desc2<B_MN>(sb + (B_MN ? k16 * 2048 : k16 * 32));
+                        tc_mma(tacc, da, db, idesc, (i > 0 || k16 > 0) ? 1u : 0u);
+                    }
+                    tc_commit(empty_bar(s));
+                }
+                tc_commit(tfull_bar(acc));
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue (4 warps)
+        const int lg = warp & 3;
+        const int et = threadIdx.x - 64;
+        const uint32_t slab0 = epi_base + (uint32_t)(warp - 2) * 2 * SLAB_BYTES;
+        const uint32_t row_off = (uint32_t)lane * 128u;
+        const uint32_t sw = (uint32_t)(lane & 7);
+        uint32_t slab_sel = 0, tl = 0;
+        for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++tl) {
+            int m0, n0, kb0, nkb, split;
+            W.decode(u, m0, n0, kb0, nkb, split);
+            const uint32_t acc = tl & 1u, aph = (tl >> 1) & 1u;
+            if (bias) {   // the tile's 256 bias values -> smem (split 0 only adds them)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int cidx = n0 + et + 128 * j;
+                    const float bv = (split == 0 && cidx < N) ? __ldg(bias + cidx) : 0.f;
+                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_base + 4u * (et + 128 * j)), "f"(bv) : "memory");
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            mbar_wait(tfull_bar(acc), aph);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + acc * BN + ((uint32_t)(lg * 32) << 16);
+            const int row0 = m0 + lg * 32;
+            const bool rows_live = row0 < M;
+#pragma unroll 1
+            for (int c = 0; c < BN / 64; ++c) {
+                uint32_t r[64];
+                tc_ld32_nowait(tacc + c * 64, r);
+                tc_ld32_nowait(tacc + c * 64 + 32, r + 32);
+                tc_wait_ld();
+                const int col0 = n0 + c * 64;
+                if (!rows_live || col0 >= N) continue;   // warp-uniform
+                if (bias) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        float4 b4;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                     : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w) : "r"(bias_base + 4u * (c * 64 + 4 * q)));
+                        r[4 * q] = __float_as_uint(fmaf(alpha, __uint_as_float(r[4 * q]), b4.x));
+                        r[4 * q + 1] = __float_as_uint(fmaf(alpha, __uint_as_float(r[4 * q + 1]), b4.y));
+                        r[4 * q + 2] = __float_as_uint(fmaf(alpha, __uint_as_float(r[4 * q + 2]), b4.z));
+                        r[4 * q + 3] = __float_as_uint(fmaf(alpha, __uint_as_float(r[4 * q + 3]), b4.w));
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) r[i] = __float_as_uint(alpha * __uint_as_float(r[i]));
+                }
+                if (out_bf16) {
+                    // one slab: 32 rows x 64 columns of bf16 (128 B per row), 128B-swizzled like the TMA box expects
+                    const uint32_t slab = slab0 + slab_sel * SLAB_BYTES;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        st_shared_v4(slab + row_off + ((((uint32_t)q) ^ sw) << 4),
+                                     pack_bf16(__uint_as_float(r[8 * q]), __uint_as_float(r[8 * q + 1])),
+                                     pack_bf16(__uint_as_float(r[8 * q + 2]), __uint_as_float(r[8 * q + 3])),
+                                     pack_bf16(__uint_as_float(r[8 * q + 4]), __uint_as_float(r[8 * q + 5])),
+                                     pack_bf16(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&tmC, slab, col0, row0, reduce);
+                    slab_sel ^= 1u;
+                } else {
+                    // two slabs of 32 rows x 32 fp32 columns
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        if (col0 + 32 * hf < N) {
+                            const uint32_t slab = slab0 + slab_sel * SLAB_BYTES;
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            __syncwarp();
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                st_shared_v4(slab + row_off + ((((uint32_t)q) ^ sw) << 4), r[32 * hf + 4 * q], r[32 * hf + 4 * q + 1],
+                                             r[32 * hf + 4 * q + 2], r[32 * hf + 4 * q + 3]);
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) tma_store_2d(&tmC, slab, col0 + 32 * hf, row0, reduce);
+                            slab_sel ^= 1u;
+                        }
+                    }
+                }
+            }
+            // accumulator fully read into registers: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+}  // namespace v2
+
 void encode_map(CUtensorMap* map, const bf16* ptr, int ld, int mn_major, long long rows_mn, long long K, int tile_mn) {
     // K-major  : global (rows_mn, K), K contiguous  -> dims {K, rows_mn}, box {64, tile_mn}
     // MN-major : global (K, rows_mn), rows contiguous -> dims {rows_mn, K}, box {64, 64}
@@ -296,6 +579,28 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, float* Cf, bf16* Ch, i
     k_gemm_tc<A_MN, B_MN><<<grid, NTHREADS, SMEM_BYTES, s>>>(ta, tb, Cf, Ch, ldc, M, N, K, alpha, bias, mode, kbps, vec_ok);
     COUNT_LAUNCH();
 }
+
+void encode_c_map(CUtensorMap* map, void* ptr, int is_bf16, int ldc, long long M, long long N) {
+    // output (M, N) row-major; one epilogue warp stores a box of 32 rows x 128 bytes (128B swizzle)
+    cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M}, strides[1] = {(cuuint64_t)ldc * (is_bf16 ? 2 : 4)};
+    cuuint32_t box[2] = {is_bf16 ? 64u : 32u, 32u}, estr[2] = {1, 1};
+    CUresult rc = g_encode(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled (C) failed with code " + std::to_string((int)rc));
+}
+
+template <int A_MN, int B_MN>
+void launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, float alpha, const float* bias,
+             int out_bf16, int reduce, const v2::Work& W, int grid, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(v2::k_gemm_tc2<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, v2::SMEM_BYTES));
+        configured = true;
+    }
+    v2::k_gemm_tc2<A_MN, B_MN><<<grid, NTHREADS, v2::SMEM_BYTES, s>>>(ta, tb, tc, M, N, alpha, bias, out_bf16, reduce, W);
+    COUNT_LAUNCH();
+}
 }  // namespace
 
 void gemm_tc_init(int device) {
@@ -322,6 +627,34 @@ void gemm_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn,
     if (!g_ready) throw std::runtime_error("gemm_tc: tcgen05 path not initialised");
     if (M <= 0 || N <= 0) return;
     if (K <= 0) throw std::runtime_error("gemm_tc: K must be positive");
+    // ---- v2: persistent 128 x 256 kernel with TMA-store epilogue (one output type, 16-byte aligned rows)
+    static const bool force_v1 = getenv("ARGSIM_GEMM_V1") != nullptr;
+    const bool one_out = (Cf != nullptr) != (Ch != nullptr);
+    const bool c_aligned = Cf ? ((((uintptr_t)Cf & 15) == 0) && ldc % 4 == 0) : ((((uintptr_t)Ch & 15) == 0) && ldc % 8 == 0);
+    if (!force_v1 && one_out && c_aligned && !(Ch && accumulate)) {
+        v2::Work W;
+        W.tiles_m = cdiv(M, v2::BM);
+        W.tiles_n = cdiv(N, v2::BN);
+        W.nkb_total = cdiv(K, v2::BK);
+        const int tiles = W.tiles_m * W.tiles_n;
+        int splits = 1;
+        if (Cf && tiles * 2 <= g_num_sms && W.nkb_total >= 8) splits = std::max(1, std::min(std::min(W.nkb_total / 4, g_num_sms / tiles), 64));
+        W.kb_per_split = cdiv(W.nkb_total, splits);
+        W.splits = cdiv(W.nkb_total, W.kb_per_split);   // no empty split
+        if (W.splits > 1 && !accumulate) CUDA_CHECK(cudaMemset2DAsync(Cf, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s));
+        const int reduce = (accumulate || W.splits > 1) ? 1 : 0;
+        CUtensorMap ta, tb, tc;
+        encode_map(&ta, A, lda, a_mn, M, K, v2::BM);
+        encode_map(&tb, B, ldb, b_mn, N, K, v2::BN);
+        encode_c_map(&tc, Cf ? (void*)Cf : (void*)Ch, Ch != nullptr, ldc, M, N);
+        const int grid = std::min(tiles * W.splits, g_num_sms);
+        const int ob = Ch != nullptr;
+        if (!a_mn && !b_mn) launch2<0, 0>(ta, tb, tc, M, N, alpha, bias, ob, reduce, W, grid, s);
+        else if (!a_mn && b_mn) launch2<0, 1>(ta, tb, tc, M, N, alpha, bias, ob, reduce, W, grid, s);
+        else if (a_mn && !b_mn) launch2<1, 0>(ta, tb, tc, M, N, alpha, bias, ob, reduce, W, grid, s);
+        else launch2<1, 1>(ta, tb, tc, M, N, alpha, bias, ob, reduce, W, grid, s);
+        return;
+    }
     CUtensorMap ta, tb;
     encode_map(&ta, A, lda, a_mn, M, K, BM);
     encode_map(&tb, B, ldb, b_mn, N, K, BN);

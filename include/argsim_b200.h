@@ -120,7 +120,7 @@ int  argsim_launch_count(argsim_handle*, int64_t* n);
 int  argsim_last_timings(argsim_handle*, int32_t cap, const char** names, float* ms);
 /* unit-test hook for the GEMM kernels: C(M,N) = alpha * op(A) op(B)^T (+bias) ; layouts:
  * a_mn/b_mn = 0 operand stored (rows=M|N, cols=K) K-contiguous, 1 stored (K, M|N).  host fp32 in/out.
- * impl 0 = SIMT fp32, 1 = tcgen05 bf16. */
+ * impl 0 = SIMT fp32, 1 = tcgen05 bf16 operands -> fp32 C, 2 = tcgen05 with a bf16 C (accumulate ignored). */
 int  argsim_test_gemm(int32_t device, int32_t impl, int32_t M, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
                       const float* A, const float* B, const float* bias_or_null, float alpha,
                       int32_t accumulate, float* C_inout, float* ms_or_null);

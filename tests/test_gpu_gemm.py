@@ -28,6 +28,10 @@ def _case(M, N, K, a_mn, b_mn, bias=False, alpha=1.0, acc=False, seed=0):
     out, ms = _lib.test_gemm(1, Ain, Bin, a_mn, b_mn, bias=bi, alpha=alpha, C0=C0)
     err = np.abs(out - ref).max() / (np.abs(ref).max() + 1e-9)
     assert err < 2e-3, (M, N, K, a_mn, b_mn, err)
+    if not acc:   # bf16-typed output (activations): same product, rounded once to bf16
+        outh, _ = _lib.test_gemm(2, Ain, Bin, a_mn, b_mn, bias=bi, alpha=alpha)
+        errh = np.abs(outh - ref).max() / (np.abs(ref).max() + 1e-9)
+        assert errh < 6e-3, (M, N, K, a_mn, b_mn, errh)
     sim, _ = _lib.test_gemm(0, Ain, Bin, a_mn, b_mn, bias=bi, alpha=alpha, C0=C0)   # SIMT fp32 twin
     ref32 = alpha * (A.astype(np.float64) @ B.astype(np.float64).T) + (bi if bias else 0) + (C0 if acc else 0)
     assert np.abs(sim - ref32).max() / (np.abs(ref32).max() + 1e-9) < 1e-5
@@ -70,3 +74,16 @@ def test_model_shapes():
     _case(900, 512, 3072, 0, 1)                        # dgrad through [W_f;W_b]
     _case(64, 1024, 1024, 0, 1, bias=True)             # latent affine, tiny M
     _case(1024, 512, 64, 1, 1)                         # latent wgrad, K = batch
+
+
+@pytest.mark.parametrize('a_mn,b_mn', [(0, 0), (0, 1), (1, 0), (1, 1)])
+def test_persistent_many_tiles(a_mn, b_mn):
+    # more 128 x 256 work units than SMs: every CTA walks several tiles through both TMEM accumulator buffers,
+    # ragged in M, N and K (TMA zero fill on loads, clipping on stores)
+    _case(2504, 4104, 200, a_mn, b_mn, bias=True, alpha=0.25, seed=5)   # MN-major operands need ld % 8 == 0
+    _case(3000, 2048, 72, a_mn, b_mn, acc=True, seed=6)
+
+
+def test_split_k_units():
+    _case(304, 520, 4096, 1, 1, acc=True, seed=7)     # few tiles, many k-blocks: split-K through TMA reduce-add
+    _case(256, 256, 8192, 0, 0, seed=8)

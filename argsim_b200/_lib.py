@@ -66,6 +66,7 @@ SIGNATURES = {
                                    _f32p, _f32p, C.c_float, C.c_int32, _f32p, _f32p]),
     'argsim_test_softmax_ce': (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, _f32p, _i32p, C.c_float, C.c_int32, _f32p,
                                          _f32p, _f32p, _i32p, C.POINTER(C.c_double)]),
+    'argsim_bench_exchange': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), _i32p]),
     'argsim_bench_kernel': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, _f32p, C.POINTER(C.c_double),
                                       C.POINTER(C.c_double)]),
     'argsim_plan_batch': (C.c_int, [_i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _u8p, _i32p,
@@ -182,6 +183,16 @@ def test_softmax_ce(logits, labels=None, gscale=1.0, bf16=True, write_grad=True,
     if rc != 0:
         raise RuntimeError(lib().argsim_last_error(None).decode())
     return dict(grad=grad, loss_samp=loss, err_samp=err, pred=pred, stats=np.array(stats[:]))
+
+
+def bench_exchange(method, groups, rows, iters=2000, device=0):
+    """cycles per 16-CTA all-gather round for one exchange mechanism (see argsim_bench_exchange)."""
+    cyc = C.c_double()
+    mc = np.zeros(1, np.int32)
+    rc = lib().argsim_bench_exchange(device, method, groups, rows, iters, C.byref(cyc), _p(mc, _i32p))
+    if rc != 0:
+        raise RuntimeError(lib().argsim_last_error(None).decode())
+    return cyc.value, int(mc[0])
 
 
 class Handle:

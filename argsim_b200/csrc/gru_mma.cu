@@ -387,6 +387,300 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd(const __grid_constant__ 
 }
 
 // =========================================================================================
+// forward, v2: the poll IS the operand fetch
+// =========================================================================================
+// Same decomposition as k_gru_mma_fwd (16 CTAs per group, 96 rows of R register-stationary per CTA), but the serial
+// chain of a step is cut from {poll -> smem -> barrier -> ldmatrix -> HMMA -> smem -> barrier -> gates -> barrier} to
+// {poll -> HMMA -> smem -> barrier -> gates}:
+//   * the LL exchange buffer is laid out in MMA-FRAGMENT order: word index ((row*32 + kt)*4 + q4)*2 + half holds
+//     h[row][16kt + 8half + 2q4 .. +1] (bf16x2) + the step tag, so the 16 bytes a lane needs for one k-tile of its
+//     B fragment ({b0,tag,b1,tag}) are ONE ld.volatile.v4 straight from L2 into registers -- no shared-memory staging,
+//     no ldmatrix, no block barrier between the poll and the MMAs; every warp starts its HMMAs as soon as ITS words
+//     arrived;
+//   * the 8 warps split K eight ways (64 k each, all 6 m-tiles: 96 registers of R per thread), so no operand word is
+//     fetched twice per CTA and the dependent HMMA chain per accumulator is 4 long; the 8 partial sums meet in a
+//     double-buffered shared-memory tile, ONE barrier per chunk;
+//   * the gate warp publishes the new h (LL store) BEFORE the bookkeeping stores (hs, gate cache).
+constexpr int KW = 8;   // k-slices = warps
+template <int OPT>
+__global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd2(const __grid_constant__ FwdP P) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    float* red = reinterpret_cast<float*>(sm);                         // [2][KW][CH][RED_LD] k-slice partial sums
+    float* hst = red + 2 * KW * CH * RED_LD;                           // [bslr][UN] fp32 state of the own units
+    int* s_nact = reinterpret_cast<int*>(hst + (size_t)P.bslr * UN);   // [Tseg+2] step tables
+    int* s_off = s_nact + P.Tseg + 2;
+    float* gxs = reinterpret_cast<float*>(s_off + P.Tseg + 2);         // [2][CH][3][UN] next step's gx of chunk 0 (cp.async)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < P.Tseg + 2; i += NTH) {
+        const int tt = P.t0 - 1 + i;
+        s_nact[i] = (tt >= 0 && tt < P.Ttot) ? slice_rows(P.nact[tt], blockIdx.x / CL % P.nslices, P.nslices) : 0;
+        s_off[i] = (tt >= 0 && tt <= P.Ttot) ? P.off[tt] : 0;
+    }
+    const int grp = blockIdx.x / CL, c = blockIdx.x % CL;
+    const int ns = P.nslices, d = grp / ns, sl = grp % ns;
+    const FwdDirP& A = P.dir[d];
+    const int g4 = lane >> 2, q4 = lane & 3;
+    const bool rowmaj = (P.variant & 8) != 0, repoll_all = (P.variant & 16) != 0;   // A/B switches (ARGSIM_GRU_VARIANT)
+
+    // ---- R slice -> registers (A fragments): local row lr = gate*32 + unit <-> R row gate*H + 32c + unit; k in [64w, 64w+64)
+    uint32_t a[6][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 6; ++mt) {
+        const int lr0 = mt * 16 + g4, lr1 = lr0 + 8;
+        const bf16* r0 = A.R + (size_t)((lr0 >> 5) * HH + UN * c + (lr0 & 31)) * HH;
+        const bf16* r1 = A.R + (size_t)((lr1 >> 5) * HH + UN * c + (lr1 & 31)) * HH;
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+            const int k0 = 64 * warp + 16 * kt + 2 * q4;
+            a[mt][kt][0] = *reinterpret_cast<const uint32_t*>(r0 + k0);
+            a[mt][kt][1] = *reinterpret_cast<const uint32_t*>(r1 + k0);
+            a[mt][kt][2] = *reinterpret_cast<const uint32_t*>(r0 + k0 + 8);
+            a[mt][kt][3] = *reinterpret_cast<const uint32_t*>(r1 + k0 + 8);
+        }
+    }
+    const int col = UN * c + lane;
+    const float bRr = A.bR[col], bRu = A.bR[HH + col], bRn = A.bR[2 * HH + col];
+    const int nloc = slice_rows(P.b, sl, ns);
+    for (int i = tid; i < nloc * UN; i += NTH) {
+        const int jl = i >> 5, u = i & 31;
+        hst[i] = A.h0 ? A.h0[(size_t)(jl * ns + sl) * HH + UN * c + u] : 0.f;
+    }
+    const size_t xpar = (size_t)P.bslr * (HH / 2);
+    unsigned long long* X = P.xbuf + (size_t)grp * 2 * xpar;
+    __syncthreads();
+
+    int na_prev = 0;
+    bool first = true;
+    bool staged = false;   // chunk 0 of the current step has its gx in gxs[k & 1] (copied by THIS thread one step ago)
+    unsigned rbuf = 0;
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long plast = clock64();
+    // step tables are read one step ahead (the shared-memory latency of the lookups is off the serial chain)
+    int na_nx = NA(A.reverse ? P.t0 + P.Tseg - 1 : P.t0), off_nx = OFF(A.reverse ? P.t0 + P.Tseg - 1 : P.t0);
+    for (int k = 0; k < P.Tseg; ++k) {
+        const int t = A.reverse ? P.t0 + P.Tseg - 1 - k : P.t0 + k;
+        const int na = (OPT & 1) ? na_nx : NA(t);
+        const long long row_base = (OPT & 1) ? off_nx : OFF(t);
+        if ((OPT & 1) && k + 1 < P.Tseg) {
+            const int tn = A.reverse ? t - 1 : t + 1;
+            na_nx = NA(tn); off_nx = OFF(tn);
+        }
+        if (na == 0) {
+            if (A.reverse) continue;
+            break;
+        }
+        PROF_MARK(0);
+        const int npoll = first ? 0 : min(na, na_prev);
+        const unsigned tag = P.tag_base + (unsigned)(k - 1), tagw = P.tag_base + (unsigned)k;
+        const unsigned long long* Xr = X + (size_t)((k - 1) & 1) * xpar;
+        unsigned long long* Xw = X + (size_t)(k & 1) * xpar;
+        for (int ch = 0; ch * CH < na; ++ch) {
+            const int nrows = min(CH, na - ch * CH);
+            const int ntl = nrows > 8 ? 2 : 1;   // n=8 MMA tiles that hold live rows (warp-uniform)
+            // ---------------- operand fetch: B fragments of h_{t-1} for this warp's 64 k, rows g4 (+8)
+            uint32_t b[2][4][2];
+            if (first) {
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const int jl = ch * CH + nt * 8 + g4;
+                    const float* hp = (A.h0 && nt < ntl && jl < na) ? A.h0 + (size_t)(jl * ns + sl) * HH + 64 * warp + 2 * q4 : nullptr;
+#pragma unroll
+                    for (int kt = 0; kt < 4; ++kt) {
+                        if (hp) {
+                            const float2 v0 = *reinterpret_cast<const float2*>(hp + 16 * kt);
+                            const float2 v1 = *reinterpret_cast<const float2*>(hp + 16 * kt + 8);
+                            b[nt][kt][0] = bf16_bits(v0.x) | (bf16_bits(v0.y) << 16);
+                            b[nt][kt][1] = bf16_bits(v1.x) | (bf16_bits(v1.y) << 16);
+                        } else {
+                            b[nt][kt][0] = b[nt][kt][1] = 0u;
+                        }
+                    }
+                }
+            } else {
+                bool need[2];
+                const unsigned long long* src[2];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    const int jl = ch * CH + nt * 8 + g4;
+                    need[nt] = nt < ntl && jl < npoll;   // rows >= npoll join here with zero state (reverse direction)
+                    src[nt] = rowmaj ? Xr + ((size_t)jl * 32 + 4 * warp) * 8 + 2 * q4 : Xr + ((size_t)(4 * warp) * P.bslr + jl) * 8 + 2 * q4;
+                }
+                uint4 x[2][4];
+                bool miss[2][4];   // words still outstanding: only those are re-polled (fewer L1TEX wavefronts per round)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int kt = 0; kt < 4; ++kt) miss[nt][kt] = need[nt];
+                bool ok;
+                const long long tp0 = clock64();
+                const size_t kts = rowmaj ? 8 : (size_t)P.bslr * 8;
+                do {
+                    ok = true;
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int kt = 0; kt < 4; ++kt)
+                            if (miss[nt][kt]) x[nt][kt] = ll_load2(src[nt] + kts * kt);
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int kt = 0; kt < 4; ++kt)
+                            if (miss[nt][kt]) {
+                                const bool m = (x[nt][kt].y != tag || x[nt][kt].w != tag);
+                                if (!repoll_all) miss[nt][kt] = m;
+                                if (m) ok = false;
+                            }
+                    POLL_GUARD(tp0);
+                } while (!ok);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int kt = 0; kt < 4; ++kt) {
+                        b[nt][kt][0] = need[nt] ? x[nt][kt].x : 0u;
+                        b[nt][kt][1] = need[nt] ? x[nt][kt].z : 0u;
+                    }
+            }
+            PROF_MARK(1);   // operand fetch (poll)
+            // gx of the rows this warp finishes (row n -> warp n & 7): L2 hits (prefetched two steps ago), they
+            // complete under the HMMAs and the barrier
+            float gxv[2][3];
+            const bool from_smem = (P.variant & 64) && ch == 0 && staged;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = warp + 8 * e;
+                gxv[e][0] = gxv[e][1] = gxv[e][2] = 0.f;
+                if (n < nrows && !from_smem) {
+                    const float* gp = A.gx + (size_t)(row_base + (long long)(ch * CH + n) * ns + sl) * A.ld_gx + col;
+                    gxv[e][0] = ld_f32(gp); gxv[e][1] = ld_f32(gp + HH); gxv[e][2] = ld_f32(gp + 2 * HH);
+                }
+            }
+            float* redw = red + ((size_t)(rbuf * KW + warp) * CH) * RED_LD;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                if (nt >= ntl) continue;
+                float acc[6][4];
+#pragma unroll
+                for (int mt = 0; mt < 6; ++mt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[mt][i] = 0.f;
+#pragma unroll
+                for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+                    for (int mt = 0; mt < 6; ++mt) mma16816(acc[mt], a[mt][kt], b[nt][kt][0], b[nt][kt][1]);
+#pragma unroll
+                for (int mt = 0; mt < 6; ++mt) {
+                    float* rp = redw + (nt * 8 + 2 * q4) * RED_LD + mt * 16 + g4;
+                    rp[0] = acc[mt][0]; rp[RED_LD] = acc[mt][1];
+                    rp[8] = acc[mt][2]; rp[RED_LD + 8] = acc[mt][3];
+                }
+            }
+            PROF_MARK(2);   // MMA + partial stores
+            __syncthreads();
+            PROF_MARK(3);   // barrier issue (the wait itself is deferred to the first dependent instruction)
+            // ---------------- gates: lane = unit, warp -> rows w, w+8
+            const float* redr = red + ((size_t)(rbuf * KW) * CH) * RED_LD;
+            if (from_smem) {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");   // own copies, issued one step ago
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = warp + 8 * e;
+                    if (n < nrows) {
+                        const float* gs = gxs + (((k & 1) * CH + n) * 3) * UN + lane;
+                        gxv[e][0] = gs[0]; gxv[e][1] = gs[UN]; gxv[e][2] = gs[2 * UN];
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = warp + 8 * e;
+                if (n < nrows) {
+                    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                    for (int q = 0; q < KW; ++q) {
+                        const float* rb = redr + (q * CH + n) * RED_LD;
+                        s0 += rb[lane]; s1 += rb[32 + lane]; s2 += rb[64 + lane];
+                    }
+                    if ((OPT & 2) && e == 0) PROF_MARK(4);   // barrier wait + partial-sum reads
+                    const float r = sigm(gxv[e][0] + s0 + bRr);
+                    const float z = sigm(gxv[e][1] + s1 + bRu);
+                    const float qq = s2 + bRn;
+                    const float nn = tanh_fast(gxv[e][2] + r * qq);
+                    const int jl = ch * CH + n;
+                    const float hp = hst[jl * UN + lane];
+                    const float h = (1.f - z) * nn + z * hp;
+                    const __nv_bfloat16 hb16 = __float2bfloat16(h);
+                    // publish first: this store is on every peer's critical path
+                    const uint32_t hb = (uint32_t)__bfloat16_as_ushort(hb16);
+                    const uint32_t ob = __shfl_down_sync(0xffffffffu, hb, 1);
+                    if (!(lane & 1))
+                        ll_store(Xw + (rowmaj ? ((size_t)jl * 32 + 2 * c + (lane >> 4)) : ((size_t)(2 * c + (lane >> 4)) * P.bslr + jl)) * 8 + ((lane & 7) >> 1) * 2 + ((lane >> 3) & 1), hb | (ob << 16), tagw);
+                    if ((OPT & 2) && e == 0) PROF_MARK(5);   // gate math + publish
+                    hst[jl * UN + lane] = h;
+                    const size_t row = (size_t)(row_base + (long long)jl * ns + sl);
+                    if (A.hs_h) A.hs_h[row * A.ld_hs + col] = hb16;
+                    if (A.hs_f) A.hs_f[row * A.ld_hs + col] = h;
+                    if (A.cache) {
+                        float* cp = A.cache + row * 4 * HH + col;
+                        cp[0] = r; cp[HH] = z; cp[2 * HH] = nn; cp[3 * HH] = qq;
+                    }
+                }
+            }
+            PROF_MARK(6);   // bookkeeping stores (+ second row)
+            // next step's gx of chunk 0 -> shared memory (cp.async by the thread that will use it: no barrier needed);
+            // issued after the publish, it lands while the exchange is in flight (L2 hit: prefetched one step earlier)
+            if ((P.variant & 64) && ch == 0) {
+                staged = false;
+                if (k + 1 < P.Tseg) {
+                    const int tn = A.reverse ? t - 1 : t + 1;
+                    const int nan = NA(tn);
+                    if (nan > 0) {
+                        staged = true;
+                        const long long rbn = OFF(tn);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int n = warp + 8 * e;
+                            if (n < nan) {
+                                const float* gp = A.gx + (size_t)(rbn + (long long)n * ns + sl) * A.ld_gx + col;
+                                float* gd = gxs + ((((k + 1) & 1) * CH + n) * 3) * UN + lane;
+                                cp_async4(gd, gp); cp_async4(gd + UN, gp + HH); cp_async4(gd + 2 * UN, gp + 2 * HH);
+                            }
+                        }
+                        asm volatile("cp.async.commit_group;" ::: "memory");
+                    }
+                }
+            }
+            // gx rows of the step after next -> L2, by the warps that have no row to finish in this chunk
+            if ((P.variant & 2) && ch == 0 && warp >= nrows && k + 2 < P.Tseg) {
+                const int tn = A.reverse ? t - 2 : t + 2;
+                const int nan = NA(tn);
+                const long long rbn = OFF(tn);
+                const int nidle = NTH / 32 - nrows;
+                for (int n = warp - nrows; n < nan; n += nidle) {
+                    const float* gp = A.gx + (size_t)(rbn + (long long)n * ns + sl) * A.ld_gx + UN * c;
+                    if (lane < 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + lane * HH));
+                }
+            }
+            rbuf ^= 1u;
+            // A/B: keep the warps without a gate row from spinning on the next step's operands while the gate warps still
+            // publish (their polls queue in front of the LL stores in the in-order LSU)
+            if (P.variant & 32) __syncthreads();
+        }
+        na_prev = na;
+        first = false;
+        PROF_MARK(7);
+    }
+    if (A.hT) {   // state handed to the next time segment of this layer
+        __syncthreads();
+        for (int i = tid; i < nloc * UN; i += NTH) {
+            const int jl = i >> 5, u = i & 31;
+            A.hT[(size_t)(jl * ns + sl) * HH + UN * c + u] = hst[i];
+        }
+    }
+    if (P.prof && tid == 0)
+        for (int i = 0; i < 8; ++i) P.prof[blockIdx.x * 8 + i] = pacc[i];
+}
+
+// =========================================================================================
 // backward (BPTT)
 // =========================================================================================
 __device__ __forceinline__ size_t yidx(int par, int dest, int src, int pair, int ul, int npair) {
@@ -395,8 +689,8 @@ __device__ __forceinline__ size_t yidx(int par, int dest, int src, int pair, int
 
 __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ BwdP P) {
     extern __shared__ __align__(16) unsigned char sm[];
-    bf16* Gs = reinterpret_cast<bf16*>(sm);                               // [CH][GS_LD]  own dgh columns of the chunk
-    float* cs = reinterpret_cast<float*>(sm + CH * GS_LD * 2);           // [bslr][UN]   d*u carried to the next step
+    bf16* Gs0 = reinterpret_cast<bf16*>(sm);                              // [2][CH][GS_LD] own dgh columns of the chunk (double
+    float* cs = reinterpret_cast<float*>(sm + 2 * CH * GS_LD * 2);       // buffered: no barrier after the MMA) ; [bslr][UN] d*u carried
     int* s_nact = reinterpret_cast<int*>(cs + (size_t)P.bslr * UN);     // [Tmax], [Tmax+1]: step tables in smem
     int* s_off = s_nact + P.Tseg + 2;
     // cp.async landing zone for the NEXT step's gate inputs of chunk 0 (dhs, r, u, n, q: fp32; h_prev: bf16),
@@ -444,6 +738,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
 
     int na_prev = 0;
     bool first = true;
+    unsigned gbuf = 0;
     bool staged = false;      // chunk 0 of the current step was prefetched into stg[k & 1]
     int k_last = -1;
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -502,56 +797,14 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
                 }
             }
             PROF_MARK(1);   // reduce-scatter receive
-            // ---- prefetch the NEXT step's chunk-0 gate inputs (issued after the poll: the L1TEX queue is in order)
-            bool staged_next = false;
-            if ((P.variant & 1) && ch == 0 && k + 1 < P.Tseg && A.hs_h) {
-                const int tq = A.reverse ? t + 1 : t - 1;
-                const int naq = NA(tq);
-                if (naq > 0) {
-                    staged_next = true;
-                    const int thq = A.reverse ? tq + 1 : tq - 1;
-                    const int nhq = (thq >= 0 && thq < P.Ttot) ? min(naq, NA(thq)) : 0;
-                    const long long rbq = OFF(tq), rbh = (thq >= 0 && thq <= P.Ttot) ? OFF(thq) : 0;
-                    const int pq = (k + 1) & 1;
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int n = warp + 8 * e;
-                        if (n < naq) {
-                            const size_t rq = (size_t)(rbq + (long long)n * ns + sl);
-                            float* d = stg + ((pq * CH + n) * 5) * UN + lane;
-                            cp_async4(d, A.dhs + rq * A.ld_dhs + col);
-                            const float* cq = A.cache + rq * 4 * HH + col;
-                            cp_async4(d + UN, cq); cp_async4(d + 2 * UN, cq + HH);
-                            cp_async4(d + 3 * UN, cq + 2 * HH); cp_async4(d + 4 * UN, cq + 3 * HH);
-                            if (n < nhq && !(lane & 1))
-                                cp_async4(stgh + (pq * CH + n) * UN + lane, A.hs_h + (size_t)(rbh + (long long)n * ns + sl) * A.ld_hs + col);
-                        }
-                    }
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
             if (ch == 0 && staged) {
-                // everything but the group just committed (= this step's inputs, issued one step ago) has landed
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");   // this step's inputs, issued one step ago by this thread's warp
                 __syncwarp();
             }
-            // gate inputs of the BPTT step after next -> L2 (by the warps without a row in this chunk), so that the
-            // cp.async staging issued next step hits L2 and does not hold up the in-order L1TEX queue
-            if ((P.variant & 2) && ch == 0 && warp >= nrows && k + 2 < P.Tseg) {
-                const int tn = A.reverse ? t + 2 : t - 2;
-                const int nan = NA(tn);
-                const long long rbn = OFF(tn);
-                const int thn = A.reverse ? tn + 1 : tn - 1;
-                const long long rbh = (thn >= 0 && thn < P.Ttot) ? OFF(thn) : -1;
-                const int nidle = NTH / 32 - nrows;
-                for (int n = warp - nrows; n < nan; n += nidle) {
-                    const size_t rown = (size_t)(rbn + (long long)n * ns + sl);
-                    if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cache + rown * 4 * HH + UN * c + lane * HH));
-                    if (lane == 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.dhs + rown * A.ld_dhs + UN * c));
-                    if (lane == 5 && rbh >= 0 && A.hs_h && n < NA(thn))
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.hs_h + (size_t)(rbh + (long long)n * ns + sl) * A.ld_hs + UN * c));
-                }
-            }
+            bf16* Gs = Gs0 + gbuf * CH * GS_LD;
+            float sv[2][5];      // dr, du, dn, dnr, hp of the rows this warp finishes: written to HBM after the send
+            size_t srow[2];
+            bool slive[2] = {false, false};
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int n = warp + 8 * e;
@@ -588,13 +841,9 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
                     dr = dn * qq * r * (1.f - r);
                     dnr = dn * r;
                     cs[jl * UN + lane] = dd * z;
-                    const size_t o = row * A.ld_dg + col;
-                    if (A.dgx_f) { A.dgx_f[o] = dr; A.dgx_f[o + HH] = du; A.dgx_f[o + 2 * HH] = dn; }
-                    if (A.dgx_h) { A.dgx_h[o] = __float2bfloat16(dr); A.dgx_h[o + HH] = __float2bfloat16(du); A.dgx_h[o + 2 * HH] = __float2bfloat16(dn); }
-                    if (A.dgh_f) { A.dgh_f[o] = dr; A.dgh_f[o + HH] = du; A.dgh_f[o + 2 * HH] = dnr; }
-                    if (A.dgh_h) { A.dgh_h[o] = __float2bfloat16(dr); A.dgh_h[o + HH] = __float2bfloat16(du); A.dgh_h[o + 2 * HH] = __float2bfloat16(dnr); }
-                    if (A.hp_f) A.hp_f[row * A.ld_hp + col] = hp;
-                    if (A.hp_h) A.hp_h[row * A.ld_hp + col] = __float2bfloat16(hp);
+                    sv[e][0] = dr; sv[e][1] = du; sv[e][2] = dn; sv[e][3] = dnr; sv[e][4] = hp;
+                    srow[e] = row;
+                    slive[e] = true;
                 }
                 bf16* gp = Gs + n * GS_LD + lane;
                 gp[0] = __float2bfloat16(dr); gp[32] = __float2bfloat16(du); gp[64] = __float2bfloat16(dnr);
@@ -637,9 +886,68 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
                     ll_store(Y + yidx(parw, o1 >> 5, c, pair, o1 & 31, npair), bf16_bits(acc[mt][nt][2]) | (bf16_bits(acc[mt][nt][3]) << 16), tagw);
                 }
             PROF_MARK(5);   // send
-            __syncthreads();
-            PROF_MARK(6);   // barrier 2
+            // ---- bookkeeping, off the serial chain: this step's gate gradients -> HBM (operands of the batched wgrad / dgrad GEMMs)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                if (!slive[e]) continue;
+                const float dr = sv[e][0], du = sv[e][1], dn = sv[e][2], dnr = sv[e][3], hp = sv[e][4];
+                const size_t row = srow[e];
+                const size_t o = row * A.ld_dg + col;
+                if (A.dgx_f) { A.dgx_f[o] = dr; A.dgx_f[o + HH] = du; A.dgx_f[o + 2 * HH] = dn; }
+                if (A.dgx_h) { A.dgx_h[o] = __float2bfloat16(dr); A.dgx_h[o + HH] = __float2bfloat16(du); A.dgx_h[o + 2 * HH] = __float2bfloat16(dn); }
+                if (A.dgh_f) { A.dgh_f[o] = dr; A.dgh_f[o + HH] = du; A.dgh_f[o + 2 * HH] = dnr; }
+                if (A.dgh_h) { A.dgh_h[o] = __float2bfloat16(dr); A.dgh_h[o + HH] = __float2bfloat16(du); A.dgh_h[o + 2 * HH] = __float2bfloat16(dnr); }
+                if (A.hp_f) A.hp_f[row * A.ld_hp + col] = hp;
+                if (A.hp_h) A.hp_h[row * A.ld_hp + col] = __float2bfloat16(hp);
+            }
+            // ---- prefetch the NEXT step's chunk-0 gate inputs (after the send: off the serial chain)
+            bool staged_next = false;
+            if ((P.variant & 1) && ch == 0 && k + 1 < P.Tseg && A.hs_h) {
+                const int tq = A.reverse ? t + 1 : t - 1;
+                const int naq = NA(tq);
+                if (naq > 0) {
+                    staged_next = true;
+                    const int thq = A.reverse ? tq + 1 : tq - 1;
+                    const int nhq = (thq >= 0 && thq < P.Ttot) ? min(naq, NA(thq)) : 0;
+                    const long long rbq = OFF(tq), rbh = (thq >= 0 && thq <= P.Ttot) ? OFF(thq) : 0;
+                    const int pq = (k + 1) & 1;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int n = warp + 8 * e;
+                        if (n < naq) {
+                            const size_t rq = (size_t)(rbq + (long long)n * ns + sl);
+                            float* d = stg + ((pq * CH + n) * 5) * UN + lane;
+                            cp_async4(d, A.dhs + rq * A.ld_dhs + col);
+                            const float* cq = A.cache + rq * 4 * HH + col;
+                            cp_async4(d + UN, cq); cp_async4(d + 2 * UN, cq + HH);
+                            cp_async4(d + 3 * UN, cq + 2 * HH); cp_async4(d + 4 * UN, cq + 3 * HH);
+                            if (n < nhq && !(lane & 1))
+                                cp_async4(stgh + (pq * CH + n) * UN + lane, A.hs_h + (size_t)(rbh + (long long)n * ns + sl) * A.ld_hs + col);
+                        }
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            // gate inputs of the BPTT step after next -> L2 (by the warps without a row in this chunk), so that the
+            // cp.async staging issued next step hits L2 and does not hold up the in-order L1TEX queue
+            if ((P.variant & 2) && ch == 0 && warp >= nrows && k + 2 < P.Tseg) {
+                const int tn = A.reverse ? t + 2 : t - 2;
+                const int nan = NA(tn);
+                const long long rbn = OFF(tn);
+                const int thn = A.reverse ? tn + 1 : tn - 1;
+                const long long rbh = (thn >= 0 && thn < P.Ttot) ? OFF(thn) : -1;
+                const int nidle = NTH / 32 - nrows;
+                for (int n = warp - nrows; n < nan; n += nidle) {
+                    const size_t rown = (size_t)(rbn + (long long)n * ns + sl);
+                    if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.cache + rown * 4 * HH + UN * c + lane * HH));
+                    if (lane == 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.dhs + rown * A.ld_dhs + UN * c));
+                    if (lane == 5 && rbh >= 0 && A.hs_h && n < NA(thn))
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.hs_h + (size_t)(rbh + (long long)n * ns + sl) * A.ld_hs + UN * c));
+                }
+            }
+            PROF_MARK(6);   // bookkeeping stores + next-step staging
             if (ch == 0) staged = staged_next;
+            gbuf ^= 1u;
         }
         na_prev = na;
         first = false;
@@ -697,7 +1005,9 @@ struct GruMmaCtx {
     unsigned long long* ybuf[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
     size_t ycap[NSLOT] = {0, 0, 0, 0};
     bool attr_set = false;
-    int variant_fwd = 2, variant_bwd = 3;
+    int variant_fwd = 26, variant_bwd = 3;   // fwd: L2 prefetch + row-major LL layout + re-poll all words (best of the measured A/B set)
+    int fwd2_opt = 0;
+    bool fwd_v1 = false;         // ARGSIM_GRU_FWD_V1=1: the first forward kernel (smem-staged operands), for A/B runs
     long long* prof = nullptr;   // ARGSIM_GRU_PROF=1: per-phase clocks, printed to stderr after every launch
 };
 
@@ -708,8 +1018,18 @@ GruMmaCtx* gru_mma_create(int device) {
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_BSL * HS_LD * 2 + 4 * CH * RED_LD * 4 + MAX_BSL * UN * 4 + 2 * 4100 * 4));
-    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, CH * GS_LD * 2 + MAX_BSL * UN * 4 + 2 * 4100 * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2));
+    {
+        const int fwd2_smem = 2 * KW * CH * RED_LD * 4 + MAX_BSL * UN * 4 + 2 * 4100 * 4 + 2 * CH * 3 * UN * 4;
+        CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
+        if (const char* v = getenv("ARGSIM_GRU_FWD2_OPT")) c->fwd2_opt = atoi(v) & 3;
+    }
+    c->fwd_v1 = getenv("ARGSIM_GRU_FWD_V1") != nullptr;
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH * GS_LD * 2 + MAX_BSL * UN * 4 + 2 * 4100 * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2));
     if (const char* v = getenv("ARGSIM_GRU_VARIANT")) { c->variant_fwd = atoi(v) & 7; c->variant_bwd = (atoi(v) >> 3) & 7; }
+    if (const char* v = getenv("ARGSIM_GRU_FWD2_VARIANT")) c->variant_fwd = atoi(v);
     if (getenv("ARGSIM_GRU_PROF")) CUDA_CHECK(cudaMalloc(&c->prof, 160 * 8 * sizeof(long long)));
     return c;
 }
@@ -789,9 +1109,11 @@ void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& 
     P.prof = c->prof;
     P.variant = c->variant_fwd;
     if (c->launch_id >= (1u << 20)) c->launch_id = 1;
-    const size_t smem = (size_t)bslr * HS_LD * 2 + 4 * CH * RED_LD * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4;
+    const size_t smem = c->fwd_v1 ? (size_t)bslr * HS_LD * 2 + 4 * CH * RED_LD * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4
+                                  : (size_t)2 * KW * CH * RED_LD * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 2 * CH * 3 * UN * 4;
     void* args[] = {&P};
-    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gru_mma_fwd, dim3(groups * CL), dim3(NTH), args, smem, s));
+    void* fwd2_fn[4] = {(void*)k_gru_mma_fwd2<0>, (void*)k_gru_mma_fwd2<1>, (void*)k_gru_mma_fwd2<2>, (void*)k_gru_mma_fwd2<3>};
+    CUDA_CHECK(cudaLaunchCooperativeKernel(c->fwd_v1 ? (void*)k_gru_mma_fwd : fwd2_fn[c->fwd2_opt], dim3(groups * CL), dim3(NTH), args, smem, s));
     COUNT_LAUNCH();
     dump_prof(c, ndir == 2 ? "fwd_enc" : "fwd_dec", groups * CL, Tseg, s);
 }
@@ -830,7 +1152,7 @@ void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& 
     P.prof = c->prof;
     P.variant = c->variant_bwd;
     if (c->launch_id >= (1u << 20)) c->launch_id = 1;
-    const size_t smem = (size_t)CH * GS_LD * 2 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2;
+    const size_t smem = (size_t)2 * CH * GS_LD * 2 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2;
     void* args[] = {&P};
     CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gru_mma_bwd, dim3(groups * CL), dim3(NTH), args, smem, s));
     COUNT_LAUNCH();

@@ -106,3 +106,5 @@ void gru_mma_fwd(GruMmaCtx*, const GruFwdArgs* dirs, int ndir, const SeqPlan& P,
                  int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0);
 void gru_mma_bwd(GruMmaCtx*, const GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
                  int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0);
+// xbench.cu: exchange-latency measurement hook
+int xbench_run(int device, int method, int groups, int rows, int iters, double* cycles_per_iter, int* max_clusters);

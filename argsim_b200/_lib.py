@@ -57,6 +57,7 @@ SIGNATURES = {
     'argsim_embed': (C.c_int, [C.c_void_p, _i32p, C.c_int32, C.c_int32, _f32p]),
     'argsim_decode_init': (C.c_int, [C.c_void_p, _f32p, C.c_int32, _f32p]),
     'argsim_decode_step': (C.c_int, [C.c_void_p, _i32p, C.c_int32, _f32p, _i32p]),
+    'argsim_decode': (C.c_int, [C.c_void_p, _f32p, C.c_int32, C.c_int32, _i32p, _i32p]),
     'argsim_save': (C.c_int, [C.c_void_p, C.c_char_p]),
     'argsim_load': (C.c_int, [C.c_void_p, C.c_char_p]),
     'argsim_bench_resident': (C.c_int, [C.c_void_p, C.c_int32, _f32p]),
@@ -347,6 +348,15 @@ class Handle:
         pred = np.empty(lead.shape[0], np.int32)
         self._ck(self.L.argsim_decode_step(self.h, _p(lead, _i32p), lead.shape[0], _p(state, _f32p), _p(pred, _i32p)))
         return pred, state
+
+    def decode(self, z, steps=256):
+        """greedy decode of latent states, whole loop on the device: int32 (b, t), t <= steps (may be 0)."""
+        z = np.ascontiguousarray(z, np.float32)
+        b = z.shape[0]
+        tok = np.zeros((b, steps), np.int32)
+        t = np.zeros(1, np.int32)
+        self._ck(self.L.argsim_decode(self.h, _p(z, _f32p), b, steps, _p(tok, _i32p), _p(t, _i32p)))
+        return np.ascontiguousarray(tok[:, :int(t[0])])
 
     def save(self, path):
         self._ck(self.L.argsim_save(self.h, str(path).encode()))

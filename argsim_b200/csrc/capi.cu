@@ -155,6 +155,12 @@ int argsim_decode_step(argsim_handle* h, const int32_t* lead, int32_t b, float* 
     API_BEGIN(h) h->e->decode_step(lead, b, state_inout, pred);
     API_END(h)
 }
+int argsim_decode(argsim_handle* h, const float* z, int32_t b, int32_t steps, int32_t* tokens, int32_t* t_out) {
+    API_BEGIN(h)
+    const int T = h->e->decode_loop(z, b, steps, tokens);
+    if (t_out) *t_out = T;
+    API_END(h)
+}
 int argsim_save(argsim_handle* h, const char* path) {
     API_BEGIN(h) h->e->save(path);
     API_END(h)

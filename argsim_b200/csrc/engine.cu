@@ -217,7 +217,11 @@ void Engine::gemm(const Mat& A, int a_mn, const Mat& B, int b_mn, const Mat& C, 
     if (!q) q = st[0];
     if (use_tc) {
         if (!A.h || !B.h) throw std::runtime_error("gemm: bf16 operand view missing (internal error)");
+        // per-group device timers (bench.py roofline): batched GEMMs outside the explicitly named groups, by role
+        const bool timed = (cfg.flags & 8) && !in_ktimer && M >= 256;
+        if (timed) kbegin(a_mn ? "k:gemm_wgrad" : (b_mn ? "k:gemm_dgrad_or_dense" : "k:gemm_proj"), q);
         gemm_tc(A.h, A.ld, a_mn, B.h, B.ld, b_mn, C.f, C.h, C.ld, (int)M, N, (int)K, alpha, bias, accumulate, q);
+        if (timed) kend(q, 2.0 * (double)M * N * K * 1e-9);
     } else {
         if (!A.f || !B.f) throw std::runtime_error("gemm: fp32 operand view missing (internal error)");
         gemm_simt(A.f, A.ld, a_mn, B.f, B.ld, b_mn, C.f, C.ld, (int)M, N, (int)K, alpha, bias, accumulate, C.h, q);
@@ -283,8 +287,9 @@ void Engine::phase(const char* name) {
     CUDA_CHECK(cudaEventRecord(pev[pcount], st[0]));
     ++pcount;
 }
-void Engine::kbegin(const char* name) {
+void Engine::kbegin(const char* name, cudaStream_t q) {
     if (!(cfg.flags & 8)) return;
+    in_ktimer = true;
     if (kcount == ktimers.size()) {
         KTimer k;
         CUDA_CHECK(cudaEventCreate(&k.a));
@@ -292,12 +297,15 @@ void Engine::kbegin(const char* name) {
         ktimers.push_back(k);
     }
     ktimers[kcount].name = name;
-    CUDA_CHECK(cudaEventRecord(ktimers[kcount].a, st[0]));
+    ktimers[kcount].gflop = 0.0;
+    CUDA_CHECK(cudaEventRecord(ktimers[kcount].a, q ? q : st[0]));
 }
-void Engine::kend() {
+void Engine::kend(cudaStream_t q, double gflop) {
     if (!(cfg.flags & 8)) return;
-    CUDA_CHECK(cudaEventRecord(ktimers[kcount].b, st[0]));
+    ktimers[kcount].gflop = gflop;
+    CUDA_CHECK(cudaEventRecord(ktimers[kcount].b, q ? q : st[0]));
     ++kcount;
+    in_ktimer = false;
 }
 void Engine::collect_timings() {
     tnames.clear(); tms.clear();
@@ -308,17 +316,23 @@ void Engine::collect_timings() {
         tms.push_back(ms);
     }
     std::map<std::string, std::pair<float, int>> agg;
+    std::map<std::string, double> gf;
     for (size_t i = 0; i < kcount; ++i) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ktimers[i].a, ktimers[i].b);
         agg[ktimers[i].name].first += ms;
         agg[ktimers[i].name].second += 1;
+        gf[ktimers[i].name] += ktimers[i].gflop;
     }
     for (auto& kv : agg) {
         tnames.push_back(kv.first);
         tms.push_back(kv.second.first);
         tnames.push_back(kv.first + "#n");
         tms.push_back((float)kv.second.second);
+        if (gf[kv.first] > 0.0) {
+            tnames.push_back(kv.first + "#gflop");
+            tms.push_back((float)gf[kv.first]);
+        }
     }
 }
 
@@ -965,6 +979,64 @@ void Engine::decode_step(const int32_t* lead, int b, float* state, int32_t* pred
     CUDA_CHECK(cudaMemcpyAsync(state, dst, sizeof(float) * L * b * H, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
     cudaFree(dl); cudaFree(dpred); cudaFree(dst); cudaFree(x); cudaFree(gx); cudaFree(gh); cudaFree(ho); cudaFree(lg);
+}
+
+// decode() of the reference as ONE device-resident loop: no host round trip per token (the
+// reference does a sess.run per step, model.py:215); the all-eos stop test runs on the device and the host looks at
+// it every 16 steps.  fp32 arithmetic, the same kernels as decode_step, so both paths give identical tokens.
+int Engine::decode_loop(const float* z, int b, int steps, int32_t* tokens) {
+    if (b <= 0 || steps <= 0) throw std::runtime_error("decode: b and steps must be positive");
+    cudaStream_t s = st[0];
+    float *dz, *dst, *x, *gx, *gh, *ho, *lg;
+    int *dlead, *dpred, *dout, *dflag;
+    CUDA_CHECK(cudaMalloc(&dz, sizeof(float) * b * R));
+    CUDA_CHECK(cudaMalloc(&dst, sizeof(float) * (L + 1) * b * H));
+    CUDA_CHECK(cudaMalloc(&x, sizeof(float) * b * D));
+    CUDA_CHECK(cudaMalloc(&gx, sizeof(float) * b * 3 * H));
+    CUDA_CHECK(cudaMalloc(&gh, sizeof(float) * b * 3 * H));
+    CUDA_CHECK(cudaMalloc(&ho, sizeof(float) * b * D));
+    CUDA_CHECK(cudaMalloc(&lg, sizeof(float) * b * V));
+    CUDA_CHECK(cudaMalloc(&dlead, sizeof(int) * b));
+    CUDA_CHECK(cudaMalloc(&dpred, sizeof(int) * b));
+    CUDA_CHECK(cudaMalloc(&dout, sizeof(int) * (size_t)b * steps));
+    CUDA_CHECK(cudaMalloc(&dflag, sizeof(int) * 2));
+    CUDA_CHECK(cudaMemsetAsync(dflag, 0, sizeof(int) * 2, s));
+    copy_sync(dz, z, sizeof(float) * b * R, cudaMemcpyHostToDevice);
+    // state_in = stack((ex(z),) * L)  (model.py:156-158)
+    float* dh = dst + (size_t)L * b * H;
+    gemm_simt(dz, R, 0, p + pinfo("latent/ex/kernel").off, D, 1, dh, H, b, D, R, 1.f, p + pinfo("latent/ex/bias").off, 0, nullptr, s);
+    for (int l = 0; l < L; ++l)
+        CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)l * b * H, dh, sizeof(float) * b * H, cudaMemcpyDeviceToDevice, s));
+    launch_fill_i32(dlead, b, cfg.bos, s);
+    int flag[2] = {0, 0};
+    for (int t = 0; t < steps; ++t) {
+        launch_embed_gather_f32(dlead, b, p + pinfo("embed/embedding").off, D, x, s);
+        const float* in = x;
+        for (int l = 0; l < L; ++l) {
+            const std::string pre = "decode/rnn/l" + std::to_string(l) + "/";
+            gemm_simt(in, D, 0, p + pinfo(pre + "W").off, D, 0, gx, 3 * H, b, 3 * H, D, 1.f, p + pinfo(pre + "bW").off, 0, nullptr, s);
+            float* stl = dst + (size_t)l * b * H;
+            gru_generic_cell(gx, 3 * H, p + pinfo(pre + "R").off, p + pinfo(pre + "bR").off, stl, gh, b, H, s);
+            in = stl;
+        }
+        gemm_simt(in, H, 0, p + pinfo("decode/out/kernel").off, D, 1, ho, D, b, D, D, 1.f, p + pinfo("decode/out/bias").off, 0, nullptr, s);
+        gemm_simt(ho, D, 0, p + pinfo("embed/embedding").off, D, 0, lg, V, b, V, D, 1.0f / sqrtf((float)D), nullptr, 0, nullptr, s);
+        launch_ce_f32(lg, V, nullptr, b, V, 0.f, 0, nullptr, nullptr, dpred, d_stats, s);
+        launch_decode_advance(dpred, b, cfg.eos, dout + (size_t)t * b, dlead, dflag, t, s);
+        if ((t & 15) == 15 || t + 1 == steps) {
+            copy_sync(flag, dflag, sizeof(flag), cudaMemcpyDeviceToHost);
+            if (flag[0]) break;
+        }
+    }
+    const int T = flag[1];
+    std::vector<int32_t> tb((size_t)std::max(T, 1) * b);
+    if (T > 0) copy_sync(tb.data(), dout, sizeof(int) * (size_t)T * b, cudaMemcpyDeviceToHost);
+    for (int i = 0; i < b; ++i)
+        for (int t = 0; t < T; ++t) tokens[(size_t)i * steps + t] = tb[(size_t)t * b + i];
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    cudaFree(dz); cudaFree(dst); cudaFree(x); cudaFree(gx); cudaFree(gh); cudaFree(ho); cudaFree(lg);
+    cudaFree(dlead); cudaFree(dpred); cudaFree(dout); cudaFree(dflag);
+    return T;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -36,6 +36,7 @@ public:
 struct KTimer {
     std::string name;
     cudaEvent_t a, b;
+    double gflop = 0.0;   // algorithmic work of the bracketed launches (GEMM groups), 0 if the caller accounts for it
 };
 
 class Engine {
@@ -73,6 +74,7 @@ public:
     void embed(const int32_t* src, int b, int T, float* mu_out);
     void embed_one(const int32_t* src, int b, int T, float* mu_out);
     void decode_init(const float* z, int b, float* state);
+    int decode_loop(const float* z, int b, int steps, int32_t* tokens);   // returns t <= steps; tokens is (b, steps) row-major
     void decode_step(const int32_t* lead, int b, float* state, int32_t* pred);
     void bench_resident(int iters, float* ms);
     void save(const char* path);
@@ -124,8 +126,9 @@ private:
     void phase(const char* name);
     std::vector<KTimer> ktimers;
     size_t kcount = 0;
-    void kbegin(const char* name);
-    void kend();
+    void kbegin(const char* name, cudaStream_t q = nullptr);
+    void kend(cudaStream_t q = nullptr, double gflop = 0.0);
+    bool in_ktimer = false;
     void collect_timings();
 
     Mat pmat(const std::string& name);

@@ -639,9 +639,15 @@ void gemm_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn,
         const int tiles = W.tiles_m * W.tiles_n;
         int splits = 1;
         if (Cf && tiles * 2 <= g_num_sms && W.nkb_total >= 8) splits = std::max(1, std::min(std::min(W.nkb_total / 4, g_num_sms / tiles), 64));
+        // bf16 output with fewer work units than half the SMs and a long K (dho = dlogits . E): two k-halves meet in a bf16
+        // reduce-add (0 + p1 is exact, so the result is p1 + p2 rounded once more: deterministic, <= 1 bf16 ulp)
+        if (Ch && tiles * 2 <= g_num_sms && W.nkb_total >= 32) splits = 2;
         W.kb_per_split = cdiv(W.nkb_total, splits);
         W.splits = cdiv(W.nkb_total, W.kb_per_split);   // no empty split
-        if (W.splits > 1 && !accumulate) CUDA_CHECK(cudaMemset2DAsync(Cf, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s));
+        if (W.splits > 1 && !accumulate) {
+            if (Cf) CUDA_CHECK(cudaMemset2DAsync(Cf, (size_t)ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, s));
+            else CUDA_CHECK(cudaMemset2DAsync(Ch, (size_t)ldc * sizeof(bf16), 0, (size_t)N * sizeof(bf16), M, s));
+        }
         const int reduce = (accumulate || W.splits > 1) ? 1 : 0;
         CUtensorMap ta, tb, tc;
         encode_map(&ta, A, lda, a_mn, M, K, v2::BM);

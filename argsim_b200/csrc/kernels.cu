@@ -545,6 +545,39 @@ void launch_cast_f32(const bf16* in, float* out, long long n, cudaStream_t s) {
     k_cast_f32<<<blocks, 256, 0, s>>>(in, out, n);
     COUNT_LAUNCH();
 }
+// greedy decode (model.py:204-219), device-resident loop: one step's bookkeeping.  Appends pred to the output,
+// feeds it back as the next lead, and raises the stop flag when every row emitted eos (the reference breaks BEFORE
+// appending that step).  flag[0] = stopped, flag[1] = number of steps kept.
+__global__ void __launch_bounds__(256) k_decode_advance(const int* __restrict__ pred, int b, int eos, int* __restrict__ out_t,
+                                                        int* __restrict__ lead, int* __restrict__ flag, int t) {
+    if (flag[0]) return;
+    int all = 1;
+    for (int i = threadIdx.x; i < b; i += 256) all &= (pred[i] == eos);
+    all = __syncthreads_and(all);
+    if (all) {
+        if (threadIdx.x == 0) { flag[0] = 1; flag[1] = t; }
+        return;
+    }
+    for (int i = threadIdx.x; i < b; i += 256) {
+        const int v = pred[i];
+        out_t[i] = v;
+        lead[i] = v;
+    }
+    if (threadIdx.x == 0) flag[1] = t + 1;
+}
+void launch_decode_advance(const int* pred, int b, int eos, int* out_t, int* lead, int* flag, int t, cudaStream_t s) {
+    k_decode_advance<<<1, 256, 0, s>>>(pred, b, eos, out_t, lead, flag, t);
+    COUNT_LAUNCH();
+}
+__global__ void __launch_bounds__(256) k_fill_i32(int* p, long long n, int v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+void launch_fill_i32(int* p, long long n, int v, cudaStream_t s) {
+    if (n <= 0) return;
+    k_fill_i32<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(p, n, v);
+    COUNT_LAUNCH();
+}
 __global__ void __launch_bounds__(256) k_fill(float* p, long long n, float v) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;

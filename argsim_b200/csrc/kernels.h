@@ -35,6 +35,8 @@ void launch_cast_f32(const bf16* in, float* out, long long n, cudaStream_t s);
 void launch_row_scatter(const float* in, int ld_in, float* out, int ld_out, const int* dst_idx, int n, int cols,
                         int accumulate, cudaStream_t s);
 void launch_fill(float* p, long long n, float v, cudaStream_t s);
+void launch_fill_i32(int* p, long long n, int v, cudaStream_t s);
+void launch_decode_advance(const int* pred, int b, int eos, int* out_t, int* lead, int* flag, int t, cudaStream_t s);
 // one GRU cell step on nb rows (decode(), model.py:204-219): state updated in place
 void gru_generic_cell(const float* gx, int ld_gx, const float* R, const float* bR, float* state, float* gh_work, int nb,
                       int H, cudaStream_t s);

@@ -284,6 +284,12 @@ def encode(sess, vae, src):
 def decode(sess, vae, z, steps=256):
     """greedy decoding of latent states (src/model.py:204-219): array i32 (b, t), t <= steps.
     As in the reference, an output that is all-eos from the first step raises (np.concatenate of [])."""
+    if getattr(sess, 'handle', None) is not None and not _state.get('decode_host_loop'):
+        # the whole loop on the device (argsim_decode): same tokens as the per-step path below, no host round trips
+        y = sess.handle.decode(z, steps)
+        if y.shape[1] == 0:
+            raise ValueError('need at least one array to concatenate')   # what np.concatenate([]) raises in the reference
+        return y
     x = np.full((1, len(z)), vae.bos, dtype=np.int32)
     s = sess.run(vae.state_in, {vae.z: z})
     y = []

@@ -180,7 +180,7 @@ def cpu_baseline_leg():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=('ours', 'reference'))
     ap.add_argument('--workload', default='train', choices=('train', 'embed'))
@@ -292,8 +292,9 @@ def main():
     value = gb / (ms / 1e3)
     fl = algo_flops(S_glob, N_glob, gb)
     # dominant kernel = largest k: timer of the last timed step
-    kt = {k[2:]: v for k, v in tm.items() if k.startswith('k:') and not k.endswith('#n')}
+    kt = {k[2:]: v for k, v in tm.items() if k.startswith('k:') and '#' not in k}
     kn = {k[2:-2]: v for k, v in tm.items() if k.startswith('k:') and k.endswith('#n')}
+    kg = {k[2:-6]: v for k, v in tm.items() if k.startswith('k:') and k.endswith('#gflop')}   # GEMM groups: flops counted by the library
     phases = {k: round(v, 4) for k, v in tm.items() if not k.startswith('k:')}
     plan_l = _lib.plan_batch(src, tgt)
     S_l, N_l = plan_l['S'], plan_l['N']
@@ -306,6 +307,8 @@ def main():
         'softmax_ce': ('hbm', (4 if args.precision == 'bf16' else 8) * N_l * CFG['dim_tgt']),
         'adam': ('hbm', 24410112 * (30 if args.precision == 'bf16' else 28)),
     }
+    for k, gfl in kg.items():
+        kalgo[k] = ('tensor', gfl * 1e9)
     kernels = {}
     for k, t in kt.items():
         if k in kalgo and t > 0:

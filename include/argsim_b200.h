@@ -106,6 +106,12 @@ int  argsim_decode_init(argsim_handle*, const float* z, int32_t b, float* state 
 int  argsim_decode_step(argsim_handle*, const int32_t* lead /* b */, int32_t b,
                         float* state_inout /* L*b*H */, int32_t* pred /* b */);
 
+/* the whole decode() loop of model.py:204-219 on the device: x = bos; repeat {pred, state} until
+ * every row emits eos or `steps` steps; no host round trip per token.  tokens: (b, steps) int32 row-major, the
+ * first *t_out columns are valid (the all-eos step is not kept, like the reference's break before append). */
+int  argsim_decode(argsim_handle*, const float* z /* b*dim_rep */, int32_t b, int32_t steps,
+                   int32_t* tokens /* b*steps */, int32_t* t_out);
+
 /* tf.train.Saver save/restore (train.py:92-96,121): own flat container (params, Adam slots, step) */
 int  argsim_save(argsim_handle*, const char* path);
 int  argsim_load(argsim_handle*, const char* path);

@@ -153,6 +153,25 @@ def test_decode_and_checkpoint_roundtrip(tmp_path):
             break
         ys.append(x)
     np.testing.assert_array_equal(np.stack(ys, 1), ref)
+    # the same loop resident on the device (argsim_decode): identical tokens, the step budget is honoured, and the
+    # all-eos stop test works (force eos by making its embedding row dominate the tied output projection)
+    np.testing.assert_array_equal(h.decode(z, steps=6), ref)
+    np.testing.assert_array_equal(h.decode(z, steps=3), ref[:, :3])
+    long = O.decode_greedy({k: v.astype(np.float32) for k, v in P.items()}, cfg, z, steps=10)
+    np.testing.assert_array_equal(h.decode(z, steps=10), long)
+    P2 = {k: v.astype(np.float32).copy() for k, v in P.items()}
+    P2['decode/out/kernel'][:] = 0.0
+    P2['decode/out/bias'][:] = 0.05
+    P2['embed/embedding'][:] = -np.abs(P2['embed/embedding'])
+    P2['embed/embedding'][cfg['eos']] = 1.0          # logits = D^-1/2 * <out, E[v]>: eos wins for every input
+    hz = _lib.Handle(precision=_lib.FP32_VALIDATE, **cfg)
+    hz.set_params(P2)
+    assert hz.decode(z, steps=20).shape == (4, 0)     # all-eos at the first step: nothing kept (the reference raises here)
+    P2['embed/embedding'][7] = 2.0                    # token 7 wins forever: never stops, uses the whole budget
+    hz.set_params(P2)
+    out = hz.decode(z, steps=37)
+    assert out.shape == (4, 37) and (out == 7).all()
+    hz.close()
     src = ragged_batch(3, 8, cfg['dim_tgt'], 9)
     h.train_step(src, src)
     path = str(tmp_path / 'ckpt.bin')

@@ -1,4 +1,7 @@
-// gru_generic.cu -- reference-order GRU recurrence, one fp32 GEMM + one gate kernel per time step.
+// gru_generic.cu -- reference-order GRU recurrence, one GEMM + one gate kernel per time step.
+// The per-step GEMM is fp32 SIMT in the validation mode and, in bf16 mode with a hidden size the persistent
+// kernel does not cover (H != 512, e.g. the 4x-wide BASELINE configs[4]), the tcgen05 GEMM on the bf16 weight
+// shadow (split-K through TMA reduce-add: R no longer fits on chip, it streams from L2 every step).
 // Used by the FP32_VALIDATE precision mode (parity runs against the fp64/fp32 oracle at 1e-3),
 // for hidden sizes the persistent kernel does not cover, and as the on-device checker of
 // gru_mma.cu.  Cell = cuDNN form (src/model.py:15):
@@ -12,7 +15,7 @@ namespace {
 __global__ void __launch_bounds__(256) k_gate_fwd(const float* __restrict__ gx, int ld_gx, const float* __restrict__ gh,
                                                   const float* __restrict__ bR, float* __restrict__ state,
                                                   float* __restrict__ hs_f, bf16* __restrict__ hs_h, int ld_hs,
-                                                  float* __restrict__ cache, int na, int H) {
+                                                  float* __restrict__ cache, int na, int H, bf16* __restrict__ state_h) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= na * H) return;
     const int j = idx / H, u = idx - j * H;
@@ -25,6 +28,7 @@ __global__ void __launch_bounds__(256) k_gate_fwd(const float* __restrict__ gx, 
     const float hp = state[(long long)j * H + u];
     const float h = (1.f - z) * n + z * hp;
     state[(long long)j * H + u] = h;
+    if (state_h) state_h[(long long)j * H + u] = __float2bfloat16(h);
     if (hs_f) hs_f[(long long)j * ld_hs + u] = h;
     if (hs_h) hs_h[(long long)j * ld_hs + u] = __float2bfloat16(h);
     if (cache) {
@@ -83,7 +87,17 @@ void fork_join_init() {
 }
 }  // namespace
 
-size_t gru_generic_work_floats(int b, int H) { return (size_t)b * H * 4; }
+__global__ void __launch_bounds__(256) k_state_to_bf16(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = __float2bfloat16(x[i]);
+}
+static bool use_tc_gemm(const bf16* R_h, int H) {
+    static const bool off = getenv("ARGSIM_GENERIC_SIMT") != nullptr;
+    return !off && R_h != nullptr && gemm_tc_available() && H % 64 == 0;
+}
+
+// per direction: fp32 state / carry (b,H), gh / dgh scratch (b,3H), bf16 state (b,H)
+size_t gru_generic_work_floats(int b, int H) { return (size_t)b * H * 5; }
 
 void gru_generic_fwd(const GruFwdArgs* dirs, int ndir, const SeqPlan& P, int H, float* work, cudaStream_t* streams) {
     fork_join_init();
@@ -97,18 +111,24 @@ void gru_generic_fwd(const GruFwdArgs* dirs, int ndir, const SeqPlan& P, int H, 
         cudaStream_t s = streams[d];
         float* state = work + d * wstride;
         float* gh = state + (size_t)P.b * H;
+        bf16* state_h = use_tc_gemm(a.R_h, H) ? reinterpret_cast<bf16*>(gh + (size_t)P.b * 3 * H) : nullptr;
         if (a.h0 && !a.reverse)
             CUDA_CHECK(cudaMemcpyAsync(state, a.h0, sizeof(float) * P.b * H, cudaMemcpyDeviceToDevice, s));
         else
             CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(float) * P.b * H, s));
+        if (state_h) {
+            k_state_to_bf16<<<cdiv((long long)P.b * H, 256), 256, 0, s>>>(state, state_h, (long long)P.b * H);
+            COUNT_LAUNCH();
+        }
         for (int k = 0; k < P.Tmax; ++k) {
             const int t = a.reverse ? P.Tmax - 1 - k : k;
             const int na = P.nact[t];
             const long long r0 = P.off[t];
-            gemm_simt(state, H, 0, a.R_f, H, 0, gh, 3 * H, na, 3 * H, H, 1.f, nullptr, 0, nullptr, s);
+            if (state_h) gemm_tc(state_h, H, 0, a.R_h, H, 0, gh, nullptr, 3 * H, na, 3 * H, H, 1.f, nullptr, 0, s);
+            else gemm_simt(state, H, 0, a.R_f, H, 0, gh, 3 * H, na, 3 * H, H, 1.f, nullptr, 0, nullptr, s);
             k_gate_fwd<<<cdiv((long long)na * H, 256), 256, 0, s>>>(
                 a.gx + r0 * a.ld_gx, a.ld_gx, gh, a.bR, state, a.hs_f ? a.hs_f + r0 * a.ld_hs : nullptr,
-                a.hs_h ? a.hs_h + r0 * a.ld_hs : nullptr, a.ld_hs, a.cache ? a.cache + r0 * 4 * H : nullptr, na, H);
+                a.hs_h ? a.hs_h + r0 * a.ld_hs : nullptr, a.ld_hs, a.cache ? a.cache + r0 * 4 * H : nullptr, na, H, state_h);
             COUNT_LAUNCH();
         }
     }
@@ -158,7 +178,10 @@ void gru_generic_bwd(const GruBwdArgs* dirs, int ndir, const SeqPlan& P, int H, 
                 a.hp_f ? a.hp_f + r0 * a.ld_hp : nullptr, a.hp_h ? a.hp_h + r0 * a.ld_hp : nullptr, a.ld_hp, na, H);
             COUNT_LAUNCH();
             // carry[0:na] += dgh[0:na] . R        (R is (3H,H): stored (K, N) -> b_mn = 1)
-            gemm_simt(tmp, 3 * H, 0, a.R_f, H, 1, carry, H, na, H, 3 * H, 1.f, nullptr, 1, nullptr, s);
+            if (a.dgh_h && a.ld_dg % 8 == 0 && use_tc_gemm(a.R_h, H))
+                gemm_tc(a.dgh_h + r0 * a.ld_dg, a.ld_dg, 0, a.R_h, H, 1, carry, nullptr, H, na, H, 3 * H, 1.f, nullptr, 1, s);
+            else
+                gemm_simt(tmp, 3 * H, 0, a.R_f, H, 1, carry, H, na, H, 3 * H, 1.f, nullptr, 1, nullptr, s);
         }
         if (a.dh0 && !a.reverse) {
             k_axpy<<<cdiv((long long)P.b * H, 256), 256, 0, s>>>(a.dh0, carry, (long long)P.b * H);
@@ -176,6 +199,6 @@ void gru_generic_bwd(const GruBwdArgs* dirs, int ndir, const SeqPlan& P, int H, 
 void gru_generic_cell(const float* gx, int ld_gx, const float* R, const float* bR, float* state, float* gh_work, int nb,
                       int H, cudaStream_t s) {
     gemm_simt(state, H, 0, R, H, 0, gh_work, 3 * H, nb, 3 * H, H, 1.f, nullptr, 0, nullptr, s);
-    k_gate_fwd<<<cdiv((long long)nb * H, 256), 256, 0, s>>>(gx, ld_gx, gh_work, bR, state, nullptr, nullptr, H, nullptr, nb, H);
+    k_gate_fwd<<<cdiv((long long)nb * H, 256), 256, 0, s>>>(gx, ld_gx, gh_work, bR, state, nullptr, nullptr, H, nullptr, nb, H, nullptr);
     COUNT_LAUNCH();
 }

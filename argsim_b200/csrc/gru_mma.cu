@@ -889,7 +889,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
             // ---- bookkeeping, off the serial chain: this step's gate gradients -> HBM (operands of the batched wgrad / dgrad GEMMs)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                if (!slive[e]) continue;
+                if (!slive[e] || (P.variant & 4)) continue;   // variant bit 2: measurement only (results invalid)
                 const float dr = sv[e][0], du = sv[e][1], dn = sv[e][2], dnr = sv[e][3], hp = sv[e][4];
                 const size_t row = srow[e];
                 const size_t o = row * A.ld_dg + col;

@@ -420,7 +420,9 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd2(const __grid_constant__
     const int ns = P.nslices, d = grp / ns, sl = grp % ns;
     const FwdDirP& A = P.dir[d];
     const int g4 = lane >> 2, q4 = lane & 3;
-    const bool rowmaj = (P.variant & 8) != 0, repoll_all = (P.variant & 16) != 0;   // A/B switches (ARGSIM_GRU_VARIANT)
+    // compile-time A/B switches (OPT): 1 step tables one step ahead, 2 fine profile marks, 4 k-tile-major LL layout,
+    // 8 re-poll only the missing words, 16 next step's gx staged in shared memory by cp.async
+    constexpr bool rowmaj = !(OPT & 4), repoll_all = !(OPT & 8), stage_gx = (OPT & 16) != 0;
 
     // ---- R slice -> registers (A fragments): local row lr = gate*32 + unit <-> R row gate*H + 32c + unit; k in [64w, 64w+64)
     uint32_t a[6][4][4];
@@ -544,7 +546,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd2(const __grid_constant__
             // gx of the rows this warp finishes (row n -> warp n & 7): L2 hits (prefetched two steps ago), they
             // complete under the HMMAs and the barrier
             float gxv[2][3];
-            const bool from_smem = (P.variant & 64) && ch == 0 && staged;
+            const bool from_smem = stage_gx && ch == 0 && staged;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int n = warp + 8 * e;
@@ -628,7 +630,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd2(const __grid_constant__
             PROF_MARK(6);   // bookkeeping stores (+ second row)
             // next step's gx of chunk 0 -> shared memory (cp.async by the thread that will use it: no barrier needed);
             // issued after the publish, it lands while the exchange is in flight (L2 hit: prefetched one step earlier)
-            if ((P.variant & 64) && ch == 0) {
+            if (stage_gx && ch == 0) {
                 staged = false;
                 if (k + 1 < P.Tseg) {
                     const int tn = A.reverse ? t - 1 : t + 1;
@@ -661,9 +663,6 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd2(const __grid_constant__
                 }
             }
             rbuf ^= 1u;
-            // A/B: keep the warps without a gate row from spinning on the next step's operands while the gate warps still
-            // publish (their polls queue in front of the LL stores in the in-order LSU)
-            if (P.variant & 32) __syncthreads();
         }
         na_prev = na;
         first = false;
@@ -1005,7 +1004,7 @@ struct GruMmaCtx {
     unsigned long long* ybuf[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
     size_t ycap[NSLOT] = {0, 0, 0, 0};
     bool attr_set = false;
-    int variant_fwd = 26, variant_bwd = 3;   // fwd: L2 prefetch + row-major LL layout + re-poll all words (best of the measured A/B set)
+    int variant_fwd = 2, variant_bwd = 3;   // bit 1: L2 prefetch two steps ahead by idle warps; bwd bit 0: cp.async staging
     int fwd2_opt = 0;
     bool fwd_v1 = false;         // ARGSIM_GRU_FWD_V1=1: the first forward kernel (smem-staged operands), for A/B runs
     long long* prof = nullptr;   // ARGSIM_GRU_PROF=1: per-phase clocks, printed to stderr after every launch
@@ -1021,10 +1020,10 @@ GruMmaCtx* gru_mma_create(int device) {
     {
         const int fwd2_smem = 2 * KW * CH * RED_LD * 4 + MAX_BSL * UN * 4 + 2 * 4100 * 4 + 2 * CH * 3 * UN * 4;
         CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
         CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
-        CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
-        if (const char* v = getenv("ARGSIM_GRU_FWD2_OPT")) c->fwd2_opt = atoi(v) & 3;
+        CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
+        if (const char* v = getenv("ARGSIM_GRU_FWD2_OPT")) c->fwd2_opt = atoi(v);
     }
     c->fwd_v1 = getenv("ARGSIM_GRU_FWD_V1") != nullptr;
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH * GS_LD * 2 + MAX_BSL * UN * 4 + 2 * 4100 * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2));
@@ -1112,8 +1111,9 @@ void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& 
     const size_t smem = c->fwd_v1 ? (size_t)bslr * HS_LD * 2 + 4 * CH * RED_LD * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4
                                   : (size_t)2 * KW * CH * RED_LD * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 2 * CH * 3 * UN * 4;
     void* args[] = {&P};
-    void* fwd2_fn[4] = {(void*)k_gru_mma_fwd2<0>, (void*)k_gru_mma_fwd2<1>, (void*)k_gru_mma_fwd2<2>, (void*)k_gru_mma_fwd2<3>};
-    CUDA_CHECK(cudaLaunchCooperativeKernel(c->fwd_v1 ? (void*)k_gru_mma_fwd : fwd2_fn[c->fwd2_opt], dim3(groups * CL), dim3(NTH), args, smem, s));
+    void* fwd2_fn = c->fwd2_opt == 2 ? (void*)k_gru_mma_fwd2<2> : c->fwd2_opt == 12 ? (void*)k_gru_mma_fwd2<12>
+                  : c->fwd2_opt == 16 ? (void*)k_gru_mma_fwd2<16> : (void*)k_gru_mma_fwd2<0>;
+    CUDA_CHECK(cudaLaunchCooperativeKernel(c->fwd_v1 ? (void*)k_gru_mma_fwd : fwd2_fn, dim3(groups * CL), dim3(NTH), args, smem, s));
     COUNT_LAUNCH();
     dump_prof(c, ndir == 2 ? "fwd_enc" : "fwd_dec", groups * CL, Tseg, s);
 }

@@ -34,7 +34,7 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
         throw std::runtime_error("attentive=true is not implemented (unused by config.json; the reference marks it 'todo fixme', src/model.py:136)");
     if (!c.bidirectional || !c.bidir_stacked)
         throw std::runtime_error("only the stacked bidirectional encoder of config.json is implemented (src/model.py:118-122)");
-    if (!c.logit_use_embed) throw std::runtime_error("logit_use_embed=false is not implemented (src/model.py:167-168)");
+    tied = c.logit_use_embed != 0;   // false: separate (D,V) projection + bias (src/model.py:167-168)
     if (D % 8 || R % 8 || V % 8) throw std::runtime_error("dim_tgt, dim_emb and dim_rep must be multiples of 8");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -66,6 +66,10 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
         pindex[name] = (int)params.size();
         params.push_back(pi);
     };
+    if (!tied) {   // first in backward-completion order: part of the first all-reduce bucket
+        add("logits/dense/kernel", D, V);
+        add("logits/dense/bias", V, 0);
+    }
     add("decode/out/kernel", D, D);
     add("decode/out/bias", D, 0);
     for (int j = L - 1; j >= 0; --j) {
@@ -240,10 +244,10 @@ cudaEvent_t Engine::next_event() {
 bool Engine::dec_wavefront(const SeqPlan& Dp) const {
     return use_mma && L > 1 && dec_seg > 0 && Dp.Tmax > dec_seg && gru_mma_fits(mma, 1, Dp.b);
 }
-void Engine::colsum(const Mat& A, long long rows, int cols, float* out) {
+void Engine::colsum(const Mat& A, long long rows, int cols, float* out, int accumulate) {
     if (arena.dry) return;
-    if (A.f) launch_colsum_f32(A.f, A.ld, rows, cols, out, st[0]);
-    else launch_colsum_bf16(A.h, A.ld, rows, cols, out, st[0]);
+    if (A.f) launch_colsum_f32(A.f, A.ld, rows, cols, out, st[0], accumulate);
+    else launch_colsum_bf16(A.h, A.ld, rows, cols, out, st[0], accumulate);
 }
 void Engine::gather_embed(const int* ids, long long n, const Mat& out) {
     if (arena.dry) return;
@@ -580,10 +584,13 @@ void Engine::program(int mode, bool apply_update) {
     Mat dHO = train ? act(N, D) : Mat();
     Mat Emb = pmat("embed/embedding");
     Mat gE = gmat("embed/embedding");
+    Mat Kl = tied ? Mat() : pmat("logits/dense/kernel");
+    Mat gKl = tied ? Mat() : gmat("logits/dense/kernel");
     for (long long r0 = 0; r0 < N; r0 += chunk) {
         const long long nr = std::min(chunk, N - r0);
         RUN(kbegin("k:logits_gemm"));
-        gemm(HO.rowslice(r0, nr), 0, Emb, 0, logits, nr, V, D, scale, nullptr, 0);
+        if (tied) gemm(HO.rowslice(r0, nr), 0, Emb, 0, logits, nr, V, D, scale, nullptr, 0);
+        else gemm(HO.rowslice(r0, nr), 0, Kl, 1, logits, nr, V, D, 1.f, p + pinfo("logits/dense/bias").off, 0);   // h.K + b, K is (in,out)
         RUN(kend());
         RUN(kbegin("k:softmax_ce"));
         if (logits.h)
@@ -596,10 +603,16 @@ void Engine::program(int mode, bool apply_update) {
         if (train) {
             // dE (dense part) += D^-1/2 * dlogits^T . ho ;  dho = D^-1/2 * dlogits . E
             RUN(kbegin("k:logits_wgrad"));
-            gemm(logits, 1, HO.rowslice(r0, nr), 1, gE, V, D, nr, scale, nullptr, 1);
+            if (tied) {
+                gemm(logits, 1, HO.rowslice(r0, nr), 1, gE, V, D, nr, scale, nullptr, 1);
+            } else {   // dK += ho^T . dlogits ; db += column sums of dlogits
+                gemm(HO.rowslice(r0, nr), 1, logits, 1, gKl, D, V, nr, 1.f, nullptr, 1);
+                colsum(logits, nr, V, gptr("logits/dense/bias"), 1);
+            }
             RUN(kend());
             RUN(kbegin("k:logits_dgrad"));
-            gemm(logits, 0, Emb, 1, dHO.rowslice(r0, nr), nr, D, V, scale, nullptr, 0);
+            if (tied) gemm(logits, 0, Emb, 1, dHO.rowslice(r0, nr), nr, D, V, scale, nullptr, 0);
+            else gemm(logits, 0, Kl, 0, dHO.rowslice(r0, nr), nr, D, V, 1.f, nullptr, 0);   // dho = dlogits . K^T
             RUN(kend());
         }
     }
@@ -973,7 +986,8 @@ void Engine::decode_step(const int32_t* lead, int b, float* state, int32_t* pred
         in = stl;
     }
     gemm_simt(in, H, 0, p + pinfo("decode/out/kernel").off, D, 1, ho, D, b, D, D, 1.f, p + pinfo("decode/out/bias").off, 0, nullptr, s);
-    gemm_simt(ho, D, 0, p + pinfo("embed/embedding").off, D, 0, lg, V, b, V, D, 1.0f / sqrtf((float)D), nullptr, 0, nullptr, s);
+    if (tied) gemm_simt(ho, D, 0, p + pinfo("embed/embedding").off, D, 0, lg, V, b, V, D, 1.0f / sqrtf((float)D), nullptr, 0, nullptr, s);
+    else gemm_simt(ho, D, 0, p + pinfo("logits/dense/kernel").off, V, 1, lg, V, b, V, D, 1.f, p + pinfo("logits/dense/bias").off, 0, nullptr, s);
     launch_ce_f32(lg, V, nullptr, b, V, 0.f, 0, nullptr, nullptr, dpred, d_stats, s);
     CUDA_CHECK(cudaMemcpyAsync(pred, dpred, sizeof(int) * b, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaMemcpyAsync(state, dst, sizeof(float) * L * b * H, cudaMemcpyDeviceToHost, s));
@@ -1020,7 +1034,8 @@ int Engine::decode_loop(const float* z, int b, int steps, int32_t* tokens) {
             in = stl;
         }
         gemm_simt(in, H, 0, p + pinfo("decode/out/kernel").off, D, 1, ho, D, b, D, D, 1.f, p + pinfo("decode/out/bias").off, 0, nullptr, s);
-        gemm_simt(ho, D, 0, p + pinfo("embed/embedding").off, D, 0, lg, V, b, V, D, 1.0f / sqrtf((float)D), nullptr, 0, nullptr, s);
+        if (tied) gemm_simt(ho, D, 0, p + pinfo("embed/embedding").off, D, 0, lg, V, b, V, D, 1.0f / sqrtf((float)D), nullptr, 0, nullptr, s);
+        else gemm_simt(ho, D, 0, p + pinfo("logits/dense/kernel").off, V, 1, lg, V, b, V, D, 1.f, p + pinfo("logits/dense/bias").off, 0, nullptr, s);
         launch_ce_f32(lg, V, nullptr, b, V, 0.f, 0, nullptr, nullptr, dpred, d_stats, s);
         launch_decode_advance(dpred, b, cfg.eos, dout + (size_t)t * b, dlead, dflag, t, s);
         if ((t & 15) == 15 || t + 1 == steps) {

@@ -129,6 +129,7 @@ private:
     void kbegin(const char* name, cudaStream_t q = nullptr);
     void kend(cudaStream_t q = nullptr, double gflop = 0.0);
     bool in_ktimer = false;
+    bool tied = true;   // logit_use_embed (src/model.py:164-168)
     void collect_timings();
 
     Mat pmat(const std::string& name);
@@ -155,7 +156,7 @@ private:
     Mat both(long long rows, int cols);
     void gemm(const Mat& A, int a_mn, const Mat& B, int b_mn, const Mat& C, long long M, int N, long long K, float alpha,
               const float* bias, int accumulate, cudaStream_t q = nullptr);
-    void colsum(const Mat& A, long long rows, int cols, float* out);
+    void colsum(const Mat& A, long long rows, int cols, float* out, int accumulate = 0);
     void gather_embed(const int* ids, long long n, const Mat& out);
     void gru_fwd(GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact);
     void gru_bwd(GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact);

@@ -508,19 +508,19 @@ __global__ void __launch_bounds__(256) k_colsum(const T* __restrict__ in, int ld
     }
 }
 template <typename T>
-static void launch_colsum(const T* in, int ld, long long rows, int cols, float* out, cudaStream_t s) {
-    CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
+static void launch_colsum(const T* in, int ld, long long rows, int cols, float* out, cudaStream_t s, int accumulate) {
+    if (!accumulate) CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float) * cols, s));
     if (rows <= 0) return;
     int gy = (int)std::max<long long>(1, std::min<long long>(64, rows / 64));
     dim3 grid(cdiv(cols, 32), gy);
     k_colsum<T><<<grid, 256, 0, s>>>(in, ld, rows, cols, out);
     COUNT_LAUNCH();
 }
-void launch_colsum_f32(const float* in, int ld, long long rows, int cols, float* out, cudaStream_t s) {
-    launch_colsum<float>(in, ld, rows, cols, out, s);
+void launch_colsum_f32(const float* in, int ld, long long rows, int cols, float* out, cudaStream_t s, int accumulate) {
+    launch_colsum<float>(in, ld, rows, cols, out, s, accumulate);
 }
-void launch_colsum_bf16(const bf16* in, int ld, long long rows, int cols, float* out, cudaStream_t s) {
-    launch_colsum<bf16>(in, ld, rows, cols, out, s);
+void launch_colsum_bf16(const bf16* in, int ld, long long rows, int cols, float* out, cudaStream_t s, int accumulate) {
+    launch_colsum<bf16>(in, ld, rows, cols, out, s, accumulate);
 }
 
 __global__ void __launch_bounds__(256) k_cast_bf16(const float* __restrict__ in, bf16* __restrict__ out, long long n) {

@@ -27,8 +27,8 @@ void launch_ce_bf16(bf16* logits, int ld, const int* labels, long long n, int V,
 void launch_adam(float* p, const float* g, float* m, float* v, bf16* shadow, long long n, float lr_t,
                  float b1, float b2, float eps, cudaStream_t s);
 // out[c] = sum_r in[r,c]
-void launch_colsum_f32(const float* in, int ld, long long rows, int cols, float* out, cudaStream_t s);
-void launch_colsum_bf16(const bf16* in, int ld, long long rows, int cols, float* out, cudaStream_t s);
+void launch_colsum_f32(const float* in, int ld, long long rows, int cols, float* out, cudaStream_t s, int accumulate = 0);
+void launch_colsum_bf16(const bf16* in, int ld, long long rows, int cols, float* out, cudaStream_t s, int accumulate = 0);
 void launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s);
 void launch_cast_f32(const bf16* in, float* out, long long n, cudaStream_t s);
 // dst[dst_idx[i],:] += (or =) src[i,:]

@@ -113,8 +113,6 @@ def vAe(mode, src=None, tgt=None, dim_tgt=8192, dim_emb=512, dim_rep=1024, rnn_l
         raise NotImplementedError("attentive=True is not on the hot path (config.json: false; 'todo fixme' at src/model.py:136)")
     if not (bidirectional and bidir_stacked):
         raise NotImplementedError('only the stacked bidirectional encoder of config.json is implemented (src/model.py:118-122)')
-    if not logit_use_embed:
-        raise NotImplementedError('logit_use_embed=False is not implemented (src/model.py:167-168)')
     if _state['config'] is None:
         _state['config'] = config
     elif _state['config'] != config:

@@ -109,7 +109,7 @@ def reverse_sequence(x, lens):
 # parameters
 # --------------------------------------------------------------------------------------
 
-def param_shapes(dim_tgt=8192, dim_emb=512, dim_rep=1024, rnn_layers=3, **_):
+def param_shapes(dim_tgt=8192, dim_emb=512, dim_rep=1024, rnn_layers=3, logit_use_embed=True, **_):
     V, D, R, L = dim_tgt, dim_emb, dim_rep, rnn_layers
     H = D
     shp = {'embed/embedding': (V, D)}
@@ -132,6 +132,9 @@ def param_shapes(dim_tgt=8192, dim_emb=512, dim_rep=1024, rnn_layers=3, **_):
         shp[p + 'bR'] = (3 * H,)
     shp['decode/out/kernel'] = (D, D)
     shp['decode/out/bias'] = (D,)
+    if not logit_use_embed:   # src/model.py:167-168: layer_aff(h, dim_tgt) = tf.layers.dense under scope 'logits'
+        shp['logits/dense/kernel'] = (D, V)
+        shp['logits/dense/bias'] = (V,)
     return shp
 
 
@@ -270,7 +273,10 @@ def forward(P, cfg, src, tgt, mode='valid', step=0, keep=None, eps=None, want_pr
     hd = y[msk_tgt] if mode != 'infer' else y.reshape(-1, H)
     ho = hd @ P['decode/out/kernel'] + P['decode/out/bias']
     scale = dt.type(D) ** dt.type(-0.5)
-    logits = ho @ (scale * E.T)
+    if cfg.get('logit_use_embed', True):
+        logits = ho @ (scale * E.T)                                          # model.py:165-166
+    else:
+        logits = ho @ P['logits/dense/kernel'] + P['logits/dense/bias']      # model.py:167-168
     o['logits'] = logits
     o['pred'] = np.argmax(logits, -1).astype(np.int32)
     if want_prob:
@@ -311,8 +317,13 @@ def backward(P, cfg, cache):
     dlog[np.arange(N), labels] -= 1.0
     dlog /= cache['n_norm']
     ho, hd = cache['ho'], cache['hd']
-    G['embed/embedding'] += scale * (dlog.T @ ho)
-    dho = dlog @ (scale * E)
+    if cfg.get('logit_use_embed', True):
+        G['embed/embedding'] += scale * (dlog.T @ ho)
+        dho = dlog @ (scale * E)
+    else:
+        G['logits/dense/kernel'] += ho.T @ dlog
+        G['logits/dense/bias'] += dlog.sum(0)
+        dho = dlog @ P['logits/dense/kernel'].T
     G['decode/out/kernel'] += hd.T @ dho
     G['decode/out/bias'] += dho.sum(0)
     dhd = dho @ P['decode/out/kernel'].T
@@ -390,7 +401,10 @@ def decode_greedy(P, cfg, z, steps=256):
             y, _ = gru_forward(y, s[j], P[p + 'W'], P[p + 'R'], P[p + 'bW'], P[p + 'bR'])
             s[j] = y[0]
         ho = y[0] @ P['decode/out/kernel'] + P['decode/out/bias']
-        x = np.argmax(ho @ (E.dtype.type(D) ** E.dtype.type(-0.5) * E.T), -1).astype(np.int32)
+        if cfg.get('logit_use_embed', True):
+            x = np.argmax(ho @ (E.dtype.type(D) ** E.dtype.type(-0.5) * E.T), -1).astype(np.int32)
+        else:
+            x = np.argmax(ho @ P['logits/dense/kernel'] + P['logits/dense/bias'], -1).astype(np.int32)
         if np.all(x == eos):
             break
         ys.append(x[None])

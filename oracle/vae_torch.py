@@ -81,7 +81,10 @@ def forward(P, cfg, src, tgt, mode='valid', step=0, keep=None, eps=None, encoder
     y, _ = torch._VF.gru(y, torch.stack((hx,) * L), flat, True, L, 0.0, False, False, False)
     hd = y[msk]
     ho = hd @ P['decode/out/kernel'] + P['decode/out/bias']
-    logits = ho @ ((D ** -0.5) * E.t())
+    if cfg.get('logit_use_embed', True):
+        logits = ho @ ((D ** -0.5) * E.t())
+    else:
+        logits = ho @ P['logits/dense/kernel'] + P['logits/dense/bias']
     labels = gold[msk]
     gen = torch.nn.functional.cross_entropy(logits, labels, reduction='none')
     kld = 0.5 * (mu * mu + torch.exp(lv) - lv - 1.0)

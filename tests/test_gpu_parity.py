@@ -182,3 +182,44 @@ def test_decode_and_checkpoint_roundtrip(tmp_path):
     for k in P:
         np.testing.assert_array_equal(h.get_param(k), h2.get_param(k))
         np.testing.assert_array_equal(h.get_opt_state(k)[1], h2.get_opt_state(k)[1])
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+def test_untied_logit_projection_branch(prec):
+    """logit_use_embed=false (src/model.py:167-168): logits = dense(h, dim_tgt) with its own (D,V) kernel and bias --
+    losses, every gradient (the new kernel / bias, and the embedding that now only gets its gather parts), three Adam
+    steps and the greedy decode against the oracle."""
+    from argsim_b200 import _lib
+    cfg = dict(SMALL, logit_use_embed=False)
+    h, P = _mk(cfg, _lib.FP32_VALIDATE if prec == 'fp32' else _lib.BF16)
+    assert h.param_shapes()['logits/dense/kernel'] == (cfg['dim_emb'], cfg['dim_tgt'])
+    assert h.param_shapes()['logits/dense/bias'] == (cfg['dim_tgt'],)
+    src = ragged_batch(7, 11, cfg['dim_tgt'], 70)
+    tgt = ragged_batch(7, 9, cfg['dim_tgt'], 71)
+    keep, eps = _inject(cfg, tgt, 72)
+    h.step = 12000
+    o, cache = O.forward(P, cfg, src, tgt, 'train', step=12000, keep=_oracle_keep(keep, tgt, cfg['eos']), eps=eps.astype(np.float64))
+    G = O.backward(P, cfg, cache)
+    st = h.grad_step(src, tgt, keep=keep, eps=eps)
+    tol = 1e-3 if prec == 'fp32' else 1e-2
+    for k in ('loss', 'loss_gen', 'loss_kld'):
+        assert rel(st[k], o[k]) < tol, (k, st[k], o[k])
+    for k in P:
+        g = h.get_grad(k).astype(np.float64)
+        if prec == 'fp32':
+            assert np.abs(g - G[k]).max() <= 2e-4 * np.abs(G[k]).max() + 1e-9, k
+        elif np.linalg.norm(G[k]) > 1e-12:
+            cos = (g.ravel() @ G[k].ravel()) / (np.linalg.norm(g) * np.linalg.norm(G[k]) + 1e-30)
+            assert cos > 0.995, (k, cos)
+    if prec == 'fp32':
+        M = {k: np.zeros_like(v) for k, v in P.items()}
+        V = {k: np.zeros_like(v) for k, v in P.items()}
+        h.step = 0
+        for it in range(3):
+            oo, _ = O.train_step(P, M, V, cfg, src, tgt, it, _oracle_keep(keep, tgt, cfg['eos']), eps.astype(np.float64))
+            s2 = h.train_step(src, tgt, keep=keep, eps=eps)
+            assert rel(s2['loss'], oo['loss']) < 1e-3, (it, s2['loss'], oo['loss'])
+        z = np.random.default_rng(4).standard_normal((3, cfg['dim_rep'])).astype(np.float32)
+        ref = O.decode_greedy({k: v.astype(np.float32) for k, v in P.items()}, cfg, z, steps=6)
+        np.testing.assert_array_equal(h.decode(z, steps=6), ref)
+    h.close()

@@ -321,11 +321,19 @@ def main():
     roofline = None
     if dom:
         d = kernels[dom]
+        traffic = None
+        try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/), if there is one
+            with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
+                traffic = json.load(f).get(dom)
+        except Exception:
+            pass
         roofline = dict(kernel=dom, bound=d['bound'], achieved=d['achieved'], peak=d['peak'],
-                        unit='GB/s' if d['bound'] == 'hbm' else 'TFLOP/s', frac=d['frac'], traffic=None,
+                        unit='GB/s' if d['bound'] == 'hbm' else 'TFLOP/s', frac=d['frac'], traffic=traffic,
                         peak_source='%s (%s)' % (pk['src'], 'hbm_gbs' if d['bound'] == 'hbm' else 'bf16_tflops_sustained: timed inside a long step'),
                         note='avg launch duration from CUDA events on the launching stream inside the timed region; '
-                             'the recurrence is bound by serial-step latency, not by the tensor pipe (DESIGN.md)')
+                             'the recurrence is bound by serial-step latency (512 dependent steps per launch, one 16-CTA '
+                             'exchange through L2 each: >= 1270 cycles, DESIGN.md section 5), not by the tensor pipe; '
+                             'traffic = dram bytes per launch from profiles/r1c_gru_*_enc_ncu.md')
     line = dict(metric=METRIC, value=value, unit='sequences/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='bf16' if args.precision == 'bf16' else 'f32', data='synthetic',

@@ -109,19 +109,40 @@ def reverse_sequence(x, lens):
 # parameters
 # --------------------------------------------------------------------------------------
 
-def param_shapes(dim_tgt=8192, dim_emb=512, dim_rep=1024, rnn_layers=3, logit_use_embed=True, **_):
+def enc_stacks(cfg):
+    """name prefixes of the encoder's independent GRU stacks for the non-default branches (src/model.py:124-131):
+    non-stacked bidirectional = two L-layer stacks ('fwd' on the sequence, 'bwd' on the reversed one), unidirectional =
+    one.  Canonical names: encode/rnn/{fwd,bwd}/l{j}/... and encode/rnn/l{j}/..."""
+    if cfg.get('bidirectional', True) and cfg.get('bidir_stacked', True):
+        return None
+    return ['encode/rnn/fwd/', 'encode/rnn/bwd/'] if cfg.get('bidirectional', True) else ['encode/rnn/']
+
+
+def param_shapes(dim_tgt=8192, dim_emb=512, dim_rep=1024, rnn_layers=3, logit_use_embed=True, bidirectional=True,
+                 bidir_stacked=True, **_):
     V, D, R, L = dim_tgt, dim_emb, dim_rep, rnn_layers
     H = D
     shp = {'embed/embedding': (V, D)}
-    for i in range(1, L + 1):
-        cin = D if i == 1 else 2 * H
-        for d in ('fwd', 'bwd'):
-            p = 'encode/rnn%d/%s/' % (i, d)
-            shp[p + 'W'] = (3 * H, cin)
-            shp[p + 'R'] = (3 * H, H)
-            shp[p + 'bW'] = (3 * H,)
-            shp[p + 'bR'] = (3 * H,)
-    for nm, (i, o) in (('mu', (2 * H, R)), ('lv', (2 * H, R)), ('ex', (R, D))):
+    stacks = enc_stacks(dict(bidirectional=bidirectional, bidir_stacked=bidir_stacked))
+    if stacks is None:
+        for i in range(1, L + 1):
+            cin = D if i == 1 else 2 * H
+            for d in ('fwd', 'bwd'):
+                p = 'encode/rnn%d/%s/' % (i, d)
+                shp[p + 'W'] = (3 * H, cin)
+                shp[p + 'R'] = (3 * H, H)
+                shp[p + 'bW'] = (3 * H,)
+                shp[p + 'bR'] = (3 * H,)
+    else:
+        for st in stacks:
+            for j in range(L):
+                p = '%sl%d/' % (st, j)
+                shp[p + 'W'] = (3 * H, D if j == 0 else H)
+                shp[p + 'R'] = (3 * H, H)
+                shp[p + 'bW'] = (3 * H,)
+                shp[p + 'bR'] = (3 * H,)
+    EH = 2 * H if bidirectional else H
+    for nm, (i, o) in (('mu', (EH, R)), ('lv', (EH, R)), ('ex', (R, D))):
         shp['latent/%s/kernel' % nm] = (i, o)
         shp['latent/%s/bias' % nm] = (o,)
     for j in range(L):
@@ -243,14 +264,28 @@ def forward(P, cfg, src, tgt, mode='valid', step=0, keep=None, eps=None, want_pr
     emb_tgt = E[lead]
     x = E[src_tm]
     enc_caches = []
-    for i in range(1, L + 1):
-        pf, pb = 'encode/rnn%d/fwd/' % i, 'encode/rnn%d/bwd/' % i
-        z0 = np.zeros((b, H), dt)
-        fwd, cf = gru_forward(x, z0, P[pf + 'W'], P[pf + 'R'], P[pf + 'bW'], P[pf + 'bR'])
-        bwd, cb = gru_forward(reverse_sequence(x, len_src), z0, P[pb + 'W'], P[pb + 'R'], P[pb + 'bW'], P[pb + 'bR'])
-        x = np.concatenate([fwd, reverse_sequence(bwd, len_src)], -1)
-        enc_caches.append((cf, cb))
-    hs = x
+    stacks = enc_stacks(cfg)
+    z0 = np.zeros((b, H), dt)
+    if stacks is None:                                   # model.py:118-122 (config.json)
+        for i in range(1, L + 1):
+            pf, pb = 'encode/rnn%d/fwd/' % i, 'encode/rnn%d/bwd/' % i
+            fwd, cf = gru_forward(x, z0, P[pf + 'W'], P[pf + 'R'], P[pf + 'bW'], P[pf + 'bR'])
+            bwd, cb = gru_forward(reverse_sequence(x, len_src), z0, P[pb + 'W'], P[pb + 'R'], P[pb + 'bW'], P[pb + 'bR'])
+            x = np.concatenate([fwd, reverse_sequence(bwd, len_src)], -1)
+            enc_caches.append((cf, cb))
+        hs = x
+    else:                                                # model.py:124-131: L-layer stack(s), concatenated at the top only
+        outs = []
+        for k, st in enumerate(stacks):
+            y = reverse_sequence(x, len_src) if k == 1 else x
+            cs = []
+            for j in range(L):
+                p = '%sl%d/' % (st, j)
+                y, c = gru_forward(y, z0, P[p + 'W'], P[p + 'R'], P[p + 'bW'], P[p + 'bR'])
+                cs.append(c)
+            enc_caches.append(cs)
+            outs.append(reverse_sequence(y, len_src) if k == 1 else y)
+        hs = np.concatenate(outs, -1)
     h = hs[len_src - 1, np.arange(b)]
     mu = h @ P['latent/mu/kernel'] + P['latent/mu/bias']
     lv = h @ P['latent/lv/kernel'] + P['latent/lv/bias']
@@ -353,14 +388,28 @@ def backward(P, cfg, cache):
     b = len(len_src)
     dhs = np.zeros(cache['hs_shape'], dt)
     dhs[len_src - 1, np.arange(b)] = dh
-    for i in range(L, 0, -1):
-        pf, pb = 'encode/rnn%d/fwd/' % i, 'encode/rnn%d/bwd/' % i
-        cf, cb = cache['enc'][i - 1]
-        dxf, _, dW, dR, dbW, dbR = gru_backward(dhs[..., :H], None, cf, P[pf + 'W'], P[pf + 'R'])
-        G[pf + 'W'] += dW; G[pf + 'R'] += dR; G[pf + 'bW'] += dbW; G[pf + 'bR'] += dbR
-        dxb, _, dW, dR, dbW, dbR = gru_backward(reverse_sequence(dhs[..., H:], len_src), None, cb, P[pb + 'W'], P[pb + 'R'])
-        G[pb + 'W'] += dW; G[pb + 'R'] += dR; G[pb + 'bW'] += dbW; G[pb + 'bR'] += dbR
-        dhs = dxf + reverse_sequence(dxb, len_src)
+    stacks = enc_stacks(cfg)
+    if stacks is None:
+        for i in range(L, 0, -1):
+            pf, pb = 'encode/rnn%d/fwd/' % i, 'encode/rnn%d/bwd/' % i
+            cf, cb = cache['enc'][i - 1]
+            dxf, _, dW, dR, dbW, dbR = gru_backward(dhs[..., :H], None, cf, P[pf + 'W'], P[pf + 'R'])
+            G[pf + 'W'] += dW; G[pf + 'R'] += dR; G[pf + 'bW'] += dbW; G[pf + 'bR'] += dbR
+            dxb, _, dW, dR, dbW, dbR = gru_backward(reverse_sequence(dhs[..., H:], len_src), None, cb, P[pb + 'W'], P[pb + 'R'])
+            G[pb + 'W'] += dW; G[pb + 'R'] += dR; G[pb + 'bW'] += dbW; G[pb + 'bR'] += dbR
+            dhs = dxf + reverse_sequence(dxb, len_src)
+    else:
+        dx = 0
+        for k, st in enumerate(stacks):
+            d = np.ascontiguousarray(dhs[..., k * H:(k + 1) * H])
+            if k == 1:
+                d = reverse_sequence(d, len_src)
+            for j in range(L - 1, -1, -1):
+                p = '%sl%d/' % (st, j)
+                d, _, dW, dR, dbW, dbR = gru_backward(d, None, cache['enc'][k][j], P[p + 'W'], P[p + 'R'])
+                G[p + 'W'] += dW; G[p + 'R'] += dR; G[p + 'bW'] += dbW; G[p + 'bR'] += dbR
+            dx = dx + (reverse_sequence(d, len_src) if k == 1 else d)
+        dhs = dx
     np.add.at(G['embed/embedding'], cache['src_tm'], dhs)
     return G
 

@@ -32,8 +32,8 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     if (V <= 0 || D <= 0 || R <= 0 || L <= 0) throw std::runtime_error("bad model dimensions");
     if (c.attentive)
         throw std::runtime_error("attentive=true is not implemented (unused by config.json; the reference marks it 'todo fixme', src/model.py:136)");
-    if (!c.bidirectional || !c.bidir_stacked)
-        throw std::runtime_error("only the stacked bidirectional encoder of config.json is implemented (src/model.py:118-122)");
+    enc_kind = (c.bidirectional && c.bidir_stacked) ? 0 : (c.bidirectional ? 1 : 2);
+    EH = (enc_kind == 2) ? H : 2 * H;
     tied = c.logit_use_embed != 0;   // false: separate (D,V) projection + bias (src/model.py:167-168)
     if (D % 8 || R % 8 || V % 8) throw std::runtime_error("dim_tgt, dim_emb and dim_rep must be multiples of 8");
     int ndev = 0;
@@ -77,9 +77,16 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
         add(pre + "W", 3 * H, D); add(pre + "R", 3 * H, H); add(pre + "bW", 3 * H, 0); add(pre + "bR", 3 * H, 0);
     }
     add("latent/ex/kernel", R, D); add("latent/ex/bias", D, 0);
-    add("latent/mu/kernel", 2 * H, R); add("latent/mu/bias", R, 0);
-    add("latent/lv/kernel", 2 * H, R); add("latent/lv/bias", R, 0);
-    for (int i = L; i >= 1; --i) {
+    add("latent/mu/kernel", EH, R); add("latent/mu/bias", R, 0);
+    add("latent/lv/kernel", EH, R); add("latent/lv/bias", R, 0);
+    if (enc_kind != 0) {   // independent L-layer stack(s): layers in backward-completion order, directions adjacent
+        for (int j = L - 1; j >= 0; --j)
+            for (int d = 0; d < (enc_kind == 1 ? 2 : 1); ++d) {
+                const std::string pre = enc_prefix(d, j);
+                add(pre + "W", 3 * H, j == 0 ? D : H); add(pre + "R", 3 * H, H); add(pre + "bW", 3 * H, 0); add(pre + "bR", 3 * H, 0);
+            }
+    }
+    for (int i = L; i >= 1 && enc_kind == 0; --i) {
         std::string pre = "encode/rnn" + std::to_string(i) + "/";
         const int in = (i == 1) ? D : 2 * H;
         // fwd and bwd tensors adjacent so that [W_f;W_b] is one (6H,in) GEMM operand
@@ -445,7 +452,36 @@ void Engine::program(int mode, bool apply_update) {
     std::vector<float*> encCache(2 * L, nullptr);
     encX[0] = act(S, D);
     gather_embed(dp.ids_src, S, encX[0]);
-    for (int i = 0; i < L; ++i) {
+    const int nd_enc = (enc_kind == 2) ? 1 : 2;
+    std::vector<Mat> encIn[2];   // branches 1 / 2: encIn[d][j] = input of layer j of stack d, [L] = its top output
+    if (enc_kind != 0) {
+        // model.py:124-131: one or two independent L-layer stacks over the packed rows (the 'bwd' stack simply walks t
+        // downwards), concatenated only at the top; the two stacks of a layer run as the two directions of one launch
+        Mat HS = act(S, EH);
+        for (int d = 0; d < nd_enc; ++d) { encIn[d].resize(L + 1); encIn[d][0] = encX[0]; }
+        for (int j = 0; j < L; ++j) {
+            GruFwdArgs a[2];
+            for (int d = 0; d < nd_enc; ++d) {
+                const std::string pre = enc_prefix(d, j);
+                Mat GX = f32(S, 3 * H);
+                gemm(encIn[d][j], 0, pmat(pre + "W"), 0, GX, S, 3 * H, j == 0 ? D : H, 1.f, p + pinfo(pre + "bW").off, 0);
+                Mat out = (j == L - 1) ? HS.colslice(d * H, H) : act(S, H);
+                if (train) encCache[d * L + j] = (float*)arena.alloc(sizeof(float) * S * 4 * H);
+                a[d].gx = GX.f; a[d].ld_gx = 3 * H;
+                a[d].R_f = p + pinfo(pre + "R").off;
+                a[d].R_h = ph ? ph + pinfo(pre + "R").off : nullptr;
+                a[d].bR = p + pinfo(pre + "bR").off;
+                a[d].h0 = nullptr;
+                a[d].hs_f = out.f; a[d].hs_h = out.h; a[d].ld_hs = out.ld;
+                a[d].cache = encCache[d * L + j];
+                a[d].reverse = (enc_kind == 1 && d == 1) ? 1 : 0;
+                encIn[d][j + 1] = out;
+            }
+            gru_fwd(a, nd_enc, E, dp.enc_off, dp.enc_nact);
+        }
+        encX[L] = HS;
+    }
+    for (int i = 0; i < L && enc_kind == 0; ++i) {
         const int in = (i == 0) ? D : 2 * H;
         const std::string pre = "encode/rnn" + std::to_string(i + 1) + "/";
         Mat W = pmat(pre + "fwd/W");
@@ -474,17 +510,17 @@ void Engine::program(int mode, bool apply_update) {
     phase("enc_fwd");
 
     // ---------------- final state + latent (model.py:133-156)
-    Mat henc = both(b, 2 * H);
-    RUN(launch_row_gather(encX[L].f, encX[L].h, 2 * H, dp.enc_last, henc.f, henc.h, 2 * H, nullptr, b, 2 * H, s));
+    Mat henc = both(b, EH);
+    RUN(launch_row_gather(encX[L].f, encX[L].h, EH, dp.enc_last, henc.f, henc.h, EH, nullptr, b, EH, s));
     Mat mulv = f32(b, 2 * R);
-    gemm(henc, 0, pmat("latent/mu/kernel"), 1, mulv.colslice(0, R), b, R, 2 * H, 1.f, p + pinfo("latent/mu/bias").off, 0);
+    gemm(henc, 0, pmat("latent/mu/kernel"), 1, mulv.colslice(0, R), b, R, EH, 1.f, p + pinfo("latent/mu/bias").off, 0);
     outp = Out();
     outp.mulv = mulv.f;
     if (mode == 0) {
         phase("latent_fwd");
         return;
     }
-    gemm(henc, 0, pmat("latent/lv/kernel"), 1, mulv.colslice(R, R), b, R, 2 * H, 1.f, p + pinfo("latent/lv/bias").off, 0);
+    gemm(henc, 0, pmat("latent/lv/kernel"), 1, mulv.colslice(R, R), b, R, EH, 1.f, p + pinfo("latent/lv/bias").off, 0);
     Mat z = both(b, R);
     float* eps_used = train ? (float*)arena.alloc(sizeof(float) * b * R) : nullptr;
     float* kld_samp = (float*)arena.alloc(sizeof(float) * b * R);
@@ -730,16 +766,16 @@ void Engine::program(int mode, bool apply_update) {
     gemm(dhx, 0, pmat("latent/ex/kernel"), 0, dz, b, R, D, 1.f, nullptr, 0);
     Mat dmulv = both(b, 2 * R);
     RUN(launch_latent_bwd(dz.f, mulv.f, eps_used, b, R, 1, anneal / ((float)b_glob * (float)R), dmulv.f, dmulv.h, s));
-    gemm(henc, 1, dmulv.colslice(0, R), 1, gmat("latent/mu/kernel"), 2 * H, R, b, 1.f, nullptr, 1);
-    gemm(henc, 1, dmulv.colslice(R, R), 1, gmat("latent/lv/kernel"), 2 * H, R, b, 1.f, nullptr, 1);
+    gemm(henc, 1, dmulv.colslice(0, R), 1, gmat("latent/mu/kernel"), EH, R, b, 1.f, nullptr, 1);
+    gemm(henc, 1, dmulv.colslice(R, R), 1, gmat("latent/lv/kernel"), EH, R, b, 1.f, nullptr, 1);
     {
         Mat a_mu(dmulv.f, nullptr, b, R, 2 * R), a_lv(dmulv.f + R, nullptr, b, R, 2 * R);
         colsum(a_mu, b, R, gptr("latent/mu/bias"));
         colsum(a_lv, b, R, gptr("latent/lv/bias"));
     }
-    Mat dhenc = f32(b, 2 * H);
-    gemm(dmulv.colslice(0, R), 0, pmat("latent/mu/kernel"), 0, dhenc, b, 2 * H, R, 1.f, nullptr, 0);
-    gemm(dmulv.colslice(R, R), 0, pmat("latent/lv/kernel"), 0, dhenc, b, 2 * H, R, 1.f, nullptr, 1);
+    Mat dhenc = f32(b, EH);
+    gemm(dmulv.colslice(0, R), 0, pmat("latent/mu/kernel"), 0, dhenc, b, EH, R, 1.f, nullptr, 0);
+    gemm(dmulv.colslice(R, R), 0, pmat("latent/lv/kernel"), 0, dhenc, b, EH, R, 1.f, nullptr, 1);
     {
         const size_t end = pinfo("latent/lv/bias").off + align_up(R, 64);
         allreduce_bucket(bucket_lo, end);
@@ -750,9 +786,58 @@ void Engine::program(int mode, bool apply_update) {
     // ---------------- backward: encoder (gather_nd adjoint, then BPTT through 3 x 2 GRUs)
     Mat dHS = f32(S, 2 * H), dHSn = f32(S, 2 * H);
     RUN(CUDA_CHECK(cudaMemsetAsync(dHS.f, 0, sizeof(float) * S * 2 * H, s)));
-    RUN(launch_row_scatter(dhenc.f, 2 * H, dHS.f, 2 * H, dp.enc_last, b, 2 * H, 0, s));
+    if (enc_kind == 0) RUN(launch_row_scatter(dhenc.f, 2 * H, dHS.f, 2 * H, dp.enc_last, b, 2 * H, 0, s));
     Mat dGXe = act(S, 6 * H), dGHe = act(S, 6 * H), HPe = act(S, 2 * H);
-    for (int i = L - 1; i >= 0; --i) {
+    if (enc_kind != 0) {
+        // BPTT through the independent stack(s): the top layer reads its slice of d hs, lower layers their own dX
+        Mat dTop(dHS.f, nullptr, S, EH, EH);
+        RUN(launch_row_scatter(dhenc.f, EH, dTop.f, EH, dp.enc_last, b, EH, 0, s));
+        Mat dcur[2], dnext[2];
+        for (int d = 0; d < nd_enc; ++d) { dcur[d] = f32(S, H); dnext[d] = f32(S, H); }
+        Mat dX0(dHSn.f, nullptr, S, D, D);
+        for (int j = L - 1; j >= 0; --j) {
+            GruBwdArgs a[2];
+            for (int d = 0; d < nd_enc; ++d) {
+                const std::string pre = enc_prefix(d, j);
+                const Mat& out = encIn[d][j + 1];
+                if (j == L - 1) { a[d].dhs = dTop.f + d * H; a[d].ld_dhs = EH; }
+                else { a[d].dhs = dcur[d].f; a[d].ld_dhs = H; }
+                a[d].hs_f = out.f; a[d].hs_h = out.h; a[d].ld_hs = out.ld;
+                a[d].h0 = nullptr;
+                a[d].cache = encCache[d * L + j];
+                a[d].R_f = p + pinfo(pre + "R").off;
+                a[d].R_h = ph ? ph + pinfo(pre + "R").off : nullptr;
+                a[d].dgx_f = dGXe.f ? dGXe.f + d * 3 * H : nullptr;
+                a[d].dgx_h = dGXe.h ? dGXe.h + d * 3 * H : nullptr;
+                a[d].dgh_f = dGHe.f ? dGHe.f + d * 3 * H : nullptr;
+                a[d].dgh_h = dGHe.h ? dGHe.h + d * 3 * H : nullptr;
+                a[d].ld_dg = 6 * H;
+                a[d].hp_f = HPe.f ? HPe.f + d * H : nullptr;
+                a[d].hp_h = HPe.h ? HPe.h + d * H : nullptr;
+                a[d].ld_hp = 2 * H;
+                a[d].dh0 = nullptr;
+                a[d].reverse = (enc_kind == 1 && d == 1) ? 1 : 0;
+            }
+            gru_bwd(a, nd_enc, E, dp.enc_off, dp.enc_nact);
+            for (int d = 0; d < nd_enc; ++d) {
+                const std::string pre = enc_prefix(d, j);
+                const int in = (j == 0) ? D : H;
+                Mat dgx = dGXe.colslice(d * 3 * H, 3 * H), dgh = dGHe.colslice(d * 3 * H, 3 * H);
+                gemm(dgx, 1, encIn[d][j], 1, gmat(pre + "W"), 3 * H, in, S, 1.f, nullptr, 1);
+                gemm(dgh, 1, HPe.colslice(d * H, H), 1, gmat(pre + "R"), 3 * H, H, S, 1.f, nullptr, 1);
+                colsum(dgx, S, 3 * H, gptr(pre + "bW"));
+                colsum(dgh, S, 3 * H, gptr(pre + "bR"));
+                if (j > 0) gemm(dgx, 0, pmat(pre + "W"), 1, dnext[d], S, H, 3 * H, 1.f, nullptr, 0);
+                else gemm(dgx, 0, pmat(pre + "W"), 1, dX0, S, D, 3 * H, 1.f, nullptr, d > 0 ? 1 : 0);   // both stacks read emb_src
+                std::swap(dcur[d], dnext[d]);
+            }
+            const size_t end = pinfo(enc_prefix(nd_enc - 1, j) + "bR").off + align_up(3 * H, 64);
+            allreduce_bucket(bucket_lo, end);
+            bucket_lo = end;
+        }
+        std::swap(dHS, dHSn);   // dHS now holds d emb_src (S,D) like the stacked branch leaves it
+    }
+    for (int i = L - 1; i >= 0 && enc_kind == 0; --i) {
         const int in = (i == 0) ? D : 2 * H;
         const std::string pre = "encode/rnn" + std::to_string(i + 1) + "/";
         GruBwdArgs a[2];

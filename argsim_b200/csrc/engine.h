@@ -130,6 +130,11 @@ private:
     void kend(cudaStream_t q = nullptr, double gflop = 0.0);
     bool in_ktimer = false;
     bool tied = true;   // logit_use_embed (src/model.py:164-168)
+    int enc_kind = 0;   // 0: stacked bidirectional (config.json); 1: two L-layer stacks, concatenated at the top; 2: one stack
+    int EH = 0;         // encoder output width: 2H (bidirectional) or H
+    std::string enc_prefix(int d, int j) const {   // encoder branches 1 / 2 (src/model.py:124-131)
+        return std::string(enc_kind == 1 ? (d ? "encode/rnn/bwd/l" : "encode/rnn/fwd/l") : "encode/rnn/l") + std::to_string(j) + "/";
+    }
     void collect_timings();
 
     Mat pmat(const std::string& name);

@@ -111,8 +111,6 @@ def vAe(mode, src=None, tgt=None, dim_tgt=8192, dim_emb=512, dim_rep=1024, rnn_l
                   learn_rate=learn_rate, bos=bos, eos=eos)
     if attentive:
         raise NotImplementedError("attentive=True is not on the hot path (config.json: false; 'todo fixme' at src/model.py:136)")
-    if not (bidirectional and bidir_stacked):
-        raise NotImplementedError('only the stacked bidirectional encoder of config.json is implemented (src/model.py:118-122)')
     if _state['config'] is None:
         _state['config'] = config
     elif _state['config'] != config:

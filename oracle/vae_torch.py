@@ -46,11 +46,22 @@ def forward(P, cfg, src, tgt, mode='valid', step=0, keep=None, eps=None, encoder
     b = src_tm.shape[1]
     x = E[src_tm]
     z0 = torch.zeros(b, H, dtype=dt)
-    for i in range(1, L + 1):
-        pf, pb = 'encode/rnn%d/fwd/' % i, 'encode/rnn%d/bwd/' % i
-        fwd, _ = _gru(x, z0, P[pf + 'W'], P[pf + 'R'], P[pf + 'bW'], P[pf + 'bR'])
-        bwd, _ = _gru(reverse_sequence(x, len_src), z0, P[pb + 'W'], P[pb + 'R'], P[pb + 'bW'], P[pb + 'bR'])
-        x = torch.cat([fwd, reverse_sequence(bwd, len_src)], -1)
+    bidir, stacked = cfg.get('bidirectional', True), cfg.get('bidir_stacked', True)
+    if bidir and stacked:                                   # model.py:118-122
+        for i in range(1, L + 1):
+            pf, pb = 'encode/rnn%d/fwd/' % i, 'encode/rnn%d/bwd/' % i
+            fwd, _ = _gru(x, z0, P[pf + 'W'], P[pf + 'R'], P[pf + 'bW'], P[pf + 'bR'])
+            bwd, _ = _gru(reverse_sequence(x, len_src), z0, P[pb + 'W'], P[pb + 'R'], P[pb + 'bW'], P[pb + 'bR'])
+            x = torch.cat([fwd, reverse_sequence(bwd, len_src)], -1)
+    else:                                                   # model.py:124-131
+        outs = []
+        for k, st in enumerate(['encode/rnn/fwd/', 'encode/rnn/bwd/'] if bidir else ['encode/rnn/']):
+            y = reverse_sequence(x, len_src) if k == 1 else x
+            for j in range(L):
+                p = '%sl%d/' % (st, j)
+                y, _ = _gru(y, z0, P[p + 'W'], P[p + 'R'], P[p + 'bW'], P[p + 'bR'])
+            outs.append(reverse_sequence(y, len_src) if k == 1 else y)
+        x = torch.cat(outs, -1)
     h = x[len_src - 1, torch.arange(b)]
     mu = h @ P['latent/mu/kernel'] + P['latent/mu/bias']
     o = dict(mu=mu, z=mu, rate_update=float(lr), rate_anneal=float(anneal))

@@ -140,3 +140,29 @@ def test_embed_microbatches_large_batch():
         np.testing.assert_allclose(big[i0:i0 + 100], h.embed(src[i0:i0 + 100]), rtol=0, atol=2e-2)
     ov, _ = O.forward(P, cfg, src[:24], src[:24], 'valid')
     assert np.abs(big[:24] - ov['mu']).max() / np.abs(ov['mu']).max() < 2e-2
+
+
+@pytest.mark.parametrize('bidirectional,bidir_stacked', [(True, False), (False, False)])
+def test_non_default_encoder_branches_on_the_persistent_kernels(bidirectional, bidir_stacked):
+    """H = 512: the independent encoder stacks of src/model.py:124-131 run on the persistent recurrence (two stacks =
+    the two directions of one launch with separate input projections; one stack = a single-direction launch)."""
+    from argsim_b200 import _lib
+    cfg = dict(dim_tgt=1024, dim_emb=512, dim_rep=256, rnn_layers=2, accelerate=1e-4, learn_rate=1e-3, bos=2, eos=1,
+               bidirectional=bidirectional, bidir_stacked=bidir_stacked)
+    h, P = _mk(cfg, _lib.BF16)
+    src = ragged_batch(12, 19, cfg['dim_tgt'], 90)
+    tgt = ragged_batch(12, 15, cfg['dim_tgt'], 91)
+    keep, eps = _inject(cfg, tgt, 92)
+    h.step = 15000
+    o, cache = O.forward(P, cfg, src, tgt, 'train', step=15000, keep=_oracle_keep(keep, tgt, cfg['eos']), eps=eps.astype(np.float64))
+    G = O.backward(P, cfg, cache)
+    st = h.grad_step(src, tgt, keep=keep, eps=eps)
+    for name in ('loss', 'loss_gen', 'loss_kld'):
+        assert rel(st[name], o[name]) < TOL, (name, st[name], o[name])
+    for k in P:
+        if np.linalg.norm(G[k]) < 1e-12:
+            continue
+        g = h.get_grad(k).astype(np.float64).ravel()
+        r = G[k].ravel()
+        cos = g @ r / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30)
+        assert cos > 0.995, (k, cos)

@@ -223,3 +223,34 @@ def test_untied_logit_projection_branch(prec):
         ref = O.decode_greedy({k: v.astype(np.float32) for k, v in P.items()}, cfg, z, steps=6)
         np.testing.assert_array_equal(h.decode(z, steps=6), ref)
     h.close()
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('bidirectional,bidir_stacked', [(True, False), (False, True)])
+def test_non_default_encoder_branches(prec, bidirectional, bidir_stacked):
+    """src/model.py:124-131: the non-stacked bidirectional encoder (two L-layer stacks, concatenated at the top) and the
+    unidirectional one (mu / lv read H instead of 2H columns) -- losses, all gradients, the embedding."""
+    from argsim_b200 import _lib
+    cfg = dict(SMALL, bidirectional=bidirectional, bidir_stacked=bidir_stacked)
+    h, P = _mk(cfg, _lib.FP32_VALIDATE if prec == 'fp32' else _lib.BF16)
+    assert set(h.param_shapes()) == set(P) and all(h.param_shapes()[k] == v.shape for k, v in P.items())
+    src = ragged_batch(9, 13, cfg['dim_tgt'], 80)
+    tgt = ragged_batch(9, 10, cfg['dim_tgt'], 81)
+    keep, eps = _inject(cfg, tgt, 82)
+    h.step = 9000
+    o, cache = O.forward(P, cfg, src, tgt, 'train', step=9000, keep=_oracle_keep(keep, tgt, cfg['eos']), eps=eps.astype(np.float64))
+    G = O.backward(P, cfg, cache)
+    st = h.grad_step(src, tgt, keep=keep, eps=eps)
+    tol = 1e-3 if prec == 'fp32' else 1e-2
+    for k in ('loss', 'loss_gen', 'loss_kld'):
+        assert rel(st[k], o[k]) < tol, (k, st[k], o[k])
+    for k in P:
+        g = h.get_grad(k).astype(np.float64)
+        if prec == 'fp32':
+            assert np.abs(g - G[k]).max() <= 2e-4 * np.abs(G[k]).max() + 1e-9, k
+        elif np.linalg.norm(G[k]) > 1e-12:
+            cos = (g.ravel() @ G[k].ravel()) / (np.linalg.norm(g) * np.linalg.norm(G[k]) + 1e-30)
+            assert cos > 0.99, (k, cos)
+    mu = h.embed(src)
+    assert np.abs(mu - o['mu']).max() <= (1e-4 if prec == 'fp32' else 3e-2) * np.abs(o['mu']).max()
+    h.close()

@@ -146,6 +146,7 @@ class Session:
         prec = {'bf16': _lib.BF16, 'fp32': _lib.FP32_VALIDATE}[precision] if isinstance(precision, str) else precision
         self.handle = _lib.Handle(precision=prec, device=device, nranks=nranks, rank=rank, nccl_id=nccl_id, flags=flags, **cfg)
         self.handle.set_seed(_state['seed'])
+        self.config = dict(cfg)
         self.nranks, self.rank = nranks, rank
         self.last_stats = None
         _state['session'] = self
@@ -261,15 +262,26 @@ def global_variables_initializer(session=None, seed=None):
 
 
 class Saver:
-    """tf.train.Saver stand-in (src/train.py:92-96,121): parameters, Adam slots and the global step in
-    the library's own flat container (TF V2 bundles cannot be parsed without TF)."""
+    """tf.train.Saver stand-in (src/train.py:92-96,121): parameters, Adam slots and the global step.  `save` writes
+    the library's own flat container, or -- `tf_format=True` -- a TF V2 bundle under the reference's variable names;
+    `restore` reads either: a path with a `<path>.index` next to it is taken for a checkpoint the reference wrote
+    (argsim_b200/tf_ckpt.py: container format restated without TensorFlow, name mapping unverified -- see its header)."""
 
-    def save(self, sess, path, write_meta_graph=False):
-        sess.handle.save(path)
+    def save(self, sess, path, write_meta_graph=False, tf_format=False):
+        if tf_format:
+            from . import tf_ckpt
+            tf_ckpt.save_reference_checkpoint(sess.handle, path, sess.config)
+        else:
+            sess.handle.save(path)
         return path
 
     def restore(self, sess, path):
-        sess.handle.load(path)
+        import os
+        if os.path.exists(path + '.index') and not os.path.exists(path):
+            from . import tf_ckpt
+            self.unplaced = tf_ckpt.load_reference_checkpoint(sess.handle, path, sess.config)
+        else:
+            sess.handle.load(path)
 
 
 def encode(sess, vae, src):

@@ -254,3 +254,36 @@ def test_non_default_encoder_branches(prec, bidirectional, bidir_stacked):
     mu = h.embed(src)
     assert np.abs(mu - o['mu']).max() <= (1e-4 if prec == 'fp32' else 3e-2) * np.abs(o['mu']).max()
     h.close()
+
+
+def test_tf_bundle_export_import_roundtrip(tmp_path):
+    """Saver.save(tf_format=True) -> <path>.index / .data-00000-of-00001 under the reference's variable names -> Saver.restore
+    into a fresh session: parameters (up to the r/u bias split the cuDNN-canonical form cannot keep), Adam slots, the
+    step and therefore the next training step are reproduced."""
+    from argsim_b200 import _lib, model as M
+    cfg = dict(SMALL)
+    M.reset() if hasattr(M, 'reset') else M._state.update(config=None, session=None)
+    m = M.vAe('valid', **cfg)
+    sess = M.Session(precision='fp32')
+    M.global_variables_initializer(sess)
+    src = ragged_batch(6, 9, cfg['dim_tgt'], 5)
+    keep, eps = _inject(cfg, src, 6)
+    for _ in range(3):
+        sess.handle.train_step(src, src, keep=keep, eps=eps)
+    path = str(tmp_path / 'master0')
+    M.Saver().save(sess, path, tf_format=True)
+    assert (tmp_path / 'master0.index').exists() and (tmp_path / 'master0.data-00000-of-00001').exists()
+    ref = sess.handle.train_step(src, src, keep=keep, eps=eps)
+    sess.close()
+    M._state.update(config=None, session=None)
+    m = M.vAe('valid', **cfg)
+    sess2 = M.Session(precision='fp32')
+    sv = M.Saver()
+    sv.restore(sess2, path)
+    assert sv.unplaced == []
+    assert sess2.handle.step == 3
+    got = sess2.handle.train_step(src, src, keep=keep, eps=eps)
+    for k in ('loss', 'loss_gen', 'loss_kld'):
+        assert rel(got[k], ref[k]) < 1e-5, (k, got[k], ref[k])
+    sess2.close()
+    M._state.update(config=None, session=None)

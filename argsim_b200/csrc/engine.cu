@@ -593,7 +593,7 @@ void Engine::program(int mode, bool apply_update) {
                     GruFwdArgs a = dec_fwd_args(j);
                     if (sg > 0) a.h0 = hT[j][(sg - 1) & 1];
                     a.hT = (sg + 1 < nseg) ? hT[j][sg & 1] : nullptr;
-                    gru_mma_fwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j);
+                    gru_mma_fwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j, (j == 0 && sg == 0 && !getenv("ARGSIM_NO_ALONE")) ? 1 : 0);   // first stage of the wavefront: nothing else runs
                     done[j * nseg + sg] = next_event();
                     CUDA_CHECK(cudaEventRecord(done[j * nseg + sg], q));
                 }
@@ -734,7 +734,7 @@ void Engine::program(int mode, bool apply_update) {
                     GruBwdArgs a = dec_bwd_args(j, dYl[j], dGXl[j], dGHl[j], HPl[j], dh0l[j]);
                     a.dh_in = (sg + 1 < nseg) ? carry[j][(sg + 1) & 1] : nullptr;
                     a.dh_out = (sg > 0) ? carry[j][sg & 1] : nullptr;
-                    gru_mma_bwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j);
+                    gru_mma_bwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j, (j == 0 && sg == 0 && !getenv("ARGSIM_NO_ALONE")) ? 1 : 0);   // last stage of the reverse wavefront
                     done[j * nseg + sg] = next_event();
                     CUDA_CHECK(cudaEventRecord(done[j * nseg + sg], q));
                 }

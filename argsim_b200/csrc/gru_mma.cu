@@ -1058,9 +1058,11 @@ static void dump_prof(GruMmaCtx* c, const char* what, int nblocks, int steps, cu
     fprintf(stderr, "\n");
 }
 
-static void pick_slices(const GruMmaCtx* c, int ndir, int b, int* ns, int* bslr) {
+// rows_per_slice = 16 fills both n=8 MMA tiles of a chunk; 8 (a launch that has the chip to itself) keeps every slice at
+// one MMA tile per step -- about 2,700 instead of 4,700 cycles per step while more than 8 rows per slice are alive
+static void pick_slices(const GruMmaCtx* c, int ndir, int b, int* ns, int* bslr, int rows_per_slice = CH) {
     const int max_groups = std::max(1, c->num_sms / CL);
-    int s = std::max(1, std::min(max_groups / ndir, (b + CH - 1) / CH));
+    int s = std::max(1, std::min(max_groups / ndir, (b + rows_per_slice - 1) / rows_per_slice));
     int per = (b + s - 1) / s;
     *ns = s;
     *bslr = (per + CH - 1) / CH * CH;
@@ -1074,7 +1076,7 @@ bool gru_mma_fits(const GruMmaCtx* c, int ndir, int b) {
 // One launch = steps [t0, t0+Tseg) of the plan (Tseg < 0: all).  `slot` selects the LL exchange buffer: launches
 // that may run CONCURRENTLY (decoder wavefront: one stream per layer) must use different slots.
 void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& Pl, const int* d_off, const int* d_nact, int H,
-                 cudaStream_t s, int t0, int Tseg, int slot) {
+                 cudaStream_t s, int t0, int Tseg, int slot, int alone) {
     if (H != HH) throw std::runtime_error("gru_mma: H must be 512");
     if (Tseg < 0) { t0 = 0; Tseg = Pl.Tmax; }
     if (Tseg >= 4096) throw std::runtime_error("gru_mma: more than 4095 steps per launch");
@@ -1083,7 +1085,7 @@ void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& 
     int ns, bslr;
     // sequences alive in the segment: forward directions shrink with t, so the first step has the most
     const int b_seg = (ndir == 1 && !dirs[0].reverse) ? Pl.nact[t0] : Pl.b;
-    pick_slices(c, ndir, b_seg, &ns, &bslr);
+    pick_slices(c, ndir, b_seg, &ns, &bslr, alone ? 8 : CH);
     if (bslr > MAX_BSL) throw std::runtime_error("gru_mma: batch too large for the persistent kernel");
     for (int d = 0; d < ndir; ++d) {
         const GruFwdArgs& a = dirs[d];
@@ -1119,7 +1121,7 @@ void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& 
 }
 
 void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& Pl, const int* d_off, const int* d_nact, int H,
-                 cudaStream_t s, int t0, int Tseg, int slot) {
+                 cudaStream_t s, int t0, int Tseg, int slot, int alone) {
     if (H != HH) throw std::runtime_error("gru_mma: H must be 512");
     if (Tseg < 0) { t0 = 0; Tseg = Pl.Tmax; }
     if (Tseg >= 4096) throw std::runtime_error("gru_mma: more than 4095 steps per launch");
@@ -1127,7 +1129,7 @@ void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& 
     BwdP P;
     int ns, bslr;
     const int b_seg = (ndir == 1 && !dirs[0].reverse) ? Pl.nact[t0] : Pl.b;
-    pick_slices(c, ndir, b_seg, &ns, &bslr);
+    pick_slices(c, ndir, b_seg, &ns, &bslr, alone ? 8 : CH);
     if (bslr > MAX_BSL) throw std::runtime_error("gru_mma: batch too large for the persistent kernel");
     for (int d = 0; d < ndir; ++d) {
         const GruBwdArgs& a = dirs[d];

@@ -1,13 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_bf16.py tests/test_golden.py tests/test_gpu_fullsize.py -m gpu -q -x 2>&1 | tail -3
-for i in 1 2; do
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/m13_bench.json 2> gpurun_out/m13_bench.err
+timeout 900 python -m pytest tests/test_gpu_bf16.py tests/test_golden.py tests/test_gpu_fullsize.py -m gpu -q -x 2>&1 | tail -2
+for NA in 0 1 0 1; do
+if [ $NA = 1 ]; then export ARGSIM_NO_ALONE=1; else unset ARGSIM_NO_ALONE; fi
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/m14_bench.json 2> gpurun_out/m14_bench.err
 python - <<PY
 import json,os
-d=json.loads(open('gpurun_out/m13_bench.json').read().strip().splitlines()[-1])
-print('ms_per_step', round(d['ms_per_step'],3), {k:round(v['ms_per_step'],3) for k,v in d['kernels'].items() if k.startswith('gru')}, d['last_step']['loss'])
+d=json.loads(open('gpurun_out/m14_bench.json').read().strip().splitlines()[-1])
+print('no_alone=$NA ms_per_step', round(d['ms_per_step'],3), {k:round(v['ms_per_step'],3) for k,v in d['kernels'].items() if k.startswith('gru')}, d['last_step']['loss'])
 PY
 done
-ARGSIM_GRU_FWD2_OPT=2 ARGSIM_GRU_PROF=1 timeout 600 python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/var.json 2> gpurun_out/var.err
-grep gru_prof gpurun_out/var.err | grep "fwd_enc\|bwd_enc" | tail -4 | cut -c1-200

@@ -1060,6 +1060,10 @@ static void dump_prof(GruMmaCtx* c, const char* what, int nblocks, int steps, cu
 
 // rows_per_slice = 16 fills both n=8 MMA tiles of a chunk; 8 (a launch that has the chip to itself) keeps every slice at
 // one MMA tile per step -- about 2,700 instead of 4,700 cycles per step while more than 8 rows per slice are alive
+static int small8_rows() {   // single-direction launches with at most this many live rows use 8-row slices (A/B: ARGSIM_SMALL8_ROWS)
+    static const int v = getenv("ARGSIM_SMALL8_ROWS") ? atoi(getenv("ARGSIM_SMALL8_ROWS")) : CH;
+    return v;
+}
 static void pick_slices(const GruMmaCtx* c, int ndir, int b, int* ns, int* bslr, int rows_per_slice = CH) {
     const int max_groups = std::max(1, c->num_sms / CL);
     int s = std::max(1, std::min(max_groups / ndir, (b + rows_per_slice - 1) / rows_per_slice));
@@ -1085,7 +1089,7 @@ void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& 
     int ns, bslr;
     // sequences alive in the segment: forward directions shrink with t, so the first step has the most
     const int b_seg = (ndir == 1 && !dirs[0].reverse) ? Pl.nact[t0] : Pl.b;
-    pick_slices(c, ndir, b_seg, &ns, &bslr, alone ? 8 : CH);
+    pick_slices(c, ndir, b_seg, &ns, &bslr, (alone || (ndir == 1 && b_seg <= small8_rows())) ? 8 : CH);   // <= 16 rows alive: two groups of <= 8 cost 16 more SMs and halve the MMA work per step
     if (bslr > MAX_BSL) throw std::runtime_error("gru_mma: batch too large for the persistent kernel");
     for (int d = 0; d < ndir; ++d) {
         const GruFwdArgs& a = dirs[d];
@@ -1129,7 +1133,7 @@ void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& 
     BwdP P;
     int ns, bslr;
     const int b_seg = (ndir == 1 && !dirs[0].reverse) ? Pl.nact[t0] : Pl.b;
-    pick_slices(c, ndir, b_seg, &ns, &bslr, alone ? 8 : CH);
+    pick_slices(c, ndir, b_seg, &ns, &bslr, (alone || (ndir == 1 && b_seg <= small8_rows())) ? 8 : CH);   // <= 16 rows alive: two groups of <= 8 cost 16 more SMs and halve the MMA work per step
     if (bslr > MAX_BSL) throw std::runtime_error("gru_mma: batch too large for the persistent kernel");
     for (int d = 0; d < ndir; ++d) {
         const GruBwdArgs& a = dirs[d];

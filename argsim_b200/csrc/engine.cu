@@ -559,6 +559,35 @@ void Engine::program(int mode, bool apply_update) {
     };
     const bool wave = dec_wavefront(Dp);
     const int nseg = wave ? (Dp.Tmax + dec_seg - 1) / dec_seg : 1;
+    // Slices per wavefront launch.  A slice of <= 8 live rows needs one n=8 MMA tile per step (~2,700 cycles), a slice of
+    // 9..16 rows two (~4,700), but 8-row slices cost twice the CTAs.  Launches (layer j, segment sg) with the same
+    // j + sg run side by side: within the 9 groups of 16 CTAs the chip holds, the launches with the most live rows get
+    // 8-row slices first.  want8[j * nseg + sg] = 1 -> 8 rows per slice.
+    std::vector<int> want8((size_t)L * nseg, 0);
+    if (wave && !getenv("ARGSIM_NO_SLICE_BUDGET")) {
+        const int max_groups = 9;
+        for (int stage = 0; stage < nseg + L - 1; ++stage) {
+            std::vector<std::pair<int, int>> items;   // (live rows, j)
+            int total = 0;
+            for (int j = 0; j < L; ++j) {
+                const int sg = stage - j;
+                if (sg < 0 || sg >= nseg) continue;
+                const int rows = Dp.nact[sg * dec_seg];
+                const bool small = rows <= 16;
+                want8[(size_t)j * nseg + sg] = small ? 1 : 0;
+                total += small ? (rows + 7) / 8 : (rows + 15) / 16;
+                if (!small) items.push_back({rows, j});
+            }
+            std::sort(items.begin(), items.end(), [](const std::pair<int, int>& x, const std::pair<int, int>& y) { return x.first > y.first; });
+            for (auto& it : items) {
+                const int g16 = (it.first + 15) / 16, g8 = (it.first + 7) / 8;
+                if (total - g16 + g8 <= max_groups) {
+                    total += g8 - g16;
+                    want8[(size_t)it.second * nseg + (stage - it.second)] = 1;
+                }
+            }
+        }
+    }
     if (!wave) {
         for (int j = 0; j < L; ++j) {
             const std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
@@ -593,7 +622,7 @@ void Engine::program(int mode, bool apply_update) {
                     GruFwdArgs a = dec_fwd_args(j);
                     if (sg > 0) a.h0 = hT[j][(sg - 1) & 1];
                     a.hT = (sg + 1 < nseg) ? hT[j][sg & 1] : nullptr;
-                    gru_mma_fwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j, (j == 0 && sg == 0 && !getenv("ARGSIM_NO_ALONE")) ? 1 : 0);   // first stage of the wavefront: nothing else runs
+                    gru_mma_fwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j, want8[(size_t)j * nseg + sg]);
                     done[j * nseg + sg] = next_event();
                     CUDA_CHECK(cudaEventRecord(done[j * nseg + sg], q));
                 }
@@ -734,7 +763,7 @@ void Engine::program(int mode, bool apply_update) {
                     GruBwdArgs a = dec_bwd_args(j, dYl[j], dGXl[j], dGHl[j], HPl[j], dh0l[j]);
                     a.dh_in = (sg + 1 < nseg) ? carry[j][(sg + 1) & 1] : nullptr;
                     a.dh_out = (sg > 0) ? carry[j][sg & 1] : nullptr;
-                    gru_mma_bwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j, (j == 0 && sg == 0 && !getenv("ARGSIM_NO_ALONE")) ? 1 : 0);   // last stage of the reverse wavefront
+                    gru_mma_bwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j, want8[(size_t)j * nseg + sg]);   // the reverse wavefront pairs the same (j, sg) launches
                     done[j * nseg + sg] = next_event();
                     CUDA_CHECK(cudaEventRecord(done[j * nseg + sg], q));
                 }

@@ -50,6 +50,8 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     for (auto& s : st) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto& s : sw) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     if (const char* ev = getenv("ARGSIM_DEC_SEG")) dec_seg = atoi(ev);
+    if (const char* ev = getenv("ARGSIM_ENC_SEG")) enc_seg = atoi(ev);
+    enc_seg_fwd = getenv("ARGSIM_ENC_SEG_FWD") != nullptr;
     if (L > 8) dec_seg = 0;
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_bucket, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
@@ -251,6 +253,34 @@ cudaEvent_t Engine::next_event() {
 bool Engine::dec_wavefront(const SeqPlan& Dp) const {
     return use_mma && L > 1 && dec_seg > 0 && Dp.Tmax > dec_seg && gru_mma_fits(mma, 1, Dp.b);
 }
+// The stacked encoder's two directions as two chains of time-segment launches (one stream each) instead of one launch
+// per layer: the forward direction has many live rows early and few late, the reverse direction the other way round, so
+// per segment the 9 groups of 16 CTAs can be split to give BOTH directions slices of <= 8 rows (one MMA tile per step)
+// almost everywhere, where a single launch is stuck with 4 slices of 16 rows per direction for all 512 steps.
+bool Engine::enc_segmented(const SeqPlan& E) const {
+    return use_mma && enc_kind == 0 && enc_seg > 0 && E.Tmax > enc_seg && gru_mma_fits(mma, 1, E.b);
+}
+// want8[d * nseg + i] for the i-th launch of chain d.  Forward pass: chain 0 walks segments upwards, chain 1 downwards;
+// BPTT: the other way round.  Launch i of both chains run side by side.
+void Engine::enc_slice_plan(const SeqPlan& E, int nseg, bool bptt, std::vector<int>* want8) const {
+    want8->assign((size_t)2 * nseg, 0);
+    for (int i = 0; i < nseg; ++i) {
+        int rows[2], g16[2], g8[2];
+        for (int d = 0; d < 2; ++d) {
+            const bool up = bptt ? (d == 1) : (d == 0);
+            const int sg = up ? i : nseg - 1 - i;
+            rows[d] = E.nact[sg * enc_seg];
+            g16[d] = (rows[d] + 15) / 16; g8[d] = (rows[d] + 7) / 8;
+        }
+        const int big = rows[0] >= rows[1] ? 0 : 1, small = 1 - big;
+        int use8[2] = {0, 0};
+        if (g8[0] + g8[1] <= 9) use8[0] = use8[1] = 1;
+        else if (g8[big] + g16[small] <= 9) use8[big] = 1;
+        else if (g16[big] + g8[small] <= 9) use8[small] = 1;
+        for (int d = 0; d < 2; ++d) (*want8)[(size_t)d * nseg + i] = use8[d] ? 1 : 2;   // 1 = 8-row slices, 2 = 16-row slices
+    }
+}
+
 void Engine::colsum(const Mat& A, long long rows, int cols, float* out, int accumulate) {
     if (arena.dry) return;
     if (A.f) launch_colsum_f32(A.f, A.ld, rows, cols, out, st[0], accumulate);
@@ -504,7 +534,39 @@ void Engine::program(int mode, bool apply_update) {
             a[d].cache = encCache[2 * i + d];
             a[d].reverse = d;
         }
-        gru_fwd(a, 2, E, dp.enc_off, dp.enc_nact);
+        if (enc_seg_fwd && enc_segmented(E)) {
+            const int nsegE = (E.Tmax + enc_seg - 1) / enc_seg;
+            float* hTe[2][2];
+            for (int d = 0; d < 2; ++d)
+                for (int q = 0; q < 2; ++q) hTe[d][q] = (float*)arena.alloc(sizeof(float) * b * H);
+            if (!arena.dry) {
+                std::vector<int> want8;
+                enc_slice_plan(E, nsegE, false, &want8);
+                for (int d = 0; d < 2; ++d)
+                    for (int q = 0; q < 2; ++q) CUDA_CHECK(cudaMemsetAsync(hTe[d][q], 0, sizeof(float) * b * H, s));
+                kbegin("k:gru_fwd_enc");
+                cudaEvent_t fork = next_event();
+                CUDA_CHECK(cudaEventRecord(fork, s));
+                for (int d = 0; d < 2; ++d) CUDA_CHECK(cudaStreamWaitEvent(sw[d], fork, 0));
+                for (int k = 0; k < nsegE; ++k)
+                    for (int d = 0; d < 2; ++d) {
+                        const int sg = d ? nsegE - 1 - k : k;   // the reverse direction starts at the end of the sequence
+                        const int t0 = sg * enc_seg, tl = std::min(enc_seg, E.Tmax - t0);
+                        GruFwdArgs x = a[d];
+                        x.h0 = (k > 0) ? hTe[d][(k - 1) & 1] : nullptr;
+                        x.hT = (k + 1 < nsegE) ? hTe[d][k & 1] : nullptr;
+                        gru_mma_fwd(mma, &x, 1, E, dp.enc_off, dp.enc_nact, H, sw[d], t0, tl, d, want8[(size_t)d * nsegE + k]);
+                    }
+                for (int d = 0; d < 2; ++d) {
+                    cudaEvent_t ev = next_event();
+                    CUDA_CHECK(cudaEventRecord(ev, sw[d]));
+                    CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));
+                }
+                kend();
+            }
+        } else {
+            gru_fwd(a, 2, E, dp.enc_off, dp.enc_nact);
+        }
         encX[i + 1] = HS;
     }
     phase("enc_fwd");
@@ -574,7 +636,7 @@ void Engine::program(int mode, bool apply_update) {
                 if (sg < 0 || sg >= nseg) continue;
                 const int rows = Dp.nact[sg * dec_seg];
                 const bool small = rows <= 16;
-                want8[(size_t)j * nseg + sg] = small ? 1 : 0;
+                want8[(size_t)j * nseg + sg] = small ? 1 : 2;   // 1 = 8-row slices, 2 = 16-row slices
                 total += small ? (rows + 7) / 8 : (rows + 15) / 16;
                 if (!small) items.push_back({rows, j});
             }
@@ -891,7 +953,41 @@ void Engine::program(int mode, bool apply_update) {
             a[d].dh0 = nullptr;
             a[d].reverse = d;
         }
-        gru_bwd(a, 2, E, dp.enc_off, dp.enc_nact);
+        if (enc_segmented(E)) {
+            // BPTT as two chains of segment launches: the forward GRU's walks the segments downwards, the reverse GRU's
+            // upwards; the gradient wrt the carried state is handed from launch to launch
+            const int nsegE = (E.Tmax + enc_seg - 1) / enc_seg;
+            float* carry[2][2];
+            for (int d = 0; d < 2; ++d)
+                for (int q = 0; q < 2; ++q) carry[d][q] = (float*)arena.alloc(sizeof(float) * b * H);
+            if (!arena.dry) {
+                std::vector<int> want8;
+                enc_slice_plan(E, nsegE, true, &want8);
+                for (int d = 0; d < 2; ++d)
+                    for (int q = 0; q < 2; ++q) CUDA_CHECK(cudaMemsetAsync(carry[d][q], 0, sizeof(float) * b * H, s));
+                kbegin("k:gru_bwd_enc");
+                cudaEvent_t fork = next_event();
+                CUDA_CHECK(cudaEventRecord(fork, s));
+                for (int d = 0; d < 2; ++d) CUDA_CHECK(cudaStreamWaitEvent(sw[d], fork, 0));
+                for (int k = 0; k < nsegE; ++k)
+                    for (int d = 0; d < 2; ++d) {
+                        const int sg = d ? k : nsegE - 1 - k;
+                        const int t0 = sg * enc_seg, tl = std::min(enc_seg, E.Tmax - t0);
+                        GruBwdArgs x = a[d];
+                        x.dh_in = (k > 0) ? carry[d][(k - 1) & 1] : nullptr;
+                        x.dh_out = (k + 1 < nsegE) ? carry[d][k & 1] : nullptr;
+                        gru_mma_bwd(mma, &x, 1, E, dp.enc_off, dp.enc_nact, H, sw[d], t0, tl, d, want8[(size_t)d * nsegE + k]);
+                    }
+                for (int d = 0; d < 2; ++d) {
+                    cudaEvent_t ev = next_event();
+                    CUDA_CHECK(cudaEventRecord(ev, sw[d]));
+                    CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));
+                }
+                kend();
+            }
+        } else {
+            gru_bwd(a, 2, E, dp.enc_off, dp.enc_nact);
+        }
         Mat gW = gmat(pre + "fwd/W");
         gW.rows = 6 * H;
         gemm(dGXe, 1, encX[i], 1, gW, 6 * H, in, S, 1.f, nullptr, 1);

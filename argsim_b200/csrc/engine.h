@@ -91,6 +91,10 @@ private:
     size_t evcount = 0;
     cudaEvent_t next_event();
     int dec_seg = 64;                                   // time steps per wavefront segment (0 = off)
+    int enc_seg = 171;                                  // encoder BPTT: time steps per (direction, segment) launch (0 = one launch per layer)
+    bool enc_seg_fwd = false;                           // measured: the forward pass is faster as one launch per layer (2.39 vs 2.56 ms), BPTT is not
+    bool enc_segmented(const SeqPlan& E) const;
+    void enc_slice_plan(const SeqPlan& E, int nseg, bool bptt, std::vector<int>* want8) const;
     bool dec_wavefront(const SeqPlan& Dp) const;
     cudaEvent_t ev_bucket = nullptr, ev_comm = nullptr;
     Arena arena;

@@ -955,9 +955,13 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
     }
     if (P.prof && tid == 0)
         for (int i = 0; i < 8; ++i) P.prof[blockIdx.x * 8 + i] = pacc[i];
-    // ---- gradient wrt the initial state (decoder: d ex(z)); the last BPTT step of a forward GRU is t = 0
-    float* const dh_dst = (P.t0 == 0) ? A.dh0 : A.dh_out;
-    if (dh_dst && !A.reverse && k_last >= 0) {
+    // ---- gradient wrt the state before the segment's first forward-pass step.  Forward GRU: its BPTT ends at t0 -- the
+    // initial state when t0 = 0 (decoder: accumulated into d ex(z)), else handed to the earlier segment.  Reverse GRU
+    // (time-segmented encoder): its BPTT ends at t0 + Tseg - 1; the state before that step belongs to the later segment
+    // (the reverse GRU starts from zeros at the end of the sequence, so the last segment hands nothing on).
+    const bool accum_dh = !A.reverse && P.t0 == 0;
+    float* const dh_dst = A.reverse ? ((P.t0 + P.Tseg < P.Ttot) ? A.dh_out : nullptr) : ((P.t0 == 0) ? A.dh0 : A.dh_out);
+    if (dh_dst && k_last >= 0) {
         const unsigned tagr = P.tag_base + (unsigned)k_last;
         const int parr = k_last & 1;
         for (int ch = 0; ch * CH < na_prev; ++ch) {
@@ -987,7 +991,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
                 }
                 const size_t di = (size_t)(jl * ns + sl) * HH + col;
                 const float val = cs[jl * UN + lane] + pin;
-                dh_dst[di] = (P.t0 == 0) ? dh_dst[di] + val : val;
+                dh_dst[di] = accum_dh ? dh_dst[di] + val : val;
             }
         }
     }
@@ -1088,13 +1092,15 @@ void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& 
     FwdP P;
     int ns, bslr;
     // sequences alive in the segment: forward directions shrink with t, so the first step has the most
-    const int b_seg = (ndir == 1 && !dirs[0].reverse) ? Pl.nact[t0] : Pl.b;
-    pick_slices(c, ndir, b_seg, &ns, &bslr, (alone || (ndir == 1 && b_seg <= small8_rows())) ? 8 : CH);   // <= 16 rows alive: two groups of <= 8 cost 16 more SMs and halve the MMA work per step
+    // rows alive anywhere in [t0, t0+Tseg): nact is non-increasing in t, so the segment's first time step has the most
+    // (for either direction of a single-direction launch; a two-direction launch spans all rows)
+    const int b_seg = (ndir == 1) ? Pl.nact[t0] : Pl.b;
+    pick_slices(c, ndir, b_seg, &ns, &bslr, (alone == 1 || (alone == 0 && ndir == 1 && b_seg <= small8_rows())) ? 8 : CH);   // alone: 0 = by live rows (<= 16: two groups of <= 8 rows cost 16 more SMs and halve the MMA work per step), 1 = 8-row slices, 2 = 16-row slices
     if (bslr > MAX_BSL) throw std::runtime_error("gru_mma: batch too large for the persistent kernel");
     for (int d = 0; d < ndir; ++d) {
         const GruFwdArgs& a = dirs[d];
         if (!a.R_h) throw std::runtime_error("gru_mma: bf16 weights missing");
-        if (a.h0 && a.reverse) throw std::runtime_error("gru_mma: h0 is only supported for forward directions");
+        if (a.h0 && a.reverse && ndir != 1) throw std::runtime_error("gru_mma: a reverse direction takes h0 only in a single-direction (segment) launch");
         P.dir[d] = FwdDirP{a.gx, a.R_h, a.bR, a.h0, a.hs_f, a.hs_h, a.cache, a.hT, a.ld_gx, a.ld_hs, a.reverse};
     }
     if (ndir == 1) P.dir[1] = P.dir[0];
@@ -1132,8 +1138,8 @@ void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& 
     if (slot < 0 || slot >= GruMmaCtx::NSLOT) throw std::runtime_error("gru_mma: bad slot");
     BwdP P;
     int ns, bslr;
-    const int b_seg = (ndir == 1 && !dirs[0].reverse) ? Pl.nact[t0] : Pl.b;
-    pick_slices(c, ndir, b_seg, &ns, &bslr, (alone || (ndir == 1 && b_seg <= small8_rows())) ? 8 : CH);   // <= 16 rows alive: two groups of <= 8 cost 16 more SMs and halve the MMA work per step
+    const int b_seg = (ndir == 1) ? Pl.nact[t0] : Pl.b;
+    pick_slices(c, ndir, b_seg, &ns, &bslr, (alone == 1 || (alone == 0 && ndir == 1 && b_seg <= small8_rows())) ? 8 : CH);   // alone: 0 = by live rows (<= 16: two groups of <= 8 rows cost 16 more SMs and halve the MMA work per step), 1 = 8-row slices, 2 = 16-row slices
     if (bslr > MAX_BSL) throw std::runtime_error("gru_mma: batch too large for the persistent kernel");
     for (int d = 0; d < ndir; ++d) {
         const GruBwdArgs& a = dirs[d];

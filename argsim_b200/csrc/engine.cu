@@ -620,7 +620,11 @@ void Engine::program(int mode, bool apply_update) {
         return a;
     };
     const bool wave = dec_wavefront(Dp);
-    const int nseg = wave ? (Dp.Tmax + dec_seg - 1) / dec_seg : 1;
+    // a trailing segment shorter than a quarter of the others is merged into its neighbour (IAC batches: 513 = 8 * 64 + 1
+    // steps would otherwise pay a whole pipeline stage of launches for one step)
+    int nseg = wave ? (Dp.Tmax + dec_seg - 1) / dec_seg : 1;
+    if (wave && nseg > 1 && (Dp.Tmax - (nseg - 1) * dec_seg) * 4 < dec_seg) --nseg;
+    auto seg_len = [&](int sg) { return sg + 1 < nseg ? dec_seg : Dp.Tmax - sg * dec_seg; };
     // Slices per wavefront launch.  A slice of <= 8 live rows needs one n=8 MMA tile per step (~2,700 cycles), a slice of
     // 9..16 rows two (~4,700), but 8-row slices cost twice the CTAs.  Launches (layer j, segment sg) with the same
     // j + sg run side by side: within the 9 groups of 16 CTAs the chip holds, the launches with the most live rows get
@@ -671,7 +675,7 @@ void Engine::program(int mode, bool apply_update) {
             for (int j = 0; j < L; ++j) CUDA_CHECK(cudaStreamWaitEvent(sw[j], fork, 0));
             std::vector<cudaEvent_t> done(L * nseg);
             for (int sg = 0; sg < nseg; ++sg) {
-                const int t0 = sg * dec_seg, tl = std::min(dec_seg, Dp.Tmax - t0);
+                const int t0 = sg * dec_seg, tl = seg_len(sg);
                 const long long r0 = Dp.off[t0], nr = Dp.off[t0 + tl] - r0;
                 for (int j = 0; j < L; ++j) {
                     cudaStream_t q = sw[j];
@@ -813,7 +817,7 @@ void Engine::program(int mode, bool apply_update) {
             for (int j = 0; j < L; ++j) CUDA_CHECK(cudaStreamWaitEvent(sw[j], fork, 0));
             std::vector<cudaEvent_t> done(L * nseg);
             for (int sg = nseg - 1; sg >= 0; --sg) {
-                const int t0 = sg * dec_seg, tl = std::min(dec_seg, Dp.Tmax - t0);
+                const int t0 = sg * dec_seg, tl = seg_len(sg);
                 const long long r0 = Dp.off[t0], nr = Dp.off[t0 + tl] - r0;
                 for (int j = L - 1; j >= 0; --j) {
                     cudaStream_t q = sw[j];

@@ -264,6 +264,7 @@ bool Engine::enc_segmented(const SeqPlan& E) const {
 // BPTT: the other way round.  Launch i of both chains run side by side.
 void Engine::enc_slice_plan(const SeqPlan& E, int nseg, bool bptt, std::vector<int>* want8) const {
     want8->assign((size_t)2 * nseg, 0);
+    const int cap = cfg.nranks > 1 ? 8 : 9;   // groups of 16 CTAs; data parallel leaves 20 SMs to the NCCL kernels of the overlapped buckets
     for (int i = 0; i < nseg; ++i) {
         int rows[2], g16[2], g8[2];
         for (int d = 0; d < 2; ++d) {
@@ -274,9 +275,9 @@ void Engine::enc_slice_plan(const SeqPlan& E, int nseg, bool bptt, std::vector<i
         }
         const int big = rows[0] >= rows[1] ? 0 : 1, small = 1 - big;
         int use8[2] = {0, 0};
-        if (g8[0] + g8[1] <= 9) use8[0] = use8[1] = 1;
-        else if (g8[big] + g16[small] <= 9) use8[big] = 1;
-        else if (g16[big] + g8[small] <= 9) use8[small] = 1;
+        if (g8[0] + g8[1] <= cap) use8[0] = use8[1] = 1;
+        else if (g8[big] + g16[small] <= cap) use8[big] = 1;
+        else if (g16[big] + g8[small] <= cap) use8[small] = 1;
         for (int d = 0; d < 2; ++d) (*want8)[(size_t)d * nseg + i] = use8[d] ? 1 : 2;   // 1 = 8-row slices, 2 = 16-row slices
     }
 }
@@ -631,7 +632,7 @@ void Engine::program(int mode, bool apply_update) {
     // 8-row slices first.  want8[j * nseg + sg] = 1 -> 8 rows per slice.
     std::vector<int> want8((size_t)L * nseg, 0);
     if (wave && !getenv("ARGSIM_NO_SLICE_BUDGET")) {
-        const int max_groups = 9;
+        const int max_groups = cfg.nranks > 1 ? 8 : 9;   // data parallel: leave 20 SMs to the NCCL kernels of the overlapped buckets
         for (int stage = 0; stage < nseg + L - 1; ++stage) {
             std::vector<std::pair<int, int>> items;   // (live rows, j)
             int total = 0;

@@ -31,6 +31,8 @@ struct XP {
     unsigned long long* gbuf;   // methods 0/1: [group][2][rows][256] LL words
     long long* out;             // [blocks][2]: cycles, checksum
     int rows, iters, method;
+    int* smids;                 // [blocks] scratch: grouping by physical SM id instead of block id (method + 16)
+    int active_groups;          // groups beyond this one exit at once (method + 32: grid padded to 8 groups = 128 CTAs)
 };
 
 __global__ void __launch_bounds__(XNT, 1) k_xbench(const XP P) {
@@ -40,7 +42,27 @@ __global__ void __launch_bounds__(XNT, 1) k_xbench(const XP P) {
     __shared__ __align__(8) unsigned long long bars[2];
     __shared__ uint32_t s_carry;
     const int tid = threadIdx.x;
-    const int grp = blockIdx.x / XCL, c = blockIdx.x % XCL;
+    int lb = blockIdx.x;
+    if (P.smids) {   // logical block id = rank of this CTA's SM id: the 16 CTAs of a group sit on neighbouring SMs
+        __shared__ int s_rank;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        if (tid == 0) P.smids[blockIdx.x] = (int)smid * 4096 + blockIdx.x;   // unique key, ordered by SM id
+        cooperative_groups::this_grid().sync();
+        if (tid == 0) {
+            const int mine = P.smids[blockIdx.x];
+            int r = 0;
+            for (int i = 0; i < (int)gridDim.x; ++i) r += (P.smids[i] < mine);
+            s_rank = r;
+        }
+        __syncthreads();
+        lb = s_rank;
+    }
+    const int grp = lb / XCL, c = lb % XCL;
+    if (grp >= P.active_groups) {   // padding CTA: only there to give the launch the 128-CTA placement
+        if (tid == 0) { P.out[lb * 2] = 0; P.out[lb * 2 + 1] = 0; }
+        return;
+    }
     const int rows = P.rows;
     const int wpr = XH / 2;                         // LL words per row
     const size_t par_words = (size_t)rows * wpr;
@@ -57,7 +79,7 @@ __global__ void __launch_bounds__(XNT, 1) k_xbench(const XP P) {
     if (cluster) {
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    } else {
+    } else if (P.active_groups * XCL == (int)gridDim.x) {
         cooperative_groups::this_grid().sync();
     }
     long long sum = 0;
@@ -145,8 +167,8 @@ __global__ void __launch_bounds__(XNT, 1) k_xbench(const XP P) {
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        P.out[blockIdx.x * 2] = t1 - t0;
-        P.out[blockIdx.x * 2 + 1] = sum;
+        P.out[lb * 2] = t1 - t0;
+        P.out[lb * 2 + 1] = sum;
     }
 }
 }  // namespace
@@ -156,12 +178,22 @@ __global__ void __launch_bounds__(XNT, 1) k_xbench(const XP P) {
 int xbench_run(int device, int method, int groups, int rows, int iters, double* cycles_per_iter, int* max_clusters) {
     CUDA_CHECK(cudaSetDevice(device));
     XP P;
+    const bool padded = method >= 32;    // methods 32 / 33: 0 / 1 in a grid padded to 8 groups (128 CTAs), `groups` of them active
+    if (padded) method -= 32;
+    const bool by_smid = method >= 16;   // methods 16 / 17: 0 / 1 with groups formed by physical SM id
+    if (by_smid) method -= 16;
     P.rows = rows; P.iters = iters; P.method = method;
-    const int blocks = groups * XCL;
+    P.smids = nullptr;
+    const int blocks = (padded ? std::max(groups, 8) : groups) * XCL;
+    P.active_groups = groups;
     const size_t gwords = (size_t)groups * 2 * rows * (XH / 2);
     CUDA_CHECK(cudaMalloc(&P.gbuf, gwords * 8));
     CUDA_CHECK(cudaMemset(P.gbuf, 0, gwords * 8));
     CUDA_CHECK(cudaMalloc(&P.out, blocks * 2 * sizeof(long long)));
+    if (by_smid) {
+        if (method >= 2) throw std::runtime_error("xbench: SM-id grouping is for the L2 methods");
+        CUDA_CHECK(cudaMalloc(&P.smids, blocks * sizeof(int)));
+    }
     const size_t smem = method == 2 ? (size_t)2 * rows * (XH / 2) * 8 : (method == 3 ? (size_t)2 * rows * 1024 : 16);
     CUDA_CHECK(cudaFuncSetAttribute(k_xbench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     *max_clusters = 0;
@@ -184,10 +216,10 @@ int xbench_run(int device, int method, int groups, int rows, int iters, double* 
     std::vector<long long> h(blocks * 2);
     CUDA_CHECK(cudaMemcpy(h.data(), P.out, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
     long long mx = 0;
-    for (int b = 0; b < blocks; ++b) mx = std::max(mx, h[b * 2]);
+    for (int b = 0; b < groups * XCL; ++b) mx = std::max(mx, h[b * 2]);
     for (int b = 1; b < XCL; ++b)
         if (h[b * 2 + 1] != h[1]) throw std::runtime_error("xbench: CTAs of a group disagree on the gathered data");
     *cycles_per_iter = (double)mx / iters;
-    cudaFree(P.gbuf); cudaFree(P.out);
+    cudaFree(P.gbuf); cudaFree(P.out); cudaFree(P.smids);
     return 0;
 }

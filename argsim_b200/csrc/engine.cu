@@ -52,6 +52,7 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     if (const char* ev = getenv("ARGSIM_DEC_SEG")) dec_seg = atoi(ev);
     if (const char* ev = getenv("ARGSIM_ENC_SEG")) enc_seg = atoi(ev);
     enc_seg_fwd = getenv("ARGSIM_ENC_SEG_FWD") != nullptr;
+    pad_wave = getenv("ARGSIM_GRU_PAD_WAVE") ? atoi(getenv("ARGSIM_GRU_PAD_WAVE")) : 2;
     if (L > 8) dec_seg = 0;
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_bucket, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
@@ -296,14 +297,14 @@ void Engine::gather_embed(const int* ids, long long n, const Mat& out) {
 void Engine::gru_fwd(GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact) {
     if (arena.dry) return;
     kbegin(ndir == 2 ? "k:gru_fwd_enc" : "k:gru_fwd_dec");
-    if (use_mma && gru_mma_fits(mma, ndir, P.b)) gru_mma_fwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0]);
+    if (use_mma && gru_mma_fits(mma, ndir, P.b)) gru_mma_fwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0], 0, -1, 0, 0, /*pad: runs alone*/ 1);
     else gru_generic_fwd(dirs, ndir, P, H, gru_work, st);
     kend();
 }
 void Engine::gru_bwd(GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact) {
     if (arena.dry) return;
     kbegin(ndir == 2 ? "k:gru_bwd_enc" : "k:gru_bwd_dec");
-    if (use_mma && gru_mma_fits(mma, ndir, P.b)) gru_mma_bwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0]);
+    if (use_mma && gru_mma_fits(mma, ndir, P.b)) gru_mma_bwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0], 0, -1, 0, 0, /*pad: runs alone*/ 1);
     else gru_generic_bwd(dirs, ndir, P, H, gru_work, st);
     kend();
 }
@@ -556,7 +557,7 @@ void Engine::program(int mode, bool apply_update) {
                         GruFwdArgs x = a[d];
                         x.h0 = (k > 0) ? hTe[d][(k - 1) & 1] : nullptr;
                         x.hT = (k + 1 < nsegE) ? hTe[d][k & 1] : nullptr;
-                        gru_mma_fwd(mma, &x, 1, E, dp.enc_off, dp.enc_nact, H, sw[d], t0, tl, d, want8[(size_t)d * nsegE + k]);
+                        gru_mma_fwd(mma, &x, 1, E, dp.enc_off, dp.enc_nact, H, sw[d], t0, tl, d, want8[(size_t)d * nsegE + k], pad_wave);
                     }
                 for (int d = 0; d < 2; ++d) {
                     cudaEvent_t ev = next_event();
@@ -689,7 +690,7 @@ void Engine::program(int mode, bool apply_update) {
                     GruFwdArgs a = dec_fwd_args(j);
                     if (sg > 0) a.h0 = hT[j][(sg - 1) & 1];
                     a.hT = (sg + 1 < nseg) ? hT[j][sg & 1] : nullptr;
-                    gru_mma_fwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j, want8[(size_t)j * nseg + sg]);
+                    gru_mma_fwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j, want8[(size_t)j * nseg + sg], pad_wave);
                     done[j * nseg + sg] = next_event();
                     CUDA_CHECK(cudaEventRecord(done[j * nseg + sg], q));
                 }
@@ -830,7 +831,7 @@ void Engine::program(int mode, bool apply_update) {
                     GruBwdArgs a = dec_bwd_args(j, dYl[j], dGXl[j], dGHl[j], HPl[j], dh0l[j]);
                     a.dh_in = (sg + 1 < nseg) ? carry[j][(sg + 1) & 1] : nullptr;
                     a.dh_out = (sg > 0) ? carry[j][sg & 1] : nullptr;
-                    gru_mma_bwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j, want8[(size_t)j * nseg + sg]);   // the reverse wavefront pairs the same (j, sg) launches
+                    gru_mma_bwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j, want8[(size_t)j * nseg + sg], pad_wave);   // the reverse wavefront pairs the same (j, sg) launches
                     done[j * nseg + sg] = next_event();
                     CUDA_CHECK(cudaEventRecord(done[j * nseg + sg], q));
                 }
@@ -981,7 +982,7 @@ void Engine::program(int mode, bool apply_update) {
                         GruBwdArgs x = a[d];
                         x.dh_in = (k > 0) ? carry[d][(k - 1) & 1] : nullptr;
                         x.dh_out = (k + 1 < nsegE) ? carry[d][k & 1] : nullptr;
-                        gru_mma_bwd(mma, &x, 1, E, dp.enc_off, dp.enc_nact, H, sw[d], t0, tl, d, want8[(size_t)d * nsegE + k]);
+                        gru_mma_bwd(mma, &x, 1, E, dp.enc_off, dp.enc_nact, H, sw[d], t0, tl, d, want8[(size_t)d * nsegE + k], pad_wave);
                     }
                 for (int d = 0; d < 2; ++d) {
                     cudaEvent_t ev = next_event();

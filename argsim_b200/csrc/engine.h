@@ -92,6 +92,7 @@ private:
     cudaEvent_t next_event();
     int dec_seg = 64;                                   // time steps per wavefront segment (0 = off)
     int enc_seg = 171;                                  // encoder BPTT: time steps per (direction, segment) launch (0 = one launch per layer)
+    int pad_wave = 0;                                   // 2: concurrent segment launches are padded to 128 blocks (plain launch), 0: not
     bool enc_seg_fwd = false;                           // measured: the forward pass is faster as one launch per layer (2.39 vs 2.56 ms), BPTT is not
     bool enc_segmented(const SeqPlan& E) const;
     void enc_slice_plan(const SeqPlan& E, int nseg, bool bptt, std::vector<int>* want8) const;

@@ -410,6 +410,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd2(const __grid_constant__
     int* s_nact = reinterpret_cast<int*>(hst + (size_t)P.bslr * UN);   // [Tseg+2] step tables
     int* s_off = s_nact + P.Tseg + 2;
     float* gxs = reinterpret_cast<float*>(s_off + P.Tseg + 2);         // [2][CH][3][UN] next step's gx of chunk 0 (cp.async)
+    if ((int)(blockIdx.x / CL) >= P.ndir * P.nslices) return;          // padding CTA: only there for the 128-block placement
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < P.Tseg + 2; i += NTH) {
         const int tt = P.t0 - 1 + i;
@@ -696,6 +697,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
     // double buffered by step parity: their HBM latency is paid one step ahead, off the serial chain
     float* stg = reinterpret_cast<float*>(s_off + P.Tseg + 2);   // [2][CH][5][UN]
     bf16* stgh = reinterpret_cast<bf16*>(stg + 2 * CH * 5 * UN);                            // [2][CH][UN]
+    if ((int)(blockIdx.x / CL) >= P.ndir * P.nslices) return;          // padding CTA: only there for the 128-block placement
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < P.Tseg + 2; i += NTH) {
         const int tt = P.t0 - 1 + i;
@@ -1010,6 +1012,9 @@ struct GruMmaCtx {
     bool attr_set = false;
     int variant_fwd = 2, variant_bwd = 3;   // bit 1: L2 prefetch two steps ahead by idle warps; bwd bit 0: cp.async staging
     int fwd2_opt = 0;
+    int pad_groups = 8;          // launches that have the chip to themselves are padded to 8 groups = 128 blocks: the block
+                                 // dispatcher spreads a 128-block grid over all GPCs (2 CTAs of a group per GPC), a small grid
+                                 // is packed into one or two GPCs and its exchange round is ~27 % slower (xbench, profiles/)
     bool fwd_v1 = false;         // ARGSIM_GRU_FWD_V1=1: the first forward kernel (smem-staged operands), for A/B runs
     long long* prof = nullptr;   // ARGSIM_GRU_PROF=1: per-phase clocks, printed to stderr after every launch
 };
@@ -1030,6 +1035,7 @@ GruMmaCtx* gru_mma_create(int device) {
         if (const char* v = getenv("ARGSIM_GRU_FWD2_OPT")) c->fwd2_opt = atoi(v);
     }
     c->fwd_v1 = getenv("ARGSIM_GRU_FWD_V1") != nullptr;
+    if (const char* v = getenv("ARGSIM_GRU_PAD")) c->pad_groups = atoi(v);
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH * GS_LD * 2 + MAX_BSL * UN * 4 + 2 * 4100 * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2));
     if (const char* v = getenv("ARGSIM_GRU_VARIANT")) { c->variant_fwd = atoi(v) & 7; c->variant_bwd = (atoi(v) >> 3) & 7; }
     if (const char* v = getenv("ARGSIM_GRU_FWD2_VARIANT")) c->variant_fwd = atoi(v);
@@ -1084,7 +1090,7 @@ bool gru_mma_fits(const GruMmaCtx* c, int ndir, int b) {
 // One launch = steps [t0, t0+Tseg) of the plan (Tseg < 0: all).  `slot` selects the LL exchange buffer: launches
 // that may run CONCURRENTLY (decoder wavefront: one stream per layer) must use different slots.
 void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& Pl, const int* d_off, const int* d_nact, int H,
-                 cudaStream_t s, int t0, int Tseg, int slot, int alone) {
+                 cudaStream_t s, int t0, int Tseg, int slot, int alone, int pad) {
     if (H != HH) throw std::runtime_error("gru_mma: H must be 512");
     if (Tseg < 0) { t0 = 0; Tseg = Pl.Tmax; }
     if (Tseg >= 4096) throw std::runtime_error("gru_mma: more than 4095 steps per launch");
@@ -1125,13 +1131,21 @@ void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& 
     void* args[] = {&P};
     void* fwd2_fn = c->fwd2_opt == 2 ? (void*)k_gru_mma_fwd2<2> : c->fwd2_opt == 12 ? (void*)k_gru_mma_fwd2<12>
                   : c->fwd2_opt == 16 ? (void*)k_gru_mma_fwd2<16> : (void*)k_gru_mma_fwd2<0>;
-    CUDA_CHECK(cudaLaunchCooperativeKernel(c->fwd_v1 ? (void*)k_gru_mma_fwd : fwd2_fn, dim3(groups * CL), dim3(NTH), args, smem, s));
+    const int grid_groups = (!c->fwd_v1 && pad) ? std::max(groups, c->pad_groups) : groups;
+    if (pad == 2 && !c->fwd_v1) {
+        // padded launch next to other recurrence launches (wavefront / segment chains): a cooperative launch would wait for
+        // 128 free SMs.  A plain launch is safe because the padding blocks exit at once and the caller's slice budget keeps
+        // the ACTIVE blocks of all launches that can be in flight together within the SM count (1 CTA per SM): every
+        // active block gets an SM without anybody having to finish first.
+        CUDA_CHECK(cudaLaunchKernel(fwd2_fn, dim3(grid_groups * CL), dim3(NTH), args, smem, s));
+    } else
+    CUDA_CHECK(cudaLaunchCooperativeKernel(c->fwd_v1 ? (void*)k_gru_mma_fwd : fwd2_fn, dim3(grid_groups * CL), dim3(NTH), args, smem, s));
     COUNT_LAUNCH();
     dump_prof(c, ndir == 2 ? "fwd_enc" : "fwd_dec", groups * CL, Tseg, s);
 }
 
 void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& Pl, const int* d_off, const int* d_nact, int H,
-                 cudaStream_t s, int t0, int Tseg, int slot, int alone) {
+                 cudaStream_t s, int t0, int Tseg, int slot, int alone, int pad) {
     if (H != HH) throw std::runtime_error("gru_mma: H must be 512");
     if (Tseg < 0) { t0 = 0; Tseg = Pl.Tmax; }
     if (Tseg >= 4096) throw std::runtime_error("gru_mma: more than 4095 steps per launch");
@@ -1166,7 +1180,10 @@ void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& 
     if (c->launch_id >= (1u << 20)) c->launch_id = 1;
     const size_t smem = (size_t)2 * CH * GS_LD * 2 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2;
     void* args[] = {&P};
-    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gru_mma_bwd, dim3(groups * CL), dim3(NTH), args, smem, s));
+    const int grid_groups = pad ? std::max(groups, c->pad_groups) : groups;
+    if (pad == 2) CUDA_CHECK(cudaLaunchKernel((void*)k_gru_mma_bwd, dim3(grid_groups * CL), dim3(NTH), args, smem, s));   // see gru_mma_fwd
+    else
+    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gru_mma_bwd, dim3(grid_groups * CL), dim3(NTH), args, smem, s));
     COUNT_LAUNCH();
     dump_prof(c, ndir == 2 ? "bwd_enc" : "bwd_dec", groups * CL, Tseg, s);
 }

@@ -33,6 +33,7 @@ struct XP {
     int rows, iters, method;
     int* smids;                 // [blocks] scratch: grouping by physical SM id instead of block id (method + 16)
     int active_groups;          // groups beyond this one exit at once (method + 32: grid padded to 8 groups = 128 CTAs)
+    int skip_blocks;            // the first blocks of the grid exit at once (method + 64: 6 = keep the groups off SMs 142-147)
 };
 
 __global__ void __launch_bounds__(XNT, 1) k_xbench(const XP P) {
@@ -42,7 +43,8 @@ __global__ void __launch_bounds__(XNT, 1) k_xbench(const XP P) {
     __shared__ __align__(8) unsigned long long bars[2];
     __shared__ uint32_t s_carry;
     const int tid = threadIdx.x;
-    int lb = blockIdx.x;
+    int lb = (int)blockIdx.x - P.skip_blocks;
+    if (lb < 0) return;
     if (P.smids) {   // logical block id = rank of this CTA's SM id: the 16 CTAs of a group sit on neighbouring SMs
         __shared__ int s_rank;
         unsigned smid;
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(XNT, 1) k_xbench(const XP P) {
     if (cluster) {
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    } else if (P.active_groups * XCL == (int)gridDim.x) {
+    } else if (P.active_groups * XCL == (int)gridDim.x && P.skip_blocks == 0) {
         cooperative_groups::this_grid().sync();
     }
     long long sum = 0;
@@ -178,14 +180,17 @@ __global__ void __launch_bounds__(XNT, 1) k_xbench(const XP P) {
 int xbench_run(int device, int method, int groups, int rows, int iters, double* cycles_per_iter, int* max_clusters) {
     CUDA_CHECK(cudaSetDevice(device));
     XP P;
+    const bool skip6 = method >= 64;     // methods 64+: additionally 6 leading padding blocks (they land on the 6-SM GPC)
+    if (skip6) method -= 64;
     const bool padded = method >= 32;    // methods 32 / 33: 0 / 1 in a grid padded to 8 groups (128 CTAs), `groups` of them active
     if (padded) method -= 32;
     const bool by_smid = method >= 16;   // methods 16 / 17: 0 / 1 with groups formed by physical SM id
     if (by_smid) method -= 16;
     P.rows = rows; P.iters = iters; P.method = method;
     P.smids = nullptr;
-    const int blocks = (padded ? std::max(groups, 8) : groups) * XCL;
+    const int blocks = (padded ? std::max(groups, 8) : groups) * XCL + (skip6 ? 6 : 0);
     P.active_groups = groups;
+    P.skip_blocks = skip6 ? 6 : 0;
     const size_t gwords = (size_t)groups * 2 * rows * (XH / 2);
     CUDA_CHECK(cudaMalloc(&P.gbuf, gwords * 8));
     CUDA_CHECK(cudaMemset(P.gbuf, 0, gwords * 8));

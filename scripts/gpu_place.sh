@@ -1,5 +1,5 @@
 #!/bin/bash
-./scripts/bin/smid_probe | cut -c1-400
+nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o /tmp/smid_probe scripts/smid_probe.cu && /tmp/smid_probe | cut -c1-400
 python - <<'PY'
 import sys, os
 sys.path.insert(0, os.getcwd())

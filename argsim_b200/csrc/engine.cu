@@ -47,8 +47,15 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
         if (!gemm_tc_available()) throw std::runtime_error("BF16 precision needs the tcgen05 GEMM path (sm_100a device + driver TMA entry point)");
     }
     use_mma = is_bf16 && gru_mma_supported(H) && !(c.flags & 4);
-    for (auto& s : st) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    for (auto& s : sw) CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    // the serial chain (main stream, recurrence chains) outranks the side stream that carries the weight-gradient GEMMs:
+    // when an SM frees up, a waiting recurrence block gets it before a GEMM tile does
+    int prio_least = 0, prio_greatest = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    if (const char* ev = getenv("ARGSIM_WGRAD_OVERLAP")) wgrad_overlap = atoi(ev);
+    const int prio_chain = wgrad_overlap ? prio_greatest : prio_least;
+    for (int i = 0; i < 3; ++i) CUDA_CHECK(cudaStreamCreateWithPriority(&st[i], cudaStreamNonBlocking, i == 2 ? prio_least : prio_chain));
+    for (auto& s : sw) CUDA_CHECK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_chain));
+    CUDA_CHECK(cudaStreamCreateWithPriority(&swg, cudaStreamNonBlocking, prio_least));
     if (const char* ev = getenv("ARGSIM_DEC_SEG")) dec_seg = atoi(ev);
     if (const char* ev = getenv("ARGSIM_ENC_SEG")) enc_seg = atoi(ev);
     enc_seg_fwd = getenv("ARGSIM_ENC_SEG_FWD") != nullptr;
@@ -139,6 +146,7 @@ Engine::~Engine() {
     cudaEventDestroy(ev_bucket); cudaEventDestroy(ev_comm);
     for (auto& s : st) if (s) cudaStreamDestroy(s);
     for (auto& s : sw) if (s) cudaStreamDestroy(s);
+    if (swg) cudaStreamDestroy(swg);
     for (auto& e : evpool) cudaEventDestroy(e);
 }
 
@@ -283,10 +291,11 @@ void Engine::enc_slice_plan(const SeqPlan& E, int nseg, bool bptt, std::vector<i
     }
 }
 
-void Engine::colsum(const Mat& A, long long rows, int cols, float* out, int accumulate) {
+void Engine::colsum(const Mat& A, long long rows, int cols, float* out, int accumulate, cudaStream_t q) {
     if (arena.dry) return;
-    if (A.f) launch_colsum_f32(A.f, A.ld, rows, cols, out, st[0], accumulate);
-    else launch_colsum_bf16(A.h, A.ld, rows, cols, out, st[0], accumulate);
+    if (!q) q = st[0];
+    if (A.f) launch_colsum_f32(A.f, A.ld, rows, cols, out, q, accumulate);
+    else launch_colsum_bf16(A.h, A.ld, rows, cols, out, q, accumulate);
 }
 void Engine::gather_embed(const int* ids, long long n, const Mat& out) {
     if (arena.dry) return;
@@ -309,10 +318,10 @@ void Engine::gru_bwd(GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_
     kend();
 }
 
-void Engine::allreduce_bucket(size_t off0, size_t off1) {
+void Engine::allreduce_bucket(size_t off0, size_t off1, cudaStream_t after) {
     if (arena.dry || cfg.nranks <= 1 || off1 <= off0) return;
     NcclApi& n = NcclApi::get();
-    CUDA_CHECK(cudaEventRecord(ev_bucket, st[0]));
+    CUDA_CHECK(cudaEventRecord(ev_bucket, after ? after : st[0]));
     CUDA_CHECK(cudaStreamWaitEvent(st[2], ev_bucket, 0));
     n.check(n.AllReduce(g + off0, g + off0, off1 - off0, NcclApi::Float32, NcclApi::Sum, (NcclApi::comm_t)nccl_comm, st[2]),
             "ncclAllReduce");
@@ -779,12 +788,21 @@ void Engine::program(int mode, bool apply_update) {
         a.reverse = 0;
         return a;
     };
-    auto dec_wgrad = [&](int j, const Mat& dGX, const Mat& dGH, const Mat& HP) {
+    auto dec_wgrad = [&](int j, const Mat& dGX, const Mat& dGH, const Mat& HP, cudaStream_t q = nullptr) {
         const std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
-        gemm(dGX, 1, decY[j], 1, gmat(pre + "W"), 3 * H, D, N, 1.f, nullptr, 1);
-        gemm(dGH, 1, HP, 1, gmat(pre + "R"), 3 * H, H, N, 1.f, nullptr, 1);
-        colsum(dGX, N, 3 * H, gptr(pre + "bW"));
-        colsum(dGH, N, 3 * H, gptr(pre + "bR"));
+        gemm(dGX, 1, decY[j], 1, gmat(pre + "W"), 3 * H, D, N, 1.f, nullptr, 1, q);
+        gemm(dGH, 1, HP, 1, gmat(pre + "R"), 3 * H, H, N, 1.f, nullptr, 1, q);
+        colsum(dGX, N, 3 * H, gptr(pre + "bW"), 0, q);
+        colsum(dGH, N, 3 * H, gptr(pre + "bR"), 0, q);
+    };
+    // Weight gradients are not on the serial chain: with the persistent recurrence in use they go to the low-priority
+    // side stream and fill the SMs the recurrence launches of the layers below leave free (a third of the encoder's
+    // BPTT runs on 4 of its 9 groups); the all-reduce bucket of a layer is then ordered after the side stream.
+    const bool side = wgrad_overlap && use_mma && !arena.dry;
+    auto side_after_main = [&]() {
+        cudaEvent_t ev = next_event();
+        CUDA_CHECK(cudaEventRecord(ev, s));
+        CUDA_CHECK(cudaStreamWaitEvent(swg, ev, 0));
     };
     if (!wave) {
         Mat dGX = act(N, 3 * H), dGH = act(N, 3 * H), HP = act(N, H);
@@ -839,12 +857,13 @@ void Engine::program(int mode, bool apply_update) {
             for (int j = 0; j < L; ++j) CUDA_CHECK(cudaStreamWaitEvent(s, done[j * nseg + 0], 0));
             kend();
         }
+        if (side) side_after_main();   // the wavefront has joined the main stream: dGX/dGH/HP of all layers are final
         for (int j = L - 1; j >= 0; --j) {
             const std::string pre = "decode/rnn/l" + std::to_string(j) + "/";
-            dec_wgrad(j, dGXl[j], dGHl[j], HPl[j]);
+            dec_wgrad(j, dGXl[j], dGHl[j], HPl[j], side ? swg : nullptr);
             RUN(launch_row_scatter(dh0l[j], H, dhx_sorted.f, H, nullptr, b, H, 1, s));
             const size_t end = pinfo(pre + "bR").off + align_up(3 * H, 64);
-            allreduce_bucket(bucket_lo, end);
+            allreduce_bucket(bucket_lo, end, side ? swg : nullptr);
             bucket_lo = end;
         }
         gemm(dGXl[0], 0, pmat("decode/rnn/l0/W"), 1, dYn, N, D, 3 * H, 1.f, nullptr, 0);
@@ -884,8 +903,14 @@ void Engine::program(int mode, bool apply_update) {
     Mat dHS = f32(S, 2 * H), dHSn = f32(S, 2 * H);
     RUN(CUDA_CHECK(cudaMemsetAsync(dHS.f, 0, sizeof(float) * S * 2 * H, s)));
     if (enc_kind == 0) RUN(launch_row_scatter(dhenc.f, 2 * H, dHS.f, 2 * H, dp.enc_last, b, 2 * H, 0, s));
-    Mat dGXe = act(S, 6 * H), dGHe = act(S, 6 * H), HPe = act(S, 2 * H);
+    Mat dGXe1 = act(S, 6 * H), dGHe1 = act(S, 6 * H), HPe1 = act(S, 2 * H);
+    // second set of gate-gradient buffers: layer i's weight-gradient GEMMs read one set on the side stream while layer
+    // i-1's recurrence fills the other
+    const bool side_enc = wgrad_overlap && use_mma && enc_kind == 0;
+    Mat dGXe2 = side_enc ? act(S, 6 * H) : dGXe1, dGHe2 = side_enc ? act(S, 6 * H) : dGHe1, HPe2 = side_enc ? act(S, 2 * H) : HPe1;
+    cudaEvent_t set_free[2] = {nullptr, nullptr};   // side stream done with the set (two layers ago)
     if (enc_kind != 0) {
+        const Mat &dGXe = dGXe1, &dGHe = dGHe1, &HPe = HPe1;
         // BPTT through the independent stack(s): the top layer reads its slice of d hs, lower layers their own dX
         Mat dTop(dHS.f, nullptr, S, EH, EH);
         RUN(launch_row_scatter(dhenc.f, EH, dTop.f, EH, dp.enc_last, b, EH, 0, s));
@@ -937,6 +962,11 @@ void Engine::program(int mode, bool apply_update) {
     for (int i = L - 1; i >= 0 && enc_kind == 0; --i) {
         const int in = (i == 0) ? D : 2 * H;
         const std::string pre = "encode/rnn" + std::to_string(i + 1) + "/";
+        const int set = side_enc ? ((L - 1 - i) & 1) : 0;
+        const Mat& dGXe = set ? dGXe2 : dGXe1;
+        const Mat& dGHe = set ? dGHe2 : dGHe1;
+        const Mat& HPe = set ? HPe2 : HPe1;
+        if (side && set_free[set]) CUDA_CHECK(cudaStreamWaitEvent(s, set_free[set], 0));
         GruBwdArgs a[2];
         for (int d = 0; d < 2; ++d) {
             const std::string pd = pre + (d ? "bwd/" : "fwd/");
@@ -994,23 +1024,40 @@ void Engine::program(int mode, bool apply_update) {
         } else {
             gru_bwd(a, 2, E, dp.enc_off, dp.enc_nact);
         }
-        Mat gW = gmat(pre + "fwd/W");
-        gW.rows = 6 * H;
-        gemm(dGXe, 1, encX[i], 1, gW, 6 * H, in, S, 1.f, nullptr, 1);
-        for (int d = 0; d < 2; ++d) {
-            const std::string pd = pre + (d ? "bwd/" : "fwd/");
-            gemm(dGHe.colslice(d * 3 * H, 3 * H), 1, HPe.colslice(d * H, H), 1, gmat(pd + "R"), 3 * H, H, S, 1.f, nullptr, 1);
-        }
-        colsum(dGXe, S, 6 * H, gptr(pre + "fwd/bW"));   // fwd/bW and bwd/bW are adjacent
-        colsum(dGHe, S, 6 * H, gptr(pre + "fwd/bR"));
+        // the layer below waits for d x only; with the side stream the weight gradients follow behind it. The last
+        // layer's have nothing left to hide behind and stay on the main stream.
+        const bool on_side = side && side_enc && i > 0;
+        cudaStream_t qw = on_side ? swg : nullptr;
         Mat W = pmat(pre + "fwd/W");
         W.rows = 6 * H;
         Mat dX(dHSn.f, nullptr, S, in, in);
-        gemm(dGXe, 0, W, 1, dX, S, in, 6 * H, 1.f, nullptr, 0);
+        if (on_side) {
+            side_after_main();   // the recurrence has joined the main stream
+            gemm(dGXe, 0, W, 1, dX, S, in, 6 * H, 1.f, nullptr, 0);
+        }
+        Mat gW = gmat(pre + "fwd/W");
+        gW.rows = 6 * H;
+        gemm(dGXe, 1, encX[i], 1, gW, 6 * H, in, S, 1.f, nullptr, 1, qw);
+        for (int d = 0; d < 2; ++d) {
+            const std::string pd = pre + (d ? "bwd/" : "fwd/");
+            gemm(dGHe.colslice(d * 3 * H, 3 * H), 1, HPe.colslice(d * H, H), 1, gmat(pd + "R"), 3 * H, H, S, 1.f, nullptr, 1, qw);
+        }
+        colsum(dGXe, S, 6 * H, gptr(pre + "fwd/bW"), 0, qw);   // fwd/bW and bwd/bW are adjacent
+        colsum(dGHe, S, 6 * H, gptr(pre + "fwd/bR"), 0, qw);
+        if (!on_side) gemm(dGXe, 0, W, 1, dX, S, in, 6 * H, 1.f, nullptr, 0);
         std::swap(dHS, dHSn);
+        if (on_side) {
+            set_free[set] = next_event();
+            CUDA_CHECK(cudaEventRecord(set_free[set], swg));
+        }
         const size_t end = pinfo(pre + "bwd/bR").off + align_up(3 * H, 64);
-        allreduce_bucket(bucket_lo, end);
+        allreduce_bucket(bucket_lo, end, qw);
         bucket_lo = end;
+    }
+    if (side) {   // everything the side stream produced is a gradient: Adam and the last bucket come after it
+        cudaEvent_t ev = next_event();
+        CUDA_CHECK(cudaEventRecord(ev, swg));
+        CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));
     }
     // d emb_src -> IndexedSlices part of dE (model.py:112); dHS now holds (S,D) with ld D
     RUN(launch_embed_scatter_add(dp.ids_src, S, dHS.f, D, D, gE.f, s));

@@ -87,6 +87,9 @@ public:
 private:
     cudaStream_t st[3] = {nullptr, nullptr, nullptr};  // main, second GRU direction, comm
     cudaStream_t sw[8] = {};                            // decoder wavefront: one stream per layer
+    cudaStream_t swg = nullptr;                         // lowest-priority side stream: weight-gradient GEMMs and bias column sums
+                                                        // run on the SMs the recurrence launches of the layer below leave free
+    int wgrad_overlap = 1;                              // ARGSIM_WGRAD_OVERLAP=0: weight gradients on the main stream, in line
     std::vector<cudaEvent_t> evpool;
     size_t evcount = 0;
     cudaEvent_t next_event();
@@ -166,11 +169,11 @@ private:
     Mat both(long long rows, int cols);
     void gemm(const Mat& A, int a_mn, const Mat& B, int b_mn, const Mat& C, long long M, int N, long long K, float alpha,
               const float* bias, int accumulate, cudaStream_t q = nullptr);
-    void colsum(const Mat& A, long long rows, int cols, float* out, int accumulate = 0);
+    void colsum(const Mat& A, long long rows, int cols, float* out, int accumulate = 0, cudaStream_t q = nullptr);
     void gather_embed(const int* ids, long long n, const Mat& out);
     void gru_fwd(GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact);
     void gru_bwd(GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact);
-    void allreduce_bucket(size_t off0, size_t off1);
+    void allreduce_bucket(size_t off0, size_t off1, cudaStream_t after = nullptr);   // after: the stream whose work produced the bucket (default main)
     float* gru_work = nullptr;
     size_t gru_work_cap = 0;
     size_t bucket_lo = 0;  // grads below this offset are already reduced

@@ -722,7 +722,21 @@ void Engine::program(int mode, bool apply_update) {
     long long chunk = use_tc ? 4096 : 2048;
     if (const char* ev = getenv("ARGSIM_LOGIT_CHUNK")) chunk = std::max(128, atoi(ev));
     chunk = std::min<long long>(chunk, std::max<long long>(N, 1));
-    Mat logits = act(chunk, V);
+    // Weight gradients are not on the serial chain: with the persistent recurrence in use they go to the low-priority
+    // side stream and fill the SMs the recurrence launches of the layers below leave free (a third of the encoder's
+    // BPTT runs on 4 of its 9 groups); the all-reduce bucket of a layer is then ordered after the side stream.
+    const bool side_on = wgrad_overlap && use_mma && train;
+    const bool side = side_on && !arena.dry;
+    auto side_after_main = [&]() {
+        cudaEvent_t ev = next_event();
+        CUDA_CHECK(cudaEventRecord(ev, s));
+        CUDA_CHECK(cudaStreamWaitEvent(swg, ev, 0));
+    };
+    // with the side stream every chunk keeps its own d logits until its weight-gradient GEMM has read it (<= 4 GB)
+    const long long nchunk = (N + chunk - 1) / chunk;
+    const bool side_logits = side_on && (double)nchunk * chunk * V * 2 <= 4e9;
+    std::vector<Mat> lbuf(side_logits ? nchunk : 1);
+    for (auto& m : lbuf) m = act(chunk, V);
     Mat dHO = train ? act(N, D) : Mat();
     Mat Emb = pmat("embed/embedding");
     Mat gE = gmat("embed/embedding");
@@ -730,6 +744,8 @@ void Engine::program(int mode, bool apply_update) {
     Mat gKl = tied ? Mat() : gmat("logits/dense/kernel");
     for (long long r0 = 0; r0 < N; r0 += chunk) {
         const long long nr = std::min(chunk, N - r0);
+        const Mat& logits = lbuf[side_logits ? r0 / chunk : 0];
+        cudaStream_t qw = (side && side_logits) ? swg : nullptr;
         RUN(kbegin("k:logits_gemm"));
         if (tied) gemm(HO.rowslice(r0, nr), 0, Emb, 0, logits, nr, V, D, scale, nullptr, 0);
         else gemm(HO.rowslice(r0, nr), 0, Kl, 1, logits, nr, V, D, 1.f, p + pinfo("logits/dense/bias").off, 0);   // h.K + b, K is (in,out)
@@ -744,14 +760,15 @@ void Engine::program(int mode, bool apply_update) {
         RUN(kend());
         if (train) {
             // dE (dense part) += D^-1/2 * dlogits^T . ho ;  dho = D^-1/2 * dlogits . E
-            RUN(kbegin("k:logits_wgrad"));
+            if (qw) side_after_main();   // d logits of this chunk are final
+            RUN(kbegin("k:logits_wgrad", qw));
             if (tied) {
-                gemm(logits, 1, HO.rowslice(r0, nr), 1, gE, V, D, nr, scale, nullptr, 1);
+                gemm(logits, 1, HO.rowslice(r0, nr), 1, gE, V, D, nr, scale, nullptr, 1, qw);
             } else {   // dK += ho^T . dlogits ; db += column sums of dlogits
-                gemm(HO.rowslice(r0, nr), 1, logits, 1, gKl, D, V, nr, 1.f, nullptr, 1);
-                colsum(logits, nr, V, gptr("logits/dense/bias"), 1);
+                gemm(HO.rowslice(r0, nr), 1, logits, 1, gKl, D, V, nr, 1.f, nullptr, 1, qw);
+                colsum(logits, nr, V, gptr("logits/dense/bias"), 1, qw);
             }
-            RUN(kend());
+            RUN(kend(qw));
             RUN(kbegin("k:logits_dgrad"));
             if (tied) gemm(logits, 0, Emb, 1, dHO.rowslice(r0, nr), nr, D, V, scale, nullptr, 0);
             else gemm(logits, 0, Kl, 0, dHO.rowslice(r0, nr), nr, D, V, 1.f, nullptr, 0);   // dho = dlogits . K^T
@@ -762,11 +779,15 @@ void Engine::program(int mode, bool apply_update) {
     if (!train) return;
 
     // ---------------- backward: out affine
-    gemm(decY[L], 1, dHO, 1, gmat("decode/out/kernel"), D, D, N, 1.f, nullptr, 1);
-    colsum(dHO, N, D, gptr("decode/out/bias"));
     Mat dY = f32(N, D);   // H == D (model.py:160: the decoder GRUs are dim_emb wide)
-    gemm(dHO, 0, pmat("decode/out/kernel"), 0, dY, N, D, D, 1.f, nullptr, 0);
-    allreduce_bucket(bucket_lo, pinfo("decode/out/bias").off + align_up(D, 64));
+    if (side) {
+        side_after_main();
+        gemm(dHO, 0, pmat("decode/out/kernel"), 0, dY, N, D, D, 1.f, nullptr, 0);
+    }
+    gemm(decY[L], 1, dHO, 1, gmat("decode/out/kernel"), D, D, N, 1.f, nullptr, 1, side ? swg : nullptr);
+    colsum(dHO, N, D, gptr("decode/out/bias"), 0, side ? swg : nullptr);
+    if (!side) gemm(dHO, 0, pmat("decode/out/kernel"), 0, dY, N, D, D, 1.f, nullptr, 0);
+    allreduce_bucket(bucket_lo, pinfo("decode/out/bias").off + align_up(D, 64), side ? swg : nullptr);
     bucket_lo = pinfo("decode/out/bias").off + align_up(D, 64);
 
     // ---------------- backward: decoder GRUs (BPTT), dh0 of all layers sums into d ex(z)
@@ -795,15 +816,7 @@ void Engine::program(int mode, bool apply_update) {
         colsum(dGX, N, 3 * H, gptr(pre + "bW"), 0, q);
         colsum(dGH, N, 3 * H, gptr(pre + "bR"), 0, q);
     };
-    // Weight gradients are not on the serial chain: with the persistent recurrence in use they go to the low-priority
-    // side stream and fill the SMs the recurrence launches of the layers below leave free (a third of the encoder's
-    // BPTT runs on 4 of its 9 groups); the all-reduce bucket of a layer is then ordered after the side stream.
-    const bool side = wgrad_overlap && use_mma && !arena.dry;
-    auto side_after_main = [&]() {
-        cudaEvent_t ev = next_event();
-        CUDA_CHECK(cudaEventRecord(ev, s));
-        CUDA_CHECK(cudaStreamWaitEvent(swg, ev, 0));
-    };
+
     if (!wave) {
         Mat dGX = act(N, 3 * H), dGH = act(N, 3 * H), HP = act(N, H);
         for (int j = L - 1; j >= 0; --j) {
@@ -876,25 +889,25 @@ void Engine::program(int mode, bool apply_update) {
     // ---------------- backward: latent
     Mat dhx = both(b, D);
     RUN(launch_row_gather(dhx_sorted.f, nullptr, H, nullptr, dhx.f, dhx.h, D, dp.dec_perm, b, H, s));
-    gemm(z, 1, dhx, 1, gmat("latent/ex/kernel"), R, D, b, 1.f, nullptr, 1);
-    colsum(dhx, b, D, gptr("latent/ex/bias"));
     Mat dz = f32(b, R);
     gemm(dhx, 0, pmat("latent/ex/kernel"), 0, dz, b, R, D, 1.f, nullptr, 0);
     Mat dmulv = both(b, 2 * R);
     RUN(launch_latent_bwd(dz.f, mulv.f, eps_used, b, R, 1, anneal / ((float)b_glob * (float)R), dmulv.f, dmulv.h, s));
-    gemm(henc, 1, dmulv.colslice(0, R), 1, gmat("latent/mu/kernel"), EH, R, b, 1.f, nullptr, 1);
-    gemm(henc, 1, dmulv.colslice(R, R), 1, gmat("latent/lv/kernel"), EH, R, b, 1.f, nullptr, 1);
-    {
-        Mat a_mu(dmulv.f, nullptr, b, R, 2 * R), a_lv(dmulv.f + R, nullptr, b, R, 2 * R);
-        colsum(a_mu, b, R, gptr("latent/mu/bias"));
-        colsum(a_lv, b, R, gptr("latent/lv/bias"));
-    }
     Mat dhenc = f32(b, EH);
-    gemm(dmulv.colslice(0, R), 0, pmat("latent/mu/kernel"), 0, dhenc, b, EH, R, 1.f, nullptr, 0);
-    gemm(dmulv.colslice(R, R), 0, pmat("latent/lv/kernel"), 0, dhenc, b, EH, R, 1.f, nullptr, 1);
-    {
+    {   // the three affines' weight / bias gradients: behind the chain (side stream) when it is in use
+        cudaStream_t qw = side ? swg : nullptr;
+        if (side) side_after_main();
+        gemm(z, 1, dhx, 1, gmat("latent/ex/kernel"), R, D, b, 1.f, nullptr, 1, qw);
+        colsum(dhx, b, D, gptr("latent/ex/bias"), 0, qw);
+        gemm(henc, 1, dmulv.colslice(0, R), 1, gmat("latent/mu/kernel"), EH, R, b, 1.f, nullptr, 1, qw);
+        gemm(henc, 1, dmulv.colslice(R, R), 1, gmat("latent/lv/kernel"), EH, R, b, 1.f, nullptr, 1, qw);
+        Mat a_mu(dmulv.f, nullptr, b, R, 2 * R), a_lv(dmulv.f + R, nullptr, b, R, 2 * R);
+        colsum(a_mu, b, R, gptr("latent/mu/bias"), 0, qw);
+        colsum(a_lv, b, R, gptr("latent/lv/bias"), 0, qw);
+        gemm(dmulv.colslice(0, R), 0, pmat("latent/mu/kernel"), 0, dhenc, b, EH, R, 1.f, nullptr, 0);
+        gemm(dmulv.colslice(R, R), 0, pmat("latent/lv/kernel"), 0, dhenc, b, EH, R, 1.f, nullptr, 1);
         const size_t end = pinfo("latent/lv/bias").off + align_up(R, 64);
-        allreduce_bucket(bucket_lo, end);
+        allreduce_bucket(bucket_lo, end, qw);
         bucket_lo = end;
     }
     phase("latent_bwd");

@@ -52,6 +52,7 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     int prio_least = 0, prio_greatest = 0;
     CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
     if (const char* ev = getenv("ARGSIM_WGRAD_OVERLAP")) wgrad_overlap = atoi(ev);
+    if (const char* ev = getenv("ARGSIM_GROUP_CAP")) group_cap = atoi(ev);
     const int prio_chain = wgrad_overlap ? prio_greatest : prio_least;
     for (int i = 0; i < 3; ++i) CUDA_CHECK(cudaStreamCreateWithPriority(&st[i], cudaStreamNonBlocking, i == 2 ? prio_least : prio_chain));
     for (auto& s : sw) CUDA_CHECK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_chain));
@@ -241,7 +242,7 @@ void Engine::gemm(const Mat& A, int a_mn, const Mat& B, int b_mn, const Mat& C, 
         if (!A.h || !B.h) throw std::runtime_error("gemm: bf16 operand view missing (internal error)");
         // per-group device timers (bench.py roofline): batched GEMMs outside the explicitly named groups, by role
         const bool timed = (cfg.flags & 8) && !in_ktimer && M >= 256;
-        if (timed) kbegin(a_mn ? "k:gemm_wgrad" : (b_mn ? "k:gemm_dgrad_or_dense" : "k:gemm_proj"), q);
+        if (timed) kbegin(a_mn ? (q == swg ? "k:gemm_wgrad_side" : "k:gemm_wgrad") : (b_mn ? "k:gemm_dgrad_or_dense" : "k:gemm_proj"), q);
         gemm_tc(A.h, A.ld, a_mn, B.h, B.ld, b_mn, C.f, C.h, C.ld, (int)M, N, (int)K, alpha, bias, accumulate, q);
         if (timed) kend(q, 2.0 * (double)M * N * K * 1e-9);
     } else {
@@ -273,7 +274,7 @@ bool Engine::enc_segmented(const SeqPlan& E) const {
 // BPTT: the other way round.  Launch i of both chains run side by side.
 void Engine::enc_slice_plan(const SeqPlan& E, int nseg, bool bptt, std::vector<int>* want8) const {
     want8->assign((size_t)2 * nseg, 0);
-    const int cap = cfg.nranks > 1 ? 8 : 9;   // groups of 16 CTAs; data parallel leaves 20 SMs to the NCCL kernels of the overlapped buckets
+    const int cap = group_cap ? group_cap : cfg.nranks > 1 ? 8 : 9;   // groups of 16 CTAs; data parallel leaves 20 SMs to the NCCL kernels of the overlapped buckets
     for (int i = 0; i < nseg; ++i) {
         int rows[2], g16[2], g8[2];
         for (int d = 0; d < 2; ++d) {
@@ -642,7 +643,7 @@ void Engine::program(int mode, bool apply_update) {
     // 8-row slices first.  want8[j * nseg + sg] = 1 -> 8 rows per slice.
     std::vector<int> want8((size_t)L * nseg, 0);
     if (wave && !getenv("ARGSIM_NO_SLICE_BUDGET")) {
-        const int max_groups = cfg.nranks > 1 ? 8 : 9;   // data parallel: leave 20 SMs to the NCCL kernels of the overlapped buckets
+        const int max_groups = group_cap ? group_cap : cfg.nranks > 1 ? 8 : 9;   // data parallel: leave 20 SMs to the NCCL kernels of the overlapped buckets
         for (int stage = 0; stage < nseg + L - 1; ++stage) {
             std::vector<std::pair<int, int>> items;   // (live rows, j)
             int total = 0;
@@ -761,7 +762,7 @@ void Engine::program(int mode, bool apply_update) {
         if (train) {
             // dE (dense part) += D^-1/2 * dlogits^T . ho ;  dho = D^-1/2 * dlogits . E
             if (qw) side_after_main();   // d logits of this chunk are final
-            RUN(kbegin("k:logits_wgrad", qw));
+            RUN(kbegin(qw ? "k:logits_wgrad_side" : "k:logits_wgrad", qw));
             if (tied) {
                 gemm(logits, 1, HO.rowslice(r0, nr), 1, gE, V, D, nr, scale, nullptr, 1, qw);
             } else {   // dK += ho^T . dlogits ; db += column sums of dlogits
@@ -916,6 +917,8 @@ void Engine::program(int mode, bool apply_update) {
     Mat dHS = f32(S, 2 * H), dHSn = f32(S, 2 * H);
     RUN(CUDA_CHECK(cudaMemsetAsync(dHS.f, 0, sizeof(float) * S * 2 * H, s)));
     if (enc_kind == 0) RUN(launch_row_scatter(dhenc.f, 2 * H, dHS.f, 2 * H, dp.enc_last, b, 2 * H, 0, s));
+    size_t adam_split = 0;   // parameters [0, adam_split) were updated early on the side stream
+    const bool adam_early = apply_update && cfg.nranks == 1 && L >= 2 && !getenv("ARGSIM_NO_EARLY_ADAM");
     Mat dGXe1 = act(S, 6 * H), dGHe1 = act(S, 6 * H), HPe1 = act(S, 2 * H);
     // second set of gate-gradient buffers: layer i's weight-gradient GEMMs read one set on the side stream while layer
     // i-1's recurrence fills the other
@@ -1063,6 +1066,18 @@ void Engine::program(int mode, bool apply_update) {
             set_free[set] = next_event();
             CUDA_CHECK(cudaEventRecord(set_free[set], swg));
         }
+        if (on_side && i == 1 && adam_early) {
+            // Single GPU: every parameter in front of the first encoder layer's has its final gradient once the side
+            // stream gets here and no reader left on the chain after the dgrad above: their Adam update (70 % of the
+            // 683 MB the update moves) runs on the side stream under the last layer's recurrence instead of after it.
+            side_after_main();
+            adam_split = pinfo("encode/rnn1/fwd/W").off;
+            const double t = (double)(step + 1);
+            const float lr_t = (float)((double)lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
+            kbegin("k:adam_side", swg);
+            launch_adam(p, g, m, v, ph, (long long)adam_split, lr_t, 0.9f, 0.999f, 1e-8f, swg);
+            kend(swg);
+        }
         const size_t end = pinfo(pre + "bwd/bR").off + align_up(3 * H, 64);
         allreduce_bucket(bucket_lo, end, qw);
         bucket_lo = end;
@@ -1091,7 +1106,8 @@ void Engine::program(int mode, bool apply_update) {
         const double t = (double)(step + 1);
         const float lr_t = (float)((double)lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
         RUN(kbegin("k:adam"));
-        RUN(launch_adam(p, g, m, v, ph, (long long)nflat, lr_t, 0.9f, 0.999f, 1e-8f, s));
+        RUN(launch_adam(p + adam_split, g + adam_split, m + adam_split, v + adam_split, ph ? ph + adam_split : nullptr,
+                        (long long)(nflat - adam_split), lr_t, 0.9f, 0.999f, 1e-8f, s));
         RUN(kend());
     }
     phase("adam");

@@ -53,8 +53,11 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
     if (const char* ev = getenv("ARGSIM_WGRAD_OVERLAP")) wgrad_overlap = atoi(ev);
     if (const char* ev = getenv("ARGSIM_GROUP_CAP")) group_cap = atoi(ev);
+    if (const char* ev = getenv("ARGSIM_SIDE_UNITS")) side_units = atoi(ev);
     const int prio_chain = wgrad_overlap ? prio_greatest : prio_least;
-    for (int i = 0; i < 3; ++i) CUDA_CHECK(cudaStreamCreateWithPriority(&st[i], cudaStreamNonBlocking, i == 2 ? prio_least : prio_chain));
+    // the NCCL stream sits in between: a bucket's all-reduce is on the way to the end of the step, the side stream is not
+    const int prio_comm = wgrad_overlap ? (prio_least + prio_greatest) / 2 : prio_least;
+    for (int i = 0; i < 3; ++i) CUDA_CHECK(cudaStreamCreateWithPriority(&st[i], cudaStreamNonBlocking, i == 2 ? prio_comm : prio_chain));
     for (auto& s : sw) CUDA_CHECK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_chain));
     CUDA_CHECK(cudaStreamCreateWithPriority(&swg, cudaStreamNonBlocking, prio_least));
     if (const char* ev = getenv("ARGSIM_DEC_SEG")) dec_seg = atoi(ev);
@@ -243,7 +246,8 @@ void Engine::gemm(const Mat& A, int a_mn, const Mat& B, int b_mn, const Mat& C, 
         // per-group device timers (bench.py roofline): batched GEMMs outside the explicitly named groups, by role
         const bool timed = (cfg.flags & 8) && !in_ktimer && M >= 256;
         if (timed) kbegin(a_mn ? (q == swg ? "k:gemm_wgrad_side" : "k:gemm_wgrad") : (b_mn ? "k:gemm_dgrad_or_dense" : "k:gemm_proj"), q);
-        gemm_tc(A.h, A.ld, a_mn, B.h, B.ld, b_mn, C.f, C.h, C.ld, (int)M, N, (int)K, alpha, bias, accumulate, q);
+        gemm_tc(A.h, A.ld, a_mn, B.h, B.ld, b_mn, C.f, C.h, C.ld, (int)M, N, (int)K, alpha, bias, accumulate, q,
+                q == swg ? side_units : 0);
         if (timed) kend(q, 2.0 * (double)M * N * K * 1e-9);
     } else {
         if (!A.f || !B.f) throw std::runtime_error("gemm: fp32 operand view missing (internal error)");
@@ -983,6 +987,8 @@ void Engine::program(int mode, bool apply_update) {
         const Mat& dGHe = set ? dGHe2 : dGHe1;
         const Mat& HPe = set ? HPe2 : HPe1;
         if (side && set_free[set]) CUDA_CHECK(cudaStreamWaitEvent(s, set_free[set], 0));
+        // last layer: nothing below it to hide its weight gradients behind, so they are taken per time segment
+        const bool seg_wgrad = side && side_enc && i == 0 && enc_segmented(E) && !getenv("ARGSIM_NO_SEG_WGRAD");
         GruBwdArgs a[2];
         for (int d = 0; d < 2; ++d) {
             const std::string pd = pre + (d ? "bwd/" : "fwd/");
@@ -1029,6 +1035,20 @@ void Engine::program(int mode, bool apply_update) {
                         x.dh_in = (k > 0) ? carry[d][(k - 1) & 1] : nullptr;
                         x.dh_out = (k + 1 < nsegE) ? carry[d][k & 1] : nullptr;
                         gru_mma_bwd(mma, &x, 1, E, dp.enc_off, dp.enc_nact, H, sw[d], t0, tl, d, want8[(size_t)d * nsegE + k], pad_wave);
+                        if (seg_wgrad) {
+                            // the segment's rows of d gates are final: their share of the weight / bias gradients goes to
+                            // the side stream now, so only the last segment's share is left when the chains end
+                            cudaEvent_t ev = next_event();
+                            CUDA_CHECK(cudaEventRecord(ev, sw[d]));
+                            CUDA_CHECK(cudaStreamWaitEvent(swg, ev, 0));
+                            const std::string pd = pre + (d ? "bwd/" : "fwd/");
+                            const long long r0 = E.off[t0], nr = E.off[t0 + tl] - r0;
+                            Mat dgx = dGXe.colslice(d * 3 * H, 3 * H).rowslice(r0, nr), dgh = dGHe.colslice(d * 3 * H, 3 * H).rowslice(r0, nr);
+                            gemm(dgx, 1, encX[i].rowslice(r0, nr), 1, gmat(pd + "W"), 3 * H, in, nr, 1.f, nullptr, 1, swg);
+                            gemm(dgh, 1, HPe.colslice(d * H, H).rowslice(r0, nr), 1, gmat(pd + "R"), 3 * H, H, nr, 1.f, nullptr, 1, swg);
+                            colsum(dgx, nr, 3 * H, gptr(pd + "bW"), 1, swg);
+                            colsum(dgh, nr, 3 * H, gptr(pd + "bR"), 1, swg);
+                        }
                     }
                 for (int d = 0; d < 2; ++d) {
                     cudaEvent_t ev = next_event();
@@ -1053,13 +1073,17 @@ void Engine::program(int mode, bool apply_update) {
         }
         Mat gW = gmat(pre + "fwd/W");
         gW.rows = 6 * H;
-        gemm(dGXe, 1, encX[i], 1, gW, 6 * H, in, S, 1.f, nullptr, 1, qw);
-        for (int d = 0; d < 2; ++d) {
-            const std::string pd = pre + (d ? "bwd/" : "fwd/");
-            gemm(dGHe.colslice(d * 3 * H, 3 * H), 1, HPe.colslice(d * H, H), 1, gmat(pd + "R"), 3 * H, H, S, 1.f, nullptr, 1, qw);
+        if (!seg_wgrad) {
+            gemm(dGXe, 1, encX[i], 1, gW, 6 * H, in, S, 1.f, nullptr, 1, qw);
+            for (int d = 0; d < 2; ++d) {
+                const std::string pd = pre + (d ? "bwd/" : "fwd/");
+                gemm(dGHe.colslice(d * 3 * H, 3 * H), 1, HPe.colslice(d * H, H), 1, gmat(pd + "R"), 3 * H, H, S, 1.f, nullptr, 1, qw);
+            }
+            colsum(dGXe, S, 6 * H, gptr(pre + "fwd/bW"), 0, qw);   // fwd/bW and bwd/bW are adjacent
+            colsum(dGHe, S, 6 * H, gptr(pre + "fwd/bR"), 0, qw);
+        } else {
+            qw = swg;   // the layer's all-reduce bucket follows the side stream
         }
-        colsum(dGXe, S, 6 * H, gptr(pre + "fwd/bW"), 0, qw);   // fwd/bW and bwd/bW are adjacent
-        colsum(dGHe, S, 6 * H, gptr(pre + "fwd/bR"), 0, qw);
         if (!on_side) gemm(dGXe, 0, W, 1, dX, S, in, 6 * H, 1.f, nullptr, 0);
         std::swap(dHS, dHSn);
         if (on_side) {

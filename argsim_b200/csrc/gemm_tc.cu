@@ -623,7 +623,7 @@ void gemm_tc_init(int device) {
 bool gemm_tc_available() { return g_ready; }
 
 void gemm_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, float* Cf, bf16* Ch, int ldc, int M, int N,
-             int K, float alpha, const float* bias, int accumulate, cudaStream_t s) {
+             int K, float alpha, const float* bias, int accumulate, cudaStream_t s, int short_units) {
     if (!g_ready) throw std::runtime_error("gemm_tc: tcgen05 path not initialised");
     if (M <= 0 || N <= 0) return;
     if (K <= 0) throw std::runtime_error("gemm_tc: K must be positive");
@@ -642,6 +642,8 @@ void gemm_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn,
         // bf16 output with fewer work units than half the SMs and a long K (dho = dlogits . E): two k-halves meet in a bf16
         // reduce-add (0 + p1 is exact, so the result is p1 + p2 rounded once more: deterministic, <= 1 bf16 ulp)
         if (Ch && tiles * 2 <= g_num_sms && W.nkb_total >= 32) splits = 2;
+        const bool short_ctas = short_units > 0 && Cf && !bias;
+        if (short_ctas) splits = std::max(splits, cdiv(W.nkb_total, short_units));
         W.kb_per_split = cdiv(W.nkb_total, splits);
         W.splits = cdiv(W.nkb_total, W.kb_per_split);   // no empty split
         if (W.splits > 1 && !accumulate) {
@@ -653,7 +655,7 @@ void gemm_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn,
         encode_map(&ta, A, lda, a_mn, M, K, v2::BM);
         encode_map(&tb, B, ldb, b_mn, N, K, v2::BN);
         encode_c_map(&tc, Cf ? (void*)Cf : (void*)Ch, Ch != nullptr, ldc, M, N);
-        const int grid = std::min(tiles * W.splits, g_num_sms);
+        const int grid = short_ctas ? tiles * W.splits : std::min(tiles * W.splits, g_num_sms);
         const int ob = Ch != nullptr;
         if (!a_mn && !b_mn) launch2<0, 0>(ta, tb, tc, M, N, alpha, bias, ob, reduce, W, grid, s);
         else if (!a_mn && b_mn) launch2<0, 1>(ta, tb, tc, M, N, alpha, bias, ob, reduce, W, grid, s);

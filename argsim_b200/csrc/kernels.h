@@ -47,8 +47,11 @@ void gru_generic_cell(const float* gx, int ld_gx, const float* R, const float* b
 void gemm_simt(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc,
                int M, int N, int K, float alpha, const float* bias, int accumulate, bf16* C_h, cudaStream_t s);
 // tcgen05 + TMA path (bf16 operands, fp32 accumulate in TMEM). Cf and/or Ch may be null.
+// short_units > 0 (fp32 output): for GEMMs that share the chip with higher-priority kernels. The K range is split so
+// that a work unit has at most short_units k-blocks and every unit is its own CTA (not persistent): an SM is held
+// for a few microseconds at a time and a waiting block of the other kernel gets it between two units.
 void gemm_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, float* Cf, bf16* Ch, int ldc,
-             int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s);
+             int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s, int short_units = 0);
 void gemm_tc_init(int device);
 bool gemm_tc_available();
 

@@ -52,6 +52,9 @@ SIGNATURES = {
                                     C.c_int64, C.c_int64, C.POINTER(StepStats)]),
     'argsim_grad_step': (C.c_int, [C.c_void_p, _i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, _u8p, _f32p, C.c_int64,
                                    C.c_int64, C.c_int64, C.POINTER(StepStats)]),
+    'argsim_train_step_submit': (C.c_int, [C.c_void_p, _i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, _u8p, _f32p, C.c_int64,
+                                           C.c_int64, C.c_int64]),
+    'argsim_train_step_wait': (C.c_int, [C.c_void_p, C.POINTER(StepStats)]),
     'argsim_eval_step': (C.c_int, [C.c_void_p, _i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, C.c_int64,
                                    _f32p, _i64p, _i32p]),
     'argsim_embed': (C.c_int, [C.c_void_p, _i32p, C.c_int32, C.c_int32, _f32p]),
@@ -290,7 +293,7 @@ class Handle:
         self._ck(self.L.argsim_set_seed(self.h, int(seed)))
 
     # ---- steps ------------------------------------------------------------------------
-    def _step(self, fn, src, tgt, keep, eps, n_tokens_global, b_global, row0):
+    def _step(self, fn, src, tgt, keep, eps, n_tokens_global, b_global, row0, stats=True):
         src, tgt = _tokens(src, 'src'), _tokens(tgt, 'tgt')
         if src.shape[0] != tgt.shape[0]:
             raise ValueError('src and tgt must have the same number of rows')
@@ -303,6 +306,10 @@ class Handle:
             eps = np.ascontiguousarray(eps, np.float32)
             if eps.shape != (b, self.dim_rep):
                 raise ValueError('eps must be (batch, dim_rep)')
+        if not stats:
+            self._ck(fn(self.h, _p(src, _i32p), _p(tgt, _i32p), b, src.shape[1], tgt.shape[1], _p(keep, _u8p), _p(eps, _f32p),
+                        n_tokens_global, b_global, row0))
+            return None
         st = StepStats()
         self._ck(fn(self.h, _p(src, _i32p), _p(tgt, _i32p), b, src.shape[1], tgt.shape[1], _p(keep, _u8p), _p(eps, _f32p),
                     n_tokens_global, b_global, row0, C.byref(st)))
@@ -310,6 +317,16 @@ class Handle:
 
     def train_step(self, src, tgt, keep=None, eps=None, n_tokens_global=0, b_global=0, row0=0):
         return self._step(self.L.argsim_train_step, src, tgt, keep, eps, n_tokens_global, b_global, row0)
+
+    def train_step_submit(self, src, tgt, keep=None, eps=None, n_tokens_global=0, b_global=0, row0=0):
+        """enqueue one training step and return (the arrays are not referenced afterwards); at most two un-waited steps."""
+        self._step(self.L.argsim_train_step_submit, src, tgt, keep, eps, n_tokens_global, b_global, row0, stats=False)
+
+    def train_step_wait(self):
+        """statistics of the oldest un-waited step (blocks until it has finished on the device)."""
+        st = StepStats()
+        self._ck(self.L.argsim_train_step_wait(self.h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in StepStats._fields_}
 
     def grad_step(self, src, tgt, keep=None, eps=None, n_tokens_global=0, b_global=0, row0=0):
         return self._step(self.L.argsim_grad_step, src, tgt, keep, eps, n_tokens_global, b_global, row0)

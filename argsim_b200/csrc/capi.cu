@@ -13,9 +13,14 @@ struct argsim_handle {
 
 static thread_local std::string g_create_err;
 
-#define API_BEGIN(h)                                   \
+#define API_BEGIN_NODRAIN(h)                           \
     if (!(h) || !(h)->e) return -1;                    \
     try {
+// every entry point except the pipelined submit / wait pair first lets the steps in flight finish on the device
+#define API_BEGIN(h)                                   \
+    if (!(h) || !(h)->e) return -1;                    \
+    try {                                              \
+        (h)->e->drain();
 #define API_END(h)                                     \
     } catch (const std::exception& ex) {               \
         (h)->err = ex.what();                          \
@@ -127,6 +132,18 @@ int argsim_train_step(argsim_handle* h, const int32_t* src, const int32_t* tgt, 
                       int64_t row0_global, argsim_step_stats* out) {
     API_BEGIN(h)
     h->e->train_step(src, tgt, b, T_src, T_tgt, keep_mask, eps, n_tokens_global, b_global, row0_global, true, out);
+    API_END(h)
+}
+int argsim_train_step_submit(argsim_handle* h, const int32_t* src, const int32_t* tgt, int32_t b, int32_t T_src, int32_t T_tgt,
+                             const uint8_t* keep_mask, const float* eps, int64_t n_tokens_global, int64_t b_global,
+                             int64_t row0_global) {
+    API_BEGIN_NODRAIN(h)
+    h->e->train_step_submit(src, tgt, b, T_src, T_tgt, keep_mask, eps, n_tokens_global, b_global, row0_global, true);
+    API_END(h)
+}
+int argsim_train_step_wait(argsim_handle* h, argsim_step_stats* out) {
+    API_BEGIN_NODRAIN(h)
+    h->e->train_step_wait(out);
     API_END(h)
 }
 int argsim_grad_step(argsim_handle* h, const int32_t* src, const int32_t* tgt, int32_t b, int32_t T_src, int32_t T_tgt,

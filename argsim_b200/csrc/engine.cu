@@ -144,6 +144,7 @@ Engine::~Engine() {
     if (mma) gru_mma_destroy(mma);
     cudaFree(p); cudaFree(g); cudaFree(m); cudaFree(v); cudaFree(ph);
     cudaFree(arena.base); cudaFree(d_stage); cudaFreeHost(h_stage); cudaFree(d_eps_in);
+    for (auto& ps : pend) { if (ps.done) cudaEventDestroy(ps.done); if (ps.h_stats) cudaFreeHost(ps.h_stats); }
     cudaFree(d_stats); cudaFreeHost(h_stats); cudaFreeHost(h_out); cudaFree(gru_work);
     for (auto& e : pev) cudaEventDestroy(e);
     for (auto& k : ktimers) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
@@ -411,16 +412,19 @@ void Engine::stage(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt
     size_t need = plan.ids_src.size() + plan.ids_lead.size() + plan.labels.size() + 2 * (size_t)b + (E.Tmax + 1) + E.Tmax +
                   (Dp.Tmax + 1) + Dp.Tmax + 64 * 9;
     if (need > stage_cap) {
-        CUDA_CHECK(cudaStreamSynchronize(st[0]));
+        CUDA_CHECK(cudaDeviceSynchronize());
         cudaFreeHost(h_stage); cudaFree(d_stage);
-        stage_cap = need * 2;
-        CUDA_CHECK(cudaMallocHost(&h_stage, stage_cap * sizeof(int)));
-        CUDA_CHECK(cudaMalloc(&d_stage, stage_cap * sizeof(int)));
+        stage_cap = align_up(need * 2, 64);
+        CUDA_CHECK(cudaMallocHost(&h_stage, 2 * stage_cap * sizeof(int)));
+        CUDA_CHECK(cudaMalloc(&d_stage, 2 * stage_cap * sizeof(int)));
     }
+    // slot of the step being staged: the previous step's tables stay in the other one while it runs
+    int* const hs = h_stage + (submit_seq & 1) * stage_cap;
+    int* const ds = d_stage + (submit_seq & 1) * stage_cap;
     size_t o = 0;
     auto put = [&](const std::vector<int>& vsrc, int** dev) {
-        *dev = d_stage + o;
-        if (!vsrc.empty()) memcpy(h_stage + o, vsrc.data(), vsrc.size() * sizeof(int));
+        *dev = ds + o;
+        if (!vsrc.empty()) memcpy(hs + o, vsrc.data(), vsrc.size() * sizeof(int));
         o = align_up(o + vsrc.size(), 64);
     };
     put(plan.ids_src, &dp.ids_src);
@@ -432,7 +436,7 @@ void Engine::stage(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt
     put(E.nact, &dp.enc_nact);
     put(Dp.off, &dp.dec_off);
     put(Dp.nact, &dp.dec_nact);
-    CUDA_CHECK(cudaMemcpyAsync(d_stage, h_stage, o * sizeof(int), cudaMemcpyHostToDevice, st[0]));
+    CUDA_CHECK(cudaMemcpyAsync(ds, hs, o * sizeof(int), cudaMemcpyHostToDevice, st[0]));
     have_eps = false;
     if (eps) {
         size_t n = (size_t)b * R;
@@ -1140,31 +1144,59 @@ void Engine::program(int mode, bool apply_update) {
 // ------------------------------------------------------------------------------------------
 // public steps
 // ------------------------------------------------------------------------------------------
-void Engine::train_step(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt, const uint8_t* keep, const float* eps,
-                        int64_t n_tok_global, int64_t b_global, int64_t row0, bool apply_update, argsim_step_stats* out) {
-    float keepwd, anneal, lr;
-    schedule_f32(step, cfg.accelerate, cfg.learn_rate, &keepwd, &anneal, &lr);
+void Engine::train_step_submit(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt, const uint8_t* keep, const float* eps,
+                               int64_t n_tok_global, int64_t b_global, int64_t row0, bool apply_update) {
+    if (pend_n >= 2) throw std::runtime_error("train_step_submit: two steps are already in flight, call train_step_wait first");
+    PendingStep& ps = pend[submit_seq & 1];
+    if (!ps.done) {
+        CUDA_CHECK(cudaEventCreateWithFlags(&ps.done, cudaEventDisableTiming));
+        CUDA_CHECK(cudaMallocHost(&ps.h_stats, 4 * sizeof(double)));
+    }
+    schedule_f32(step, cfg.accelerate, cfg.learn_rate, &ps.keepwd, &ps.anneal, &ps.lr);
     DropoutSpec drop;
-    drop.train = 1; drop.keep = keep; drop.rate_keepwd = keepwd; drop.seed = seed; drop.step = (uint64_t)step; drop.row0 = row0;
+    drop.train = 1; drop.keep = keep; drop.rate_keepwd = ps.keepwd; drop.seed = seed; drop.step = (uint64_t)step; drop.row0 = row0;
     last.train = 1; last.n_tok_global = n_tok_global; last.b_global = b_global; last.row0 = row0;
     stage(src, tgt, b, Ts, Tt, 1, drop, eps);
     run_device(2, apply_update);
-    CUDA_CHECK(cudaMemcpyAsync(h_stats, d_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st[0]));
-    CUDA_CHECK(cudaStreamSynchronize(st[0]));
-    CUDA_CHECK(cudaStreamSynchronize(st[2]));
-    collect_timings();
-    const double n_glob = n_tok_global > 0 ? (double)n_tok_global : (double)plan.dec.rows;
-    const double b_glob = b_global > 0 ? (double)b_global : (double)b;
+    CUDA_CHECK(cudaMemcpyAsync(ps.h_stats, d_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st[0]));
+    CUDA_CHECK(cudaEventRecord(ps.done, st[0]));   // the comm and side streams have joined the main stream by now
+    ps.n_glob = n_tok_global > 0 ? (double)n_tok_global : (double)plan.dec.rows;
+    ps.b_glob = b_global > 0 ? (double)b_global : (double)b;
     if (apply_update) step += 1;
-    if (out) {
-        out->loss_gen = (float)(h_stats[0] / n_glob);
-        out->errt = (float)(h_stats[1] / n_glob);
-        out->loss_kld = (float)(h_stats[2] / (b_glob * R));
-        out->loss = anneal * out->loss_kld + out->loss_gen;
-        out->rate_keepwd = keepwd; out->rate_anneal = anneal; out->rate_update = lr;
-        out->n_tokens = (int64_t)n_glob;
-        out->step = step;
+    ps.step_after = step;
+    ++submit_seq;
+    ++pend_n;
+}
+
+void Engine::train_step_wait(argsim_step_stats* out) {
+    if (pend_n == 0) throw std::runtime_error("train_step_wait: no step in flight");
+    PendingStep& ps = pend[(submit_seq - pend_n) & 1];
+    CUDA_CHECK(cudaEventSynchronize(ps.done));
+    --pend_n;
+    if (pend_n == 0) {   // the timers' events belong to the newest submission
+        CUDA_CHECK(cudaStreamSynchronize(st[2]));
+        collect_timings();
     }
+    if (out) {
+        out->loss_gen = (float)(ps.h_stats[0] / ps.n_glob);
+        out->errt = (float)(ps.h_stats[1] / ps.n_glob);
+        out->loss_kld = (float)(ps.h_stats[2] / (ps.b_glob * R));
+        out->loss = ps.anneal * out->loss_kld + out->loss_gen;
+        out->rate_keepwd = ps.keepwd; out->rate_anneal = ps.anneal; out->rate_update = ps.lr;
+        out->n_tokens = (int64_t)ps.n_glob;
+        out->step = ps.step_after;
+    }
+}
+
+void Engine::drain() {
+    for (int i = pend_n; i > 0; --i) CUDA_CHECK(cudaEventSynchronize(pend[(submit_seq - i) & 1].done));
+}
+
+void Engine::train_step(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt, const uint8_t* keep, const float* eps,
+                        int64_t n_tok_global, int64_t b_global, int64_t row0, bool apply_update, argsim_step_stats* out) {
+    if (pend_n) throw std::runtime_error("train_step: pipelined steps are in flight, call train_step_wait first");
+    train_step_submit(src, tgt, b, Ts, Tt, keep, eps, n_tok_global, b_global, row0, apply_update);
+    train_step_wait(out);
 }
 
 void Engine::bench_resident(int iters, float* ms) {

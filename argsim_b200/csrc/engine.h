@@ -76,6 +76,13 @@ public:
     void decode_init(const float* z, int b, float* state);
     int decode_loop(const float* z, int b, int steps, int32_t* tokens);   // returns t <= steps; tokens is (b, steps) row-major
     void decode_step(const int32_t* lead, int b, float* state, int32_t* pred);
+    // Pipelined form of train_step (src/train.py:118 fetches nothing but the op, so the call need not block): submit
+    // enqueues the step and returns; wait returns the oldest un-waited step's statistics. At most two steps may be
+    // un-waited, so the host plan + H2D of step n+1 overlap the device's step n. train_step == submit + wait.
+    void train_step_submit(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt, const uint8_t* keep, const float* eps,
+                           int64_t n_tok_global, int64_t b_global, int64_t row0, bool apply_update);
+    void train_step_wait(argsim_step_stats* out);
+    void drain();   // every submitted step complete on the device (their statistics stay queued for train_step_wait)
     void bench_resident(int iters, float* ms);
     void save(const char* path);
     void load(const char* path);
@@ -109,9 +116,19 @@ private:
 
     // staged plan
     BatchPlan plan;
-    int* h_stage = nullptr;  // pinned
+    int* h_stage = nullptr;  // pinned; two slots of stage_cap ints (one per step in flight)
     int* d_stage = nullptr;
     size_t stage_cap = 0;
+    struct PendingStep {
+        cudaEvent_t done = nullptr;
+        double* h_stats = nullptr;   // pinned, 4 doubles
+        float keepwd = 0.f, anneal = 0.f, lr = 0.f;
+        double n_glob = 0.0, b_glob = 0.0;
+        int64_t step_after = 0;
+    };
+    PendingStep pend[2];
+    uint64_t submit_seq = 0;   // steps submitted so far; slot = seq & 1
+    int pend_n = 0;            // submitted and not yet waited for (oldest: slot (submit_seq - pend_n) & 1)
     struct DevPlan {
         int *ids_src, *ids_lead, *labels, *enc_last, *dec_perm, *enc_off, *enc_nact, *dec_off, *dec_nact;
     } dp{};

@@ -148,11 +148,27 @@ class Session:
         self.handle.set_seed(_state['seed'])
         self.config = dict(cfg)
         self.nranks, self.rank = nranks, rank
-        self.last_stats = None
+        self._last_stats = None
+        self._inflight = 0     # train steps submitted and not yet waited for (<= 2)
+        self.pipelined = True  # sess.run(model.train_step) returns once the step is enqueued (src/train.py:118 fetches nothing else)
         _state['session'] = self
 
+    def _drain(self):
+        while self._inflight:
+            self._last_stats = self.handle.train_step_wait()
+            self._inflight -= 1
+
+    @property
+    def last_stats(self):
+        """statistics of the most recent training step (waits for it)."""
+        self._drain()
+        return self._last_stats
+
     def close(self):
-        self.handle.close()
+        try:
+            self._drain()
+        finally:
+            self.handle.close()
         if _state['session'] is self:
             _state['session'] = None
 
@@ -209,9 +225,19 @@ class Session:
                     tgt = item[tgt.index]
             if src is None or tgt is None:
                 raise ValueError('train_step needs src and tgt (feed them or build the model on a pipe)')
-            self.last_stats = h.train_step(src, tgt)
+            if self.pipelined and self.nranks == 1:
+                # submit(n+1) before wait(n): the host plan + H2D of this step overlap the device's previous step
+                h.train_step_submit(src, tgt)
+                self._inflight += 1
+                if self._inflight == 2:
+                    self._last_stats = h.train_step_wait()
+                    self._inflight -= 1
+            else:
+                self._drain()
+                self._last_stats = h.train_step(src, tgt)
             vals['train_step'] = None
             return vals
+        self._drain()
         if want <= {'state_in'} and 'z' in feeds:
             vals['state_in'] = h.decode_init(feeds['z'])
             return vals

@@ -84,6 +84,16 @@ int  argsim_train_step(argsim_handle*, const int32_t* src, const int32_t* tgt, i
                        int32_t T_src, int32_t T_tgt, const uint8_t* keep_mask, const float* eps,
                        int64_t n_tokens_global, int64_t b_global, int64_t row0_global,
                        argsim_step_stats* out);
+/* Pipelined form of the same call.  src/train.py:118 fetches nothing but the op (sess.run(model.train_step)), so the
+ * caller does not need the step to have finished: submit returns once the step is enqueued (host plan and H2D staging
+ * done, src/tgt/keep_mask/eps no longer referenced) and wait returns the statistics of the OLDEST un-waited step.
+ * At most two steps may be un-waited, i.e. the pattern is submit(n+1); wait(n): the host side of step n+1 overlaps the
+ * device's step n.  Every other entry point first lets the steps in flight finish; argsim_train_step itself refuses
+ * to run while un-waited steps exist. */
+int  argsim_train_step_submit(argsim_handle*, const int32_t* src, const int32_t* tgt, int32_t b,
+                              int32_t T_src, int32_t T_tgt, const uint8_t* keep_mask, const float* eps,
+                              int64_t n_tokens_global, int64_t b_global, int64_t row0_global);
+int  argsim_train_step_wait(argsim_handle*, argsim_step_stats* out);
 /* same step but stops before Adam / step increment (gradient parity, test only) */
 int  argsim_grad_step(argsim_handle*, const int32_t* src, const int32_t* tgt, int32_t b,
                       int32_t T_src, int32_t T_tgt, const uint8_t* keep_mask, const float* eps,

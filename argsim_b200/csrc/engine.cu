@@ -926,7 +926,7 @@ void Engine::program(int mode, bool apply_update) {
     RUN(CUDA_CHECK(cudaMemsetAsync(dHS.f, 0, sizeof(float) * S * 2 * H, s)));
     if (enc_kind == 0) RUN(launch_row_scatter(dhenc.f, 2 * H, dHS.f, 2 * H, dp.enc_last, b, 2 * H, 0, s));
     size_t adam_split = 0;   // parameters [0, adam_split) were updated early on the side stream
-    const bool adam_early = apply_update && cfg.nranks == 1 && L >= 2 && !getenv("ARGSIM_NO_EARLY_ADAM");
+    const bool adam_early = apply_update && L >= 2 && !getenv("ARGSIM_NO_EARLY_ADAM");
     Mat dGXe1 = act(S, 6 * H), dGHe1 = act(S, 6 * H), HPe1 = act(S, 2 * H);
     // second set of gate-gradient buffers: layer i's weight-gradient GEMMs read one set on the side stream while layer
     // i-1's recurrence fills the other
@@ -1094,21 +1094,25 @@ void Engine::program(int mode, bool apply_update) {
             set_free[set] = next_event();
             CUDA_CHECK(cudaEventRecord(set_free[set], swg));
         }
-        if (on_side && i == 1 && adam_early) {
-            // Single GPU: every parameter in front of the first encoder layer's has its final gradient once the side
-            // stream gets here and no reader left on the chain after the dgrad above: their Adam update (70 % of the
-            // 683 MB the update moves) runs on the side stream under the last layer's recurrence instead of after it.
-            side_after_main();
-            adam_split = pinfo("encode/rnn1/fwd/W").off;
-            const double t = (double)(step + 1);
-            const float lr_t = (float)((double)lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
-            kbegin("k:adam_side", swg);
-            launch_adam(p, g, m, v, ph, (long long)adam_split, lr_t, 0.9f, 0.999f, 1e-8f, swg);
-            kend(swg);
-        }
         const size_t end = pinfo(pre + "bwd/bR").off + align_up(3 * H, 64);
         allreduce_bucket(bucket_lo, end, qw);
         bucket_lo = end;
+        if (on_side && i == 1 && adam_early) {
+            // Every parameter in front of the first encoder layer's has its final gradient once the side stream (data
+            // parallel: the NCCL stream, behind the layer-2 bucket's all-reduce) gets here, and no reader left on the
+            // chain after the dgrad above: their Adam update (70 % of the 683 MB the update moves) runs under the last
+            // layer's recurrence instead of after it.
+            cudaStream_t qa = cfg.nranks > 1 ? st[2] : swg;
+            cudaEvent_t ev = next_event();
+            CUDA_CHECK(cudaEventRecord(ev, s));
+            CUDA_CHECK(cudaStreamWaitEvent(qa, ev, 0));
+            adam_split = end;
+            const double t = (double)(step + 1);
+            const float lr_t = (float)((double)lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
+            kbegin("k:adam_side", qa);
+            launch_adam(p, g, m, v, ph, (long long)adam_split, lr_t, 0.9f, 0.999f, 1e-8f, qa);
+            kend(qa);
+        }
     }
     if (side) {   // everything the side stream produced is a gradient: Adam and the last bucket come after it
         cudaEvent_t ev = next_event();

@@ -189,7 +189,7 @@ private:
     void gemm(const Mat& A, int a_mn, const Mat& B, int b_mn, const Mat& C, long long M, int N, long long K, float alpha,
               const float* bias, int accumulate, cudaStream_t q = nullptr);
     void colsum(const Mat& A, long long rows, int cols, float* out, int accumulate = 0, cudaStream_t q = nullptr);
-    void gather_embed(const int* ids, long long n, const Mat& out);
+    void gather_embed(const int* ids, long long n, const Mat& out, cudaStream_t q = nullptr);
     void gru_fwd(GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact);
     void gru_bwd(GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact);
     void allreduce_bucket(size_t off0, size_t off1, cudaStream_t after = nullptr);   // after: the stream whose work produced the bucket (default main)

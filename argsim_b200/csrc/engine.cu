@@ -54,6 +54,7 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     if (const char* ev = getenv("ARGSIM_WGRAD_OVERLAP")) wgrad_overlap = atoi(ev);
     if (const char* ev = getenv("ARGSIM_GROUP_CAP")) group_cap = atoi(ev);
     if (const char* ev = getenv("ARGSIM_SIDE_UNITS")) side_units = atoi(ev);
+    if (const char* ev = getenv("ARGSIM_DEC_EARLY")) dec_early_on = atoi(ev);
     const int prio_chain = wgrad_overlap ? prio_greatest : prio_least;
     // the NCCL stream sits in between: a bucket's all-reduce is on the way to the end of the step, the side stream is not
     const int prio_comm = wgrad_overlap ? (prio_least + prio_greatest) / 2 : prio_least;
@@ -503,7 +504,7 @@ void Engine::program(int mode, bool apply_update) {
 
     // The decoder's first-layer inputs do not depend on the encoder: emb_tgt is gathered and projected on the side
     // stream while the encoder's recurrences run (they are off the serial chain that way)
-    const bool dec_early = mode != 0 && N > 0 && wgrad_overlap && use_mma && dec_wavefront(Dp) && getenv("ARGSIM_DEC_EARLY");
+    const bool dec_early = mode != 0 && N > 0 && wgrad_overlap && use_mma && dec_wavefront(Dp) && dec_early_on;
     Mat decY0, decGX0;
     cudaEvent_t ev_dec0 = nullptr;
     if (dec_early) {

@@ -98,6 +98,7 @@ private:
                                                         // run on the SMs the recurrence launches of the layer below leave free
     int group_cap = 0;                                  // ARGSIM_GROUP_CAP: groups of 16 CTAs the slice planners may use (0 = 9, or 8 under data parallel)
     int side_units = 32;                                // ARGSIM_SIDE_UNITS: k-blocks per work unit of the side stream's GEMMs (0 = persistent CTAs; 32: 10.50 -> 10.41 ms/step)
+    int dec_early_on = 1;                               // ARGSIM_DEC_EARLY=0: decoder layer-0 gather + projection on the main stream after the encoder (10.66 vs 10.64 ms/step)
     int wgrad_overlap = 1;                              // ARGSIM_WGRAD_OVERLAP=0: weight gradients on the main stream, in line
     std::vector<cudaEvent_t> evpool;
     size_t evcount = 0;

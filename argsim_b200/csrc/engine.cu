@@ -55,6 +55,10 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     if (const char* ev = getenv("ARGSIM_GROUP_CAP")) group_cap = atoi(ev);
     if (const char* ev = getenv("ARGSIM_SIDE_UNITS")) side_units = atoi(ev);
     if (const char* ev = getenv("ARGSIM_DEC_EARLY")) dec_early_on = atoi(ev);
+    slice_budget = getenv("ARGSIM_NO_SLICE_BUDGET") == nullptr;
+    early_adam = getenv("ARGSIM_NO_EARLY_ADAM") == nullptr;
+    seg_wgrad_on = getenv("ARGSIM_NO_SEG_WGRAD") == nullptr;
+    if (const char* ev = getenv("ARGSIM_LOGIT_CHUNK")) logit_chunk = std::max(128, atoi(ev));
     const int prio_chain = wgrad_overlap ? prio_greatest : prio_least;
     // the NCCL stream sits in between: a bucket's all-reduce is on the way to the end of the step, the side stream is not
     const int prio_comm = wgrad_overlap ? (prio_least + prio_greatest) / 2 : prio_least;
@@ -679,7 +683,7 @@ void Engine::program(int mode, bool apply_update) {
     // j + sg run side by side: within the 9 groups of 16 CTAs the chip holds, the launches with the most live rows get
     // 8-row slices first.  want8[j * nseg + sg] = 1 -> 8 rows per slice.
     std::vector<int> want8((size_t)L * nseg, 0);
-    if (wave && !getenv("ARGSIM_NO_SLICE_BUDGET")) {
+    if (wave && slice_budget) {
         const int max_groups = group_cap ? group_cap : cfg.nranks > 1 ? 8 : 9;   // data parallel: leave 20 SMs to the NCCL kernels of the overlapped buckets
         for (int stage = 0; stage < nseg + L - 1; ++stage) {
             std::vector<std::pair<int, int>> items;   // (live rows, j)
@@ -758,7 +762,7 @@ void Engine::program(int mode, bool apply_update) {
     outp.loss_samp = loss_samp; outp.err_samp = err_samp; outp.pred = pred;
     const float scale = 1.0f / sqrtf((float)D);
     long long chunk = use_tc ? 4096 : 2048;
-    if (const char* ev = getenv("ARGSIM_LOGIT_CHUNK")) chunk = std::max(128, atoi(ev));
+    if (logit_chunk) chunk = logit_chunk;
     chunk = std::min<long long>(chunk, std::max<long long>(N, 1));
     // Weight gradients are not on the serial chain: with the persistent recurrence in use they go to the low-priority
     // side stream and fill the SMs the recurrence launches of the layers below leave free (a third of the encoder's
@@ -963,7 +967,7 @@ void Engine::program(int mode, bool apply_update) {
     RUN(CUDA_CHECK(cudaMemsetAsync(dHS.f, 0, sizeof(float) * S * 2 * H, s)));
     if (enc_kind == 0) RUN(launch_row_scatter(dhenc.f, 2 * H, dHS.f, 2 * H, dp.enc_last, b, 2 * H, 0, s));
     size_t adam_split = 0;   // parameters [0, adam_split) were updated early on the side stream
-    const bool adam_early = apply_update && L >= 2 && !getenv("ARGSIM_NO_EARLY_ADAM");
+    const bool adam_early = apply_update && L >= 2 && early_adam;
     Mat dGXe1 = act(S, 6 * H), dGHe1 = act(S, 6 * H), HPe1 = act(S, 2 * H);
     // second set of gate-gradient buffers: layer i's weight-gradient GEMMs read one set on the side stream while layer
     // i-1's recurrence fills the other
@@ -1029,7 +1033,7 @@ void Engine::program(int mode, bool apply_update) {
         const Mat& HPe = set ? HPe2 : HPe1;
         if (side && set_free[set]) CUDA_CHECK(cudaStreamWaitEvent(s, set_free[set], 0));
         // last layer: nothing below it to hide its weight gradients behind, so they are taken per time segment
-        const bool seg_wgrad = side && side_enc && i == 0 && enc_segmented(E) && !getenv("ARGSIM_NO_SEG_WGRAD");
+        const bool seg_wgrad = side && side_enc && i == 0 && enc_segmented(E) && seg_wgrad_on;
         GruBwdArgs a[2];
         for (int d = 0; d < 2; ++d) {
             const std::string pd = pre + (d ? "bwd/" : "fwd/");

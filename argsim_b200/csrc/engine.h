@@ -99,6 +99,10 @@ private:
     int group_cap = 0;                                  // ARGSIM_GROUP_CAP: groups of 16 CTAs the slice planners may use (0 = 9, or 8 under data parallel)
     int side_units = 32;                                // ARGSIM_SIDE_UNITS: k-blocks per work unit of the side stream's GEMMs (0 = persistent CTAs; 32: 10.50 -> 10.41 ms/step)
     int dec_early_on = 1;                               // ARGSIM_DEC_EARLY=0: decoder layer-0 gather + projection on the main stream after the encoder (10.66 vs 10.64 ms/step)
+    bool slice_budget = true;                           // ARGSIM_NO_SLICE_BUDGET: every wavefront launch takes 16-row slices
+    bool early_adam = true;                             // ARGSIM_NO_EARLY_ADAM: one Adam launch after the last gradient
+    bool seg_wgrad_on = true;                           // ARGSIM_NO_SEG_WGRAD: last encoder layer's weight gradients in one piece
+    int logit_chunk = 0;                                // ARGSIM_LOGIT_CHUNK: rows per vocabulary-projection chunk (0 = 4096 / 2048)
     int wgrad_overlap = 1;                              // ARGSIM_WGRAD_OVERLAP=0: weight gradients on the main stream, in line
     std::vector<cudaEvent_t> evpool;
     size_t evcount = 0;

@@ -360,6 +360,19 @@ def main():
                              'the recurrence is bound by serial-step latency (512 dependent steps per launch, one 16-CTA '
                              'exchange through L2 each: >= 1270 cycles, DESIGN.md section 5), not by the tensor pipe; '
                              'traffic = dram bytes per launch from profiles/r1c_gru_*_enc_ncu.md')
+        if dom.startswith('gru_'):
+            # what actually bounds these kernels: serial steps x per-step latency.  Encoder: one launch (or segment chain)
+            # per layer, Tmax_src dependent steps each; decoder: a 3-layer wavefront over Tmax_dec steps.
+            enc = dom.endswith('_enc')
+            serial = 3 * plan_l['Tmax_src'] if enc else plan_l['Tmax_dec'] + 2 * 64
+            mhz = float(clocks.get('sm_mhz') or 1965.0)
+            cyc = d['ms_per_step'] * 1e-3 / serial * mhz * 1e6
+            roofline['latency'] = dict(serial_steps_per_training_step=int(serial), cycles_per_serial_step=round(cyc, 1),
+                                       exchange_floor_cycles=950, frac_of_exchange_floor=round(950.0 / cyc, 4),
+                                       note='one 16-CTA all-gather / reduce-scatter through L2 per serial step: 950 cycles measured '
+                                            'for the bare exchange in the placement the launches use (argsim_bench_exchange, '
+                                            'profiles/r1_exchange_xbench.json); the rest of a step is HMMA issue, one block barrier '
+                                            'and the gate math (DESIGN.md section 5)')
     line = dict(metric=METRIC, value=value, unit='sequences/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='bf16' if args.precision == 'bf16' else 'f32', data='synthetic',

@@ -166,3 +166,37 @@ def test_non_default_encoder_branches_on_the_persistent_kernels(bidirectional, b
         r = G[k].ravel()
         cos = g @ r / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30)
         assert cos > 0.995, (k, cos)
+
+
+@pytest.mark.parametrize('layers,b,tmax', [(2, 24, 30), (4, 40, 200), (1, 16, 190)])
+def test_side_stream_schedule_equals_inline(monkeypatch, layers, b, tmax):
+    """weight gradients / bias sums / most of Adam on the low-priority side stream (double-buffered
+    gate gradients, per-segment wgrads of the last encoder layer, early Adam, decoder inputs during the encoder) against
+    the same library with everything in line on the main stream (ARGSIM_WGRAD_OVERLAP=0): statistics of three training
+    steps and the weights after them, for layer counts that exercise both buffer sets and both encoder BPTT forms."""
+    from argsim_b200 import _lib
+    cfg = dict(dim_tgt=1024, dim_emb=512, dim_rep=256, rnn_layers=layers, accelerate=1e-4, learn_rate=1e-3, bos=2, eos=1)
+    monkeypatch.setenv('ARGSIM_WGRAD_OVERLAP', '0')
+    hi, P = _mk(cfg, _lib.BF16, flags=0)
+    monkeypatch.setenv('ARGSIM_WGRAD_OVERLAP', '1')
+    hs, _ = _mk(cfg, _lib.BF16, flags=0)
+    for it in range(3):
+        src = ragged_batch(b, tmax, cfg['dim_tgt'], 80 + it + layers)
+        tgt = ragged_batch(b, max(2, tmax - 2), cfg['dim_tgt'], 90 + it + layers)
+        keep, eps = _inject(cfg, tgt, 95 + it)
+        a = hi.train_step(src, tgt, keep=keep, eps=eps)
+        s = hs.train_step(src, tgt, keep=keep, eps=eps)
+        for name in ('loss', 'loss_gen', 'loss_kld', 'errt'):
+            assert rel(s[name], a[name]) < 2e-3, (it, name, s[name], a[name])
+        assert s['step'] == a['step'] == it + 1
+    # Three Adam steps move every weight by ~3e-3 whatever the size of its gradient, so elements whose gradient is
+    # rounding noise may move apart between two schedules (different split-K order); a skipped, doubled or stale update
+    # of a parameter shows as a distance of the order of the update itself.
+    bad = {}
+    for k in P:
+        p0 = P[k].astype(np.float32)
+        ui, us = hi.get_param(k) - p0, hs.get_param(k) - p0
+        d = float(np.linalg.norm(us - ui) / (np.linalg.norm(ui) + 1e-12))
+        if d > 0.25:
+            bad[k] = round(d, 3)
+    assert not bad, bad

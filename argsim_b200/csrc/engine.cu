@@ -967,6 +967,14 @@ void Engine::program(int mode, bool apply_update) {
     RUN(CUDA_CHECK(cudaMemsetAsync(dHS.f, 0, sizeof(float) * S * 2 * H, s)));
     if (enc_kind == 0) RUN(launch_row_scatter(dhenc.f, 2 * H, dHS.f, 2 * H, dp.enc_last, b, 2 * H, 0, s));
     size_t adam_split = 0;   // parameters [0, adam_split) were updated early on the side stream
+    // Adam, TF-1 form (model.py:189): lr_t = lr sqrt(1 - b2^t) / (1 - b1^t), epsilon outside the bias-corrected root
+    auto adam_range = [&](size_t lo, size_t hi, cudaStream_t q, const char* timer) {
+        const double t = (double)(step + 1);
+        const float lr_t = (float)((double)lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
+        kbegin(timer, q);
+        launch_adam(p + lo, g + lo, m + lo, v + lo, ph ? ph + lo : nullptr, (long long)(hi - lo), lr_t, 0.9f, 0.999f, 1e-8f, q);
+        kend(q);
+    };
     const bool adam_early = apply_update && L >= 2 && early_adam;
     Mat dGXe1 = act(S, 6 * H), dGHe1 = act(S, 6 * H), HPe1 = act(S, 2 * H);
     // second set of gate-gradient buffers: layer i's weight-gradient GEMMs read one set on the side stream while layer
@@ -1148,11 +1156,7 @@ void Engine::program(int mode, bool apply_update) {
             CUDA_CHECK(cudaEventRecord(ev, s));
             CUDA_CHECK(cudaStreamWaitEvent(qa, ev, 0));
             adam_split = end;
-            const double t = (double)(step + 1);
-            const float lr_t = (float)((double)lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
-            kbegin("k:adam_side", qa);
-            launch_adam(p, g, m, v, ph, (long long)adam_split, lr_t, 0.9f, 0.999f, 1e-8f, qa);
-            kend(qa);
+            adam_range(0, adam_split, qa, "k:adam_side");
         }
     }
     if (side) {   // everything the side stream produced is a gradient: Adam and the last bucket come after it
@@ -1175,14 +1179,7 @@ void Engine::program(int mode, bool apply_update) {
     phase("allreduce_wait");
 
     // ---------------- Adam, TF-1 form (model.py:189)
-    if (apply_update) {
-        const double t = (double)(step + 1);
-        const float lr_t = (float)((double)lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
-        RUN(kbegin("k:adam"));
-        RUN(launch_adam(p + adam_split, g + adam_split, m + adam_split, v + adam_split, ph ? ph + adam_split : nullptr,
-                        (long long)(nflat - adam_split), lr_t, 0.9f, 0.999f, 1e-8f, s));
-        RUN(kend());
-    }
+    if (apply_update) RUN(adam_range(adam_split, nflat, s, "k:adam"));
     phase("adam");
 }
 

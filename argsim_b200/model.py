@@ -139,10 +139,19 @@ def reset():
 class Session:
     """tf.InteractiveSession analogue: owns the device state of the shared variable set."""
 
-    def __init__(self, precision='bf16', device=0, nranks=1, rank=0, nccl_id=None, flags=0, config=None):
+    def __init__(self, precision='bf16', device=None, nranks=None, rank=0, nccl_id=None, flags=0, config=None):
         cfg = config or _state['config']
         if cfg is None:
             raise RuntimeError('build a model with vAe(...) before creating the Session')
+        if nranks is None:
+            # under `python -m torch.distributed.run` every rank builds the same graph and owns one GPU: the session turns
+            # data parallel by itself (batch rows sharded per step, gradients all-reduced inside the library)
+            from . import parallel
+            nranks, rank, local = parallel.env_world()
+            if nranks > 1:
+                device = local if device is None else device
+                nccl_id = parallel.exchange_nccl_id(_lib.nccl_unique_id, nranks, rank)
+        device = 0 if device is None else device
         prec = {'bf16': _lib.BF16, 'fp32': _lib.FP32_VALIDATE}[precision] if isinstance(precision, str) else precision
         self.handle = _lib.Handle(precision=prec, device=device, nranks=nranks, rank=rank, nccl_id=nccl_id, flags=flags, **cfg)
         self.handle.set_seed(_state['seed'])
@@ -225,16 +234,23 @@ class Session:
                     tgt = item[tgt.index]
             if src is None or tgt is None:
                 raise ValueError('train_step needs src and tgt (feed them or build the model on a pipe)')
-            if self.pipelined and self.nranks == 1:
+            kw = {}
+            if self.nranks > 1:
+                # every rank draws the same global batch (same seed, same generator) and keeps its rows; the two loss
+                # means are normalised by the GLOBAL counts (model.py:181,184), known from the lengths before launch
+                from . import parallel
+                src, tgt, _, n_tok, b_glob = parallel.shard_batch(src, tgt, self.nranks, self.rank, eos=model.config.get('eos', 1))
+                kw = dict(n_tokens_global=n_tok, b_global=b_glob, row0=parallel.row0_of(self.rank, self.nranks, b_glob))
+            if self.pipelined:
                 # submit(n+1) before wait(n): the host plan + H2D of this step overlap the device's previous step
-                h.train_step_submit(src, tgt)
+                h.train_step_submit(src, tgt, **kw)
                 self._inflight += 1
                 if self._inflight == 2:
                     self._last_stats = h.train_step_wait()
                     self._inflight -= 1
             else:
                 self._drain()
-                self._last_stats = h.train_step(src, tgt)
+                self._last_stats = h.train_step(src, tgt, **kw)
             vals['train_step'] = None
             return vals
         self._drain()

@@ -31,3 +31,29 @@ def shard_batch(src, tgt, nranks, rank, eos=1):
     s = np.ascontiguousarray(s[:, :max(1, int(ls[rows].max()))])
     t = np.ascontiguousarray(t[:, :max(1, int(lt[rows].max()))])
     return s, t, rows, int((lt + 1).sum()), int(len(src))
+
+
+def env_world():
+    """(nranks, rank, local_rank) of a `python -m torch.distributed.run` launch; (1, 0, 0) outside one."""
+    import os
+    n = int(os.environ.get('WORLD_SIZE', '1'))
+    if n <= 1:
+        return 1, 0, 0
+    return n, int(os.environ['RANK']), int(os.environ.get('LOCAL_RANK', os.environ['RANK']))
+
+
+def exchange_nccl_id(make_id, nranks, rank):
+    """rank 0 draws the NCCL unique id (`make_id()` -> 128 bytes), every rank returns it.  The hand-over runs over a
+    torch.distributed gloo group on the launcher's MASTER_ADDR / MASTER_PORT rendezvous: host plumbing only, the
+    gradients never travel this way (the library all-reduces them with NCCL over NVLink)."""
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        dist.init_process_group('gloo', rank=rank, world_size=nranks)
+    obj = [make_id() if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    return bytes(obj[0])
+
+
+def row0_of(rank, nranks, b_global):
+    """offset of a rank's rows in the RNG keying of word dropout / eps (distinct streams per rank)."""
+    return rank * ((b_global + nranks - 1) // nranks)

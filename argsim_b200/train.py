@@ -9,6 +9,8 @@ Differences from the reference, all outside the hot path: summaries go to `<log>
 TensorBoard event file; checkpoints use the library's own container; `--profile` brackets one
 validation forward pass with cudaProfilerStart/Stop-friendly warm-ups and prints per-phase
 device times instead of writing a TF RunMetadata.  `--precision fp32` selects the validation mode.
+Launched as `python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 -m argsim_b200.train ...`
+the same loop trains data parallel on N GPUs (rows of every batch sharded, gradients all-reduced by the library).
 """
 import argparse
 import json
@@ -71,7 +73,9 @@ def main(argv=None):
     A = parse(argv)
     if not A.rounds and not A.profile:
         sys.exit("nothing to do")
-    os.environ['CUDA_VISIBLE_DEVICES'] = A.gpu
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world == 1:
+        os.environ['CUDA_VISIBLE_DEVICES'] = A.gpu   # src/train.py:14,26; under torch.distributed.run every rank takes GPU LOCAL_RANK
 
     import numpy as np
     from . import model as M
@@ -107,11 +111,18 @@ def main(argv=None):
         if not A.rounds:
             sys.exit("profiling done")
 
-    os.makedirs(os.path.expanduser(P.log), exist_ok=True)
-    os.makedirs(os.path.expanduser(P.ckpt), exist_ok=True)
-    log = open(pform(P.log, A.trial, '.jsonl'), 'a')
+    # data parallel (python -m torch.distributed.run --nproc-per-node N -m argsim_b200.train ...): every rank runs this
+    # same loop on the same batch stream and trains on its rows of each batch (Session.run shards them); T.batch_train is
+    # the GLOBAL batch. Rank 0 alone validates, logs and saves -- the weights are identical on every rank.
+    main_rank = sess.rank == 0
+    if main_rank:
+        os.makedirs(os.path.expanduser(P.log), exist_ok=True)
+        os.makedirs(os.path.expanduser(P.ckpt), exist_ok=True)
+    log = open(pform(P.log, A.trial, '.jsonl'), 'a') if main_rank else None
 
     def summ(step, model=model_valid):
+        if not main_rank:
+            return
         parts = [sess.run((model.errt_samp, model.loss_gen_samp, model.loss_kld_samp),
                           {model.src: valid[i:j], model.tgt: valid[i:j]})
                  for i, j in partition(len(valid), T.batch_valid, discard=False)]
@@ -131,8 +142,10 @@ def main(argv=None):
                 sess.run(model_train.train_step)
             step = sess.run(model_train.step)
             summ(step)
-        saver.save(sess, pform(P.ckpt, A.trial, step // 10000), write_meta_graph=False)
-    log.close()
+        if main_rank:
+            saver.save(sess, pform(P.ckpt, A.trial, step // 10000), write_meta_graph=False)
+    if log:
+        log.close()
 
 
 if __name__ == '__main__':

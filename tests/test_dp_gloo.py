@@ -67,3 +67,83 @@ def test_two_rank_shards_reduce_to_the_full_batch():
         p.join(60)
         assert p.exitcode == 0
     assert err < 1e-10, err
+
+
+# ---- the session / train driver side of data parallelism, with the device library stubbed out ------------------------
+class _FakeHandle:
+    """stands in for argsim_b200._lib.Handle: records what the session asks the library to do."""
+    made = []
+
+    def __init__(self, **kw):
+        self.kw, self.calls, self.step = kw, [], 0
+        _FakeHandle.made.append(self)
+
+    def set_seed(self, seed):
+        self.seed = seed
+
+    def train_step_submit(self, src, tgt, **kw):
+        self.calls.append((np.array(src), np.array(tgt), kw))
+        self.step += 1
+
+    def train_step_wait(self):
+        return dict(step=self.step)
+
+    def close(self):
+        pass
+
+
+def test_session_shards_every_batch_under_torchrun(monkeypatch):
+    """Session() inside a torch.distributed.run launch: device = LOCAL_RANK, the NCCL id comes from rank 0, and every
+    sess.run(train_step) hands the library this rank's rows with the GLOBAL normalisers."""
+    from argsim_b200 import _lib, model as M, parallel
+    M.reset()
+    monkeypatch.setenv('WORLD_SIZE', '2')
+    monkeypatch.setenv('RANK', '1')
+    monkeypatch.setenv('LOCAL_RANK', '1')
+    monkeypatch.setattr(_lib, 'Handle', _FakeHandle)
+    monkeypatch.setattr(parallel, 'exchange_nccl_id', lambda make, n, r: b'\x07' * 128)
+    _FakeHandle.made.clear()
+    cfg = dict(dim_tgt=64, dim_emb=16, dim_rep=24, rnn_layers=2)
+    m = M.vAe('train', **cfg)
+    sess = M.Session()
+    h = _FakeHandle.made[-1]
+    assert (h.kw['nranks'], h.kw['rank'], h.kw['device'], h.kw['nccl_id']) == (2, 1, 1, b'\x07' * 128)
+    src = ragged_batch(10, 9, 64, 1)
+    tgt = ragged_batch(10, 8, 64, 2)
+    for _ in range(3):
+        sess.run(m.train_step, {m.src: src, m.tgt: tgt})
+    assert len(h.calls) == 3
+    s, t, kw = h.calls[0]
+    es, et, rows, n_glob, b_glob = parallel.shard_batch(src, tgt, 2, 1)
+    np.testing.assert_array_equal(s, es)
+    np.testing.assert_array_equal(t, et)
+    assert kw == dict(n_tokens_global=n_glob, b_global=10, row0=5)
+    other = parallel.shard_batch(src, tgt, 2, 0)[2]
+    assert sorted(list(rows) + list(other)) == list(range(10))
+    assert sess.last_stats == dict(step=3)      # waits for the steps in flight
+    sess.close()
+    M.reset()
+
+
+def _id_worker(rank, world, port, q):
+    from argsim_b200 import parallel
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), WORLD_SIZE=str(world), RANK=str(rank), LOCAL_RANK=str(rank))
+    assert parallel.env_world() == (world, rank, rank)
+    got = parallel.exchange_nccl_id(lambda: bytes(range(128)), world, rank)     # only rank 0's maker may be used
+    q.put((rank, got == bytes(range(128))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_nccl_id_hand_over_between_two_ranks():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_id_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}

@@ -1,0 +1,21 @@
+#!/bin/bash
+# First GPU call of the next round: knobs of the side-stream schedule that were set with one measurement each
+# (DESIGN.md section 6 / A/B table), swept on one box so that box class does not blur the comparison.  ~15 s per line.
+mkdir -p gpurun_out
+run() {
+timeout 300 python bench.py --steps 40 --warmup 3 --no-cpu-baseline > gpurun_out/next_bench.json 2> gpurun_out/next_bench.err || tail -3 gpurun_out/next_bench.err
+python - <<PY
+import json
+d=json.loads(open('gpurun_out/next_bench.json').read().strip().splitlines()[-1])
+k=d['kernels']
+print('$1 | ms %.3f | e2e %.3f | enc_bwd %.3f (gru %.3f) dec_bwd %.3f (gru %.3f) logits %.3f' % (d['ms_per_step'], d['e2e']['ms_per_step'],
+      d['phases_ms']['enc_bwd'], k['gru_bwd_enc']['ms_per_step'], d['phases_ms']['dec_bwd'], k['gru_bwd_dec']['ms_per_step'], d['phases_ms']['logits_ce']))
+PY
+}
+run "default                 "
+for u in 16 24 48 64; do ARGSIM_SIDE_UNITS=$u run "side units $u           "; done
+for e in 128 205 256; do ARGSIM_ENC_SEG=$e run "enc seg $e             "; done
+for d in 48 96; do ARGSIM_DEC_SEG=$d run "dec seg $d              "; done
+ARGSIM_LOGIT_CHUNK=2048 run "logit chunk 2048        "
+ARGSIM_LOGIT_CHUNK=8192 run "logit chunk 8192        "
+run "default                 "

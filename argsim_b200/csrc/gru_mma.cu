@@ -424,6 +424,9 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd2(const __grid_constant__
     // compile-time A/B switches (OPT): 1 step tables one step ahead, 2 fine profile marks, 4 k-tile-major LL layout,
     // 8 re-poll only the missing words, 16 next step's gx staged in shared memory by cp.async
     constexpr bool rowmaj = !(OPT & 4), repoll_all = !(OPT & 8), stage_gx = (OPT & 16) != 0;
+    // OPT & 128: rows of a slice in chunks of 8 instead of 16. A 16-row slice then runs as two one-tile chunks per step
+    // whose exchanges alternate: chunk 0's publish travels while chunk 1 computes and vice versa, so no poll waits.
+    constexpr int CW = (OPT & 128) ? 8 : CH;
 
     // ---- R slice -> registers (A fragments): local row lr = gate*32 + unit <-> R row gate*H + 32c + unit; k in [64w, 64w+64)
     uint32_t a[6][4][4];
@@ -477,15 +480,15 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd2(const __grid_constant__
         const unsigned tag = P.tag_base + (unsigned)(k - 1), tagw = P.tag_base + (unsigned)k;
         const unsigned long long* Xr = X + (size_t)((k - 1) & 1) * xpar;
         unsigned long long* Xw = X + (size_t)(k & 1) * xpar;
-        for (int ch = 0; ch * CH < na; ++ch) {
-            const int nrows = min(CH, na - ch * CH);
+        for (int ch = 0; ch * CW < na; ++ch) {
+            const int nrows = min(CW, na - ch * CW);
             const int ntl = nrows > 8 ? 2 : 1;   // n=8 MMA tiles that hold live rows (warp-uniform)
             // ---------------- operand fetch: B fragments of h_{t-1} for this warp's 64 k, rows g4 (+8)
             uint32_t b[2][4][2];
             if (first) {
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
-                    const int jl = ch * CH + nt * 8 + g4;
+                    const int jl = ch * CW + nt * 8 + g4;
                     const float* hp = (A.h0 && nt < ntl && jl < na) ? A.h0 + (size_t)(jl * ns + sl) * HH + 64 * warp + 2 * q4 : nullptr;
 #pragma unroll
                     for (int kt = 0; kt < 4; ++kt) {
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd2(const __grid_constant__
                 const unsigned long long* src[2];
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt) {
-                    const int jl = ch * CH + nt * 8 + g4;
+                    const int jl = ch * CW + nt * 8 + g4;
                     need[nt] = nt < ntl && jl < npoll;   // rows >= npoll join here with zero state (reverse direction)
                     src[nt] = rowmaj ? Xr + ((size_t)jl * 32 + 4 * warp) * 8 + 2 * q4 : Xr + ((size_t)(4 * warp) * P.bslr + jl) * 8 + 2 * q4;
                 }
@@ -553,7 +556,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd2(const __grid_constant__
                 const int n = warp + 8 * e;
                 gxv[e][0] = gxv[e][1] = gxv[e][2] = 0.f;
                 if (n < nrows && !from_smem) {
-                    const float* gp = A.gx + (size_t)(row_base + (long long)(ch * CH + n) * ns + sl) * A.ld_gx + col;
+                    const float* gp = A.gx + (size_t)(row_base + (long long)(ch * CW + n) * ns + sl) * A.ld_gx + col;
                     gxv[e][0] = ld_f32(gp); gxv[e][1] = ld_f32(gp + HH); gxv[e][2] = ld_f32(gp + 2 * HH);
                 }
             }
@@ -608,7 +611,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd2(const __grid_constant__
                     const float z = sigm(gxv[e][1] + s1 + bRu);
                     const float qq = s2 + bRn;
                     const float nn = tanh_fast(gxv[e][2] + r * qq);
-                    const int jl = ch * CH + n;
+                    const int jl = ch * CW + n;
                     const float hp = hst[jl * UN + lane];
                     const float h = (1.f - z) * nn + z * hp;
                     const __nv_bfloat16 hb16 = __float2bfloat16(h);
@@ -652,8 +655,15 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_fwd2(const __grid_constant__
                     }
                 }
             }
+            if ((OPT & 128) && (P.variant & 2) && k + 2 < P.Tseg) {
+                // 8-row chunks keep every warp busy: each warp prefetches the gx row it will finish two steps ahead itself
+                const int tn = A.reverse ? t - 2 : t + 2;
+                const int n = ch * CW + warp;
+                if (n < NA(tn) && lane < 3)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(A.gx + (size_t)(OFF(tn) + (long long)n * ns + sl) * A.ld_gx + UN * c + lane * HH));
+            }
             // gx rows of the step after next -> L2, by the warps that have no row to finish in this chunk
-            if ((P.variant & 2) && ch == 0 && warp >= nrows && k + 2 < P.Tseg) {
+            if (!(OPT & 128) && (P.variant & 2) && ch == 0 && warp >= nrows && k + 2 < P.Tseg) {
                 const int tn = A.reverse ? t - 2 : t + 2;
                 const int nan = NA(tn);
                 const long long rbn = OFF(tn);
@@ -687,6 +697,9 @@ __device__ __forceinline__ size_t yidx(int par, int dest, int src, int pair, int
     return ((((size_t)par * CL + dest) * CL + src) * npair + pair) * UN + ul;
 }
 
+// CW = rows per chunk: 16 (two n=8 MMA tiles per chunk) or 8 (one tile; a 16-row slice then runs as two chunks per step
+// whose reduce-scatter rounds alternate, each one's exchange in flight while the other computes)
+template <int CW>
 __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ BwdP P) {
     extern __shared__ __align__(16) unsigned char sm[];
     bf16* Gs0 = reinterpret_cast<bf16*>(sm);                              // [2][CH][GS_LD] own dgh columns of the chunk (double
@@ -768,8 +781,8 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
         const unsigned tagr = P.tag_base + (unsigned)(k - 1), tagw = P.tag_base + (unsigned)k;
         const int parr = (k - 1) & 1, parw = k & 1;
         const long long row_base = OFF(t);
-        for (int ch = 0; ch * CH < na; ++ch) {
-            const int nrows = min(CH, na - ch * CH);
+        for (int ch = 0; ch * CW < na; ++ch) {
+            const int nrows = min(CW, na - ch * CW);
             const int ntl = nrows > 8 ? 2 : 1;
             // ---- reduce-scatter receive: partial sums of R^T.dgh for my unit and rows (w, w+8) from all 16 CTAs.
             // A word carries rows (2p, 2p+1) of one source; row n lives in pair n>>1, half n&1.
@@ -777,8 +790,8 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int n = warp + 8 * e;
-                if (n < nrows && ch * CH + n < ncarry) {
-                    const int pair = ch * 8 + (n >> 1);
+                if (n < nrows && ch * CW + n < ncarry) {
+                    const int pair = ch * (CW / 2) + (n >> 1);
                     uint2 w[CL];
                     bool ok;
                     const long long t0 = clock64();
@@ -812,7 +825,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
                 if (e >= ntl) continue;
                 float dr = 0.f, du = 0.f, dnr = 0.f;
                 if (n < nrows) {
-                    const int jl = ch * CH + n;
+                    const int jl = ch * CW + n;
                     const size_t row = (size_t)(row_base + (long long)jl * ns + sl);
                     const float carry = cs[jl * UN + lane] + (jl < ncarry ? pin[e] : 0.f);
                     float dhv, r, z, nn, qq, hp = 0.f;
@@ -882,7 +895,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
                 for (int nt = 0; nt < 2; ++nt) {
                     if (nt >= ntl) continue;
                     const int o0 = 64 * warp + 16 * mt + g4, o1 = o0 + 8;
-                    const int pair = ch * 8 + nt * 4 + q4;
+                    const int pair = ch * (CW / 2) + nt * 4 + q4;
                     ll_store(Y + yidx(parw, o0 >> 5, c, pair, o0 & 31, npair), bf16_bits(acc[mt][nt][0]) | (bf16_bits(acc[mt][nt][1]) << 16), tagw);
                     ll_store(Y + yidx(parw, o1 >> 5, c, pair, o1 & 31, npair), bf16_bits(acc[mt][nt][2]) | (bf16_bits(acc[mt][nt][3]) << 16), tagw);
                 }
@@ -915,7 +928,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int n = warp + 8 * e;
-                        if (n < naq) {
+                        if (n < naq && n < CW) {
                             const size_t rq = (size_t)(rbq + (long long)n * ns + sl);
                             float* d = stg + ((pq * CH + n) * 5) * UN + lane;
                             cp_async4(d, A.dhs + rq * A.ld_dhs + col);
@@ -966,13 +979,13 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_mma_bwd(const __grid_constant__ 
     if (dh_dst && k_last >= 0) {
         const unsigned tagr = P.tag_base + (unsigned)k_last;
         const int parr = k_last & 1;
-        for (int ch = 0; ch * CH < na_prev; ++ch) {
+        for (int ch = 0; ch * CW < na_prev; ++ch) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int n = warp + 8 * e;
-                const int jl = ch * CH + n;
-                if (jl >= na_prev) continue;
-                const int pair = ch * 8 + (n >> 1);
+                const int jl = ch * CW + n;
+                if (n >= CW || jl >= na_prev) continue;
+                const int pair = ch * (CW / 2) + (n >> 1);
                 float pin = 0.f;
 #pragma unroll
                 for (int s0 = 0; s0 < CL; s0 += 8) {
@@ -1015,6 +1028,7 @@ struct GruMmaCtx {
     int pad_groups = 8;          // launches that have the chip to themselves are padded to 8 groups = 128 blocks: the block
                                  // dispatcher spreads a 128-block grid over all GPCs (2 CTAs of a group per GPC), a small grid
                                  // is packed into one or two GPCs and its exchange round is ~27 % slower (xbench, profiles/)
+    bool chunk8 = false;         // ARGSIM_GRU_CHUNK=8: 8-row chunks (one MMA tile each) in both kernels
     bool fwd_v1 = false;         // ARGSIM_GRU_FWD_V1=1: the first forward kernel (smem-staged operands), for A/B runs
     long long* prof = nullptr;   // ARGSIM_GRU_PROF=1: per-phase clocks, printed to stderr after every launch
 };
@@ -1032,11 +1046,16 @@ GruMmaCtx* gru_mma_create(int device) {
         CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
         CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
         CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_fwd2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2_smem));
         if (const char* v = getenv("ARGSIM_GRU_FWD2_OPT")) c->fwd2_opt = atoi(v);
     }
     c->fwd_v1 = getenv("ARGSIM_GRU_FWD_V1") != nullptr;
     if (const char* v = getenv("ARGSIM_GRU_PAD")) c->pad_groups = atoi(v);
-    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH * GS_LD * 2 + MAX_BSL * UN * 4 + 2 * 4100 * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_bwd<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH * GS_LD * 2 + MAX_BSL * UN * 4 + 2 * 4100 * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_mma_bwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CH * GS_LD * 2 + MAX_BSL * UN * 4 + 2 * 4100 * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2));
+    // ARGSIM_GRU_CHUNK=8 (A/B, not measured yet): both kernels walk a slice in chunks of 8 rows (see k_gru_mma_bwd)
+    if (const char* v = getenv("ARGSIM_GRU_CHUNK")) c->chunk8 = atoi(v) == 8;
+    if (c->chunk8 && c->fwd2_opt == 0) c->fwd2_opt = 128;
     if (const char* v = getenv("ARGSIM_GRU_VARIANT")) { c->variant_fwd = atoi(v) & 7; c->variant_bwd = (atoi(v) >> 3) & 7; }
     if (const char* v = getenv("ARGSIM_GRU_FWD2_VARIANT")) c->variant_fwd = atoi(v);
     if (getenv("ARGSIM_GRU_PROF")) CUDA_CHECK(cudaMalloc(&c->prof, 160 * 8 * sizeof(long long)));
@@ -1130,7 +1149,8 @@ void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& 
                                   : (size_t)2 * KW * CH * RED_LD * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 2 * CH * 3 * UN * 4;
     void* args[] = {&P};
     void* fwd2_fn = c->fwd2_opt == 2 ? (void*)k_gru_mma_fwd2<2> : c->fwd2_opt == 12 ? (void*)k_gru_mma_fwd2<12>
-                  : c->fwd2_opt == 16 ? (void*)k_gru_mma_fwd2<16> : (void*)k_gru_mma_fwd2<0>;
+                  : c->fwd2_opt == 16 ? (void*)k_gru_mma_fwd2<16> : c->fwd2_opt == 128 ? (void*)k_gru_mma_fwd2<128>
+                  : (void*)k_gru_mma_fwd2<0>;
     const int grid_groups = (!c->fwd_v1 && pad) ? std::max(groups, c->pad_groups) : groups;
     if (pad == 2 && !c->fwd_v1) {
         // padded launch next to other recurrence launches (wavefront / segment chains): a cooperative launch would wait for
@@ -1181,9 +1201,10 @@ void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& 
     const size_t smem = (size_t)2 * CH * GS_LD * 2 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2;
     void* args[] = {&P};
     const int grid_groups = pad ? std::max(groups, c->pad_groups) : groups;
-    if (pad == 2) CUDA_CHECK(cudaLaunchKernel((void*)k_gru_mma_bwd, dim3(grid_groups * CL), dim3(NTH), args, smem, s));   // see gru_mma_fwd
+    void* bwd_fn = c->chunk8 ? (void*)k_gru_mma_bwd<8> : (void*)k_gru_mma_bwd<CH>;
+    if (pad == 2) CUDA_CHECK(cudaLaunchKernel(bwd_fn, dim3(grid_groups * CL), dim3(NTH), args, smem, s));   // see gru_mma_fwd
     else
-    CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gru_mma_bwd, dim3(grid_groups * CL), dim3(NTH), args, smem, s));
+    CUDA_CHECK(cudaLaunchCooperativeKernel(bwd_fn, dim3(grid_groups * CL), dim3(NTH), args, smem, s));
     COUNT_LAUNCH();
     dump_prof(c, ndir == 2 ? "bwd_enc" : "bwd_dec", groups * CL, Tseg, s);
 }

@@ -13,6 +13,13 @@ print('$1 | ms %.3f | e2e %.3f | enc_bwd %.3f (gru %.3f) dec_bwd %.3f (gru %.3f)
 PY
 }
 run "default                 "
+# untested at the end of round 1 (GPU budget spent): 8-row chunks, a 16-row slice = two alternating one-tile exchanges.
+# Run the parity tests with it FIRST; if green, compare and then retry the slice budgets with 16-row slices everywhere.
+ARGSIM_GRU_CHUNK=8 timeout 600 python -m pytest tests/test_gpu_bf16.py tests/test_gpu_fullsize.py -m gpu -x -q 2>&1 | tail -3
+ARGSIM_GRU_CHUNK=8 run "chunk 8                 "
+ARGSIM_GRU_CHUNK=8 ARGSIM_NO_SLICE_BUDGET=1 run "chunk 8, 16-row slices  "
+ARGSIM_GRU_CHUNK=8 ARGSIM_NO_SLICE_BUDGET=1 ARGSIM_ENC_SEG=0 run "chunk 8, no enc segments"
+ARGSIM_GRU_CHUNK=8 ARGSIM_GROUP_CAP=6 run "chunk 8, 6 groups       "
 for u in 16 24 48 64; do ARGSIM_SIDE_UNITS=$u run "side units $u           "; done
 for e in 128 205 256; do ARGSIM_ENC_SEG=$e run "enc seg $e             "; done
 for d in 48 96; do ARGSIM_DEC_SEG=$d run "dec seg $d              "; done

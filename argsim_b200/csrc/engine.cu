@@ -55,6 +55,7 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     if (const char* ev = getenv("ARGSIM_GROUP_CAP")) group_cap = atoi(ev);
     if (const char* ev = getenv("ARGSIM_SIDE_UNITS")) side_units = atoi(ev);
     if (const char* ev = getenv("ARGSIM_DEC_EARLY")) dec_early_on = atoi(ev);
+    if (const char* ev = getenv("ARGSIM_ENC_BWD_CHUNK")) enc_bwd_chunk = atoi(ev);
     slice_budget = getenv("ARGSIM_NO_SLICE_BUDGET") == nullptr;
     early_adam = getenv("ARGSIM_NO_EARLY_ADAM") == nullptr;
     seg_wgrad_on = getenv("ARGSIM_NO_SEG_WGRAD") == nullptr;
@@ -1087,7 +1088,7 @@ void Engine::program(int mode, bool apply_update) {
                         GruBwdArgs x = a[d];
                         x.dh_in = (k > 0) ? carry[d][(k - 1) & 1] : nullptr;
                         x.dh_out = (k + 1 < nsegE) ? carry[d][k & 1] : nullptr;
-                        gru_mma_bwd(mma, &x, 1, E, dp.enc_off, dp.enc_nact, H, sw[d], t0, tl, d, want8[(size_t)d * nsegE + k], pad_wave);
+                        gru_mma_bwd(mma, &x, 1, E, dp.enc_off, dp.enc_nact, H, sw[d], t0, tl, d, want8[(size_t)d * nsegE + k], pad_wave, enc_bwd_chunk);
                         if (seg_wgrad) {
                             // the segment's rows of d gates are final: their share of the weight / bias gradients goes to
                             // the side stream now, so only the last segment's share is left when the chains end

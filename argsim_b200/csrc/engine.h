@@ -98,6 +98,8 @@ private:
                                                         // run on the SMs the recurrence launches of the layer below leave free
     int group_cap = 0;                                  // ARGSIM_GROUP_CAP: groups of 16 CTAs the slice planners may use (0 = 9, or 8 under data parallel)
     int side_units = 32;                                // ARGSIM_SIDE_UNITS: k-blocks per work unit of the side stream's GEMMs (0 = persistent CTAs; 32: 10.50 -> 10.41 ms/step)
+    int enc_bwd_chunk = 0;                              // ARGSIM_ENC_BWD_CHUNK=8: 8-row chunks in the encoder's BPTT segment launches only (one measurement at the end
+                                                        // of round 1: encoder BPTT 3.56 -> 3.36 ms; the decoder wavefront is slower with them: 1.33 -> 1.42 / 1.86 -> 1.92 ms)
     int dec_early_on = 1;                               // ARGSIM_DEC_EARLY=0: decoder layer-0 gather + projection on the main stream after the encoder (10.66 vs 10.64 ms/step)
     bool slice_budget = true;                           // ARGSIM_NO_SLICE_BUDGET: every wavefront launch takes 16-row slices
     bool early_adam = true;                             // ARGSIM_NO_EARLY_ADAM: one Adam launch after the last gradient

@@ -1165,7 +1165,7 @@ void gru_mma_fwd(GruMmaCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& 
 }
 
 void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& Pl, const int* d_off, const int* d_nact, int H,
-                 cudaStream_t s, int t0, int Tseg, int slot, int alone, int pad) {
+                 cudaStream_t s, int t0, int Tseg, int slot, int alone, int pad, int chunk) {
     if (H != HH) throw std::runtime_error("gru_mma: H must be 512");
     if (Tseg < 0) { t0 = 0; Tseg = Pl.Tmax; }
     if (Tseg >= 4096) throw std::runtime_error("gru_mma: more than 4095 steps per launch");
@@ -1201,7 +1201,7 @@ void gru_mma_bwd(GruMmaCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& 
     const size_t smem = (size_t)2 * CH * GS_LD * 2 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 2 * CH * 5 * UN * 4 + 2 * CH * UN * 2;
     void* args[] = {&P};
     const int grid_groups = pad ? std::max(groups, c->pad_groups) : groups;
-    void* bwd_fn = c->chunk8 ? (void*)k_gru_mma_bwd<8> : (void*)k_gru_mma_bwd<CH>;
+    void* bwd_fn = (chunk == 8 || (chunk == 0 && c->chunk8)) ? (void*)k_gru_mma_bwd<8> : (void*)k_gru_mma_bwd<CH>;
     if (pad == 2) CUDA_CHECK(cudaLaunchKernel(bwd_fn, dim3(grid_groups * CL), dim3(NTH), args, smem, s));   // see gru_mma_fwd
     else
     CUDA_CHECK(cudaLaunchCooperativeKernel(bwd_fn, dim3(grid_groups * CL), dim3(NTH), args, smem, s));

@@ -109,7 +109,8 @@ bool gru_mma_fits(const GruMmaCtx*, int ndir, int b);   // batch small enough fo
 // steps [t0, t0+Tseg) (Tseg < 0: the whole plan); launches that may overlap in time need different slots (0..3)
 void gru_mma_fwd(GruMmaCtx*, const GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
                  int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0, int alone = 0, int pad = 0);
+// chunk: rows per chunk of this launch, 0 = the context's default (16, or 8 with ARGSIM_GRU_CHUNK=8), 8, 16
 void gru_mma_bwd(GruMmaCtx*, const GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
-                 int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0, int alone = 0, int pad = 0);
+                 int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0, int alone = 0, int pad = 0, int chunk = 0);
 // xbench.cu: exchange-latency measurement hook
 int xbench_run(int device, int method, int groups, int rows, int iters, double* cycles_per_iter, int* max_clusters);

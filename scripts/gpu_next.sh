@@ -13,9 +13,11 @@ print('$1 | ms %.3f | e2e %.3f | enc_bwd %.3f (gru %.3f) dec_bwd %.3f (gru %.3f)
 PY
 }
 run "default                 "
-# untested at the end of round 1 (GPU budget spent): 8-row chunks, a 16-row slice = two alternating one-tile exchanges.
+# one A/B at the end of round 1 (enc BPTT 3.56 -> 3.36 ms, decoder slower): 8-row chunks, a 16-row slice = two alternating one-tile exchanges.
 # Run the parity tests with it FIRST; if green, compare and then retry the slice budgets with 16-row slices everywhere.
 ARGSIM_GRU_CHUNK=8 timeout 600 python -m pytest tests/test_gpu_bf16.py tests/test_gpu_fullsize.py -m gpu -x -q 2>&1 | tail -3
+ARGSIM_ENC_BWD_CHUNK=8 timeout 600 python -m pytest tests/test_gpu_bf16.py tests/test_gpu_fullsize.py -m gpu -x -q 2>&1 | tail -3
+ARGSIM_ENC_BWD_CHUNK=8 run "chunk 8 in enc BPTT only"
 ARGSIM_GRU_CHUNK=8 run "chunk 8                 "
 ARGSIM_GRU_CHUNK=8 ARGSIM_NO_SLICE_BUDGET=1 run "chunk 8, 16-row slices  "
 ARGSIM_GRU_CHUNK=8 ARGSIM_NO_SLICE_BUDGET=1 ARGSIM_ENC_SEG=0 run "chunk 8, no enc segments"

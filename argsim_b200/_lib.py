@@ -55,6 +55,7 @@ SIGNATURES = {
     'argsim_train_step_submit': (C.c_int, [C.c_void_p, _i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, _u8p, _f32p, C.c_int64,
                                            C.c_int64, C.c_int64]),
     'argsim_train_step_wait': (C.c_int, [C.c_void_p, C.POINTER(StepStats)]),
+    'argsim_set_global_rows': (C.c_int, [C.c_void_p, _i64p, C.c_int32]),
     'argsim_eval_step': (C.c_int, [C.c_void_p, _i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, C.c_int64,
                                    _f32p, _i64p, _i32p]),
     'argsim_embed': (C.c_int, [C.c_void_p, _i32p, C.c_int32, C.c_int32, _f32p]),
@@ -65,6 +66,7 @@ SIGNATURES = {
     'argsim_load': (C.c_int, [C.c_void_p, C.c_char_p]),
     'argsim_bench_resident': (C.c_int, [C.c_void_p, C.c_int32, _f32p]),
     'argsim_launch_count': (C.c_int, [C.c_void_p, _i64p]),
+    'argsim_profiler': (C.c_int, [C.c_void_p, C.c_int32]),
     'argsim_last_timings': (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), _f32p]),
     'argsim_test_gemm': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p,
                                    _f32p, _f32p, C.c_float, C.c_int32, _f32p, _f32p]),
@@ -293,11 +295,16 @@ class Handle:
         self._ck(self.L.argsim_set_seed(self.h, int(seed)))
 
     # ---- steps ------------------------------------------------------------------------
-    def _step(self, fn, src, tgt, keep, eps, n_tokens_global, b_global, row0, stats=True):
+    def _step(self, fn, src, tgt, keep, eps, n_tokens_global, b_global, row0, stats=True, rows=None):
         src, tgt = _tokens(src, 'src'), _tokens(tgt, 'tgt')
         if src.shape[0] != tgt.shape[0]:
             raise ValueError('src and tgt must have the same number of rows')
         b = src.shape[0]
+        if rows is not None:   # global row indices: RNG keying invariant to the sharding (argsim_set_global_rows)
+            rows = np.ascontiguousarray(rows, np.int64)
+            if rows.shape != (b,):
+                raise ValueError('rows must hold one global row index per batch row')
+            self._ck(self.L.argsim_set_global_rows(self.h, _p(rows, _i64p), b))
         if keep is not None:
             keep = np.ascontiguousarray(keep, np.uint8)
             if keep.shape != tgt.shape:
@@ -315,12 +322,12 @@ class Handle:
                     n_tokens_global, b_global, row0, C.byref(st)))
         return {k: getattr(st, k) for k, _ in StepStats._fields_}
 
-    def train_step(self, src, tgt, keep=None, eps=None, n_tokens_global=0, b_global=0, row0=0):
-        return self._step(self.L.argsim_train_step, src, tgt, keep, eps, n_tokens_global, b_global, row0)
+    def train_step(self, src, tgt, keep=None, eps=None, n_tokens_global=0, b_global=0, row0=0, rows=None):
+        return self._step(self.L.argsim_train_step, src, tgt, keep, eps, n_tokens_global, b_global, row0, rows=rows)
 
-    def train_step_submit(self, src, tgt, keep=None, eps=None, n_tokens_global=0, b_global=0, row0=0):
+    def train_step_submit(self, src, tgt, keep=None, eps=None, n_tokens_global=0, b_global=0, row0=0, rows=None):
         """enqueue one training step and return (the arrays are not referenced afterwards); at most two un-waited steps."""
-        self._step(self.L.argsim_train_step_submit, src, tgt, keep, eps, n_tokens_global, b_global, row0, stats=False)
+        self._step(self.L.argsim_train_step_submit, src, tgt, keep, eps, n_tokens_global, b_global, row0, stats=False, rows=rows)
 
     def train_step_wait(self):
         """statistics of the oldest un-waited step (blocks until it has finished on the device)."""
@@ -328,8 +335,8 @@ class Handle:
         self._ck(self.L.argsim_train_step_wait(self.h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in StepStats._fields_}
 
-    def grad_step(self, src, tgt, keep=None, eps=None, n_tokens_global=0, b_global=0, row0=0):
-        return self._step(self.L.argsim_grad_step, src, tgt, keep, eps, n_tokens_global, b_global, row0)
+    def grad_step(self, src, tgt, keep=None, eps=None, n_tokens_global=0, b_global=0, row0=0, rows=None):
+        return self._step(self.L.argsim_grad_step, src, tgt, keep, eps, n_tokens_global, b_global, row0, rows=rows)
 
     def eval_step(self, src, tgt, want_pred=False):
         src, tgt = _tokens(src, 'src'), _tokens(tgt, 'tgt')
@@ -391,6 +398,10 @@ class Handle:
         n = C.c_int64()
         self._ck(self.L.argsim_launch_count(self.h, C.byref(n)))
         return n.value
+
+    def profiler(self, on):
+        """cudaProfilerStart/Stop + NVTX ranges around the device programs (train.py --profile)."""
+        self._ck(self.L.argsim_profiler(self.h, int(bool(on))))
 
     def last_timings(self):
         names = (C.c_char_p * 256)()

@@ -24,10 +24,24 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """compiles and links under an exclusive file lock (several ranks of one torchrun launch may get here at once);
+    the library is linked to a temporary name and moved into place atomically."""
+    import fcntl
     if not force and not needs_build():
         return LIB
     objdir = os.path.join(HERE, 'build')
     os.makedirs(objdir, exist_ok=True)
+    with open(os.path.join(objdir, '.lock'), 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():   # another process built it while this one waited
+                return LIB
+            return _build_locked(objdir, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(objdir, verbose):
 
     def cc(src):
         obj = os.path.join(objdir, os.path.splitext(src)[0] + '.o')
@@ -41,11 +55,15 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(cc, SOURCES))
-    cmd = [NVCC, '-shared', '-o', LIB] + objs + ['-Xcompiler', '-fPIC', '-ldl', '-cudart', 'static',
+    tmp = LIB + '.tmp.%d' % os.getpid()
+    cmd = [NVCC, '-shared', '-o', tmp] + objs + ['-Xcompiler', '-fPIC', '-ldl', '-cudart', 'static',
                                                   '-gencode', 'arch=compute_100a,code=sm_100a']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -2,6 +2,7 @@
 // sizes only; every entry point catches C++ exceptions and turns them into a status + message.
 #include "engine.h"
 #include "nccl_dyn.h"
+#include <cuda_profiler_api.h>
 #include <string.h>
 #include <mutex>
 
@@ -141,6 +142,11 @@ int argsim_train_step_submit(argsim_handle* h, const int32_t* src, const int32_t
     h->e->train_step_submit(src, tgt, b, T_src, T_tgt, keep_mask, eps, n_tokens_global, b_global, row0_global, true);
     API_END(h)
 }
+int argsim_set_global_rows(argsim_handle* h, const int64_t* rows, int32_t b) {
+    API_BEGIN_NODRAIN(h)
+    h->e->set_global_rows(rows, b);
+    API_END(h)
+}
 int argsim_train_step_wait(argsim_handle* h, argsim_step_stats* out) {
     API_BEGIN_NODRAIN(h)
     h->e->train_step_wait(out);
@@ -192,6 +198,18 @@ int argsim_bench_resident(argsim_handle* h, int32_t iters, float* ms_per_step) {
 }
 int argsim_launch_count(argsim_handle* h, int64_t* n) {
     API_BEGIN(h) *n = g_launch_count;
+    API_END(h)
+}
+int argsim_profiler(argsim_handle* h, int32_t on) {
+    API_BEGIN(h)
+    CUDA_CHECK(cudaDeviceSynchronize());
+    if (on) {
+        h->e->nvtx = true;
+        CUDA_CHECK(cudaProfilerStart());
+    } else {
+        CUDA_CHECK(cudaProfilerStop());
+        h->e->nvtx = false;
+    }
     API_END(h)
 }
 int argsim_last_timings(argsim_handle* h, int32_t cap, const char** names, float* ms) {

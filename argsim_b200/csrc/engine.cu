@@ -1,6 +1,7 @@
 // engine.cu -- see engine.h.  Reference: src/model.py:75-189 (graph), src/train.py:104-121 (loops).
 #include "engine.h"
 #include "nccl_dyn.h"
+#include <nvtx3/nvToolsExt.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -122,13 +123,14 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     CUDA_CHECK(cudaMalloc(&g, nflat * sizeof(float)));
     CUDA_CHECK(cudaMalloc(&m, nflat * sizeof(float)));
     CUDA_CHECK(cudaMalloc(&v, nflat * sizeof(float)));
-    CUDA_CHECK(cudaMemset(p, 0, nflat * sizeof(float)));
-    CUDA_CHECK(cudaMemset(g, 0, nflat * sizeof(float)));
-    CUDA_CHECK(cudaMemset(m, 0, nflat * sizeof(float)));
-    CUDA_CHECK(cudaMemset(v, 0, nflat * sizeof(float)));
+    // on the engine's own stream: the work streams are cudaStreamNonBlocking and do not order against the legacy stream
+    CUDA_CHECK(cudaMemsetAsync(p, 0, nflat * sizeof(float), st[0]));
+    CUDA_CHECK(cudaMemsetAsync(g, 0, nflat * sizeof(float), st[0]));
+    CUDA_CHECK(cudaMemsetAsync(m, 0, nflat * sizeof(float), st[0]));
+    CUDA_CHECK(cudaMemsetAsync(v, 0, nflat * sizeof(float), st[0]));
     if (is_bf16) {
         CUDA_CHECK(cudaMalloc(&ph, nflat * sizeof(::bf16)));
-        CUDA_CHECK(cudaMemset(ph, 0, nflat * sizeof(::bf16)));
+        CUDA_CHECK(cudaMemsetAsync(ph, 0, nflat * sizeof(::bf16), st[0]));
     }
     CUDA_CHECK(cudaMalloc(&d_stats, 4 * sizeof(double)));
     CUDA_CHECK(cudaMallocHost(&h_stats, 4 * sizeof(double)));
@@ -206,8 +208,8 @@ void Engine::init_params(uint64_t seed_) {
         }
     }
     copy_sync(p, host.data(), nflat * sizeof(float), cudaMemcpyHostToDevice);
-    CUDA_CHECK(cudaMemset(m, 0, nflat * sizeof(float)));
-    CUDA_CHECK(cudaMemset(v, 0, nflat * sizeof(float)));
+    CUDA_CHECK(cudaMemsetAsync(m, 0, nflat * sizeof(float), st[0]));
+    CUDA_CHECK(cudaMemsetAsync(v, 0, nflat * sizeof(float), st[0]));
     refresh_shadow(0, nflat);
     CUDA_CHECK(cudaStreamSynchronize(st[0]));
     step = 0;
@@ -352,6 +354,7 @@ void Engine::phase(const char* name) {
         pnames.push_back("");
     }
     pnames[pcount] = name;
+    if (nvtx) nvtxMarkA((std::string("argsim:end:") + name).c_str());
     CUDA_CHECK(cudaEventRecord(pev[pcount], st[0]));
     ++pcount;
 }
@@ -419,8 +422,8 @@ void Engine::stage(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt
         if (x < 0 || x >= V) throw std::runtime_error("tgt token id out of range [0, dim_tgt)");
     for (int x : plan.labels)
         if (x < 0 || x >= V) throw std::runtime_error("eos/tgt token id out of range [0, dim_tgt)");
-    size_t need = plan.ids_src.size() + plan.ids_lead.size() + plan.labels.size() + 2 * (size_t)b + (E.Tmax + 1) + E.Tmax +
-                  (Dp.Tmax + 1) + Dp.Tmax + 64 * 9;
+    size_t need = plan.ids_src.size() + plan.ids_lead.size() + plan.labels.size() + 3 * (size_t)b + (E.Tmax + 1) + E.Tmax +
+                  (Dp.Tmax + 1) + Dp.Tmax + 64 * 10;
     if (need > stage_cap) {
         CUDA_CHECK(cudaDeviceSynchronize());
         cudaFreeHost(h_stage); cudaFree(d_stage);
@@ -446,6 +449,11 @@ void Engine::stage(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt
     put(E.nact, &dp.enc_nact);
     put(Dp.off, &dp.dec_off);
     put(Dp.nact, &dp.dec_nact);
+    {   // global row index per row: keys the eps stream on the device (the keep mask was drawn above, on the host)
+        std::vector<int> rid(b);
+        for (int i = 0; i < b; ++i) rid[i] = (int)(drop.rows ? drop.rows[i] : drop.row0 + i);
+        put(rid, &dp.row_ids);
+    }
     CUDA_CHECK(cudaMemcpyAsync(ds, hs, o * sizeof(int), cudaMemcpyHostToDevice, st[0]));
     have_eps = false;
     if (eps) {
@@ -484,7 +492,14 @@ void Engine::ensure_arena(int mode) {
 void Engine::run_device(int mode, bool apply_update) {
     ensure_arena(mode);
     pcount = 0; kcount = 0; evcount = 0;
-    program(mode, apply_update);
+    if (nvtx) nvtxRangePushA(mode == 2 ? "argsim:train_step" : mode == 1 ? "argsim:eval_step" : "argsim:embed");
+    try {
+        program(mode, apply_update);
+    } catch (...) {
+        if (nvtx) nvtxRangePop();
+        throw;
+    }
+    if (nvtx) nvtxRangePop();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -636,7 +651,7 @@ void Engine::program(int mode, bool apply_update) {
     float* eps_used = train ? (float*)arena.alloc(sizeof(float) * b * R) : nullptr;
     float* kld_samp = (float*)arena.alloc(sizeof(float) * b * R);
     outp.kld_samp = kld_samp;
-    RUN(launch_latent_fwd(mulv.f, have_eps ? d_eps_in : nullptr, b, R, train ? 1 : 0, seed, (uint64_t)step, last.row0, eps_used,
+    RUN(launch_latent_fwd(mulv.f, have_eps ? d_eps_in : nullptr, b, R, train ? 1 : 0, seed, (uint64_t)step, last.row0, dp.row_ids, eps_used,
                           z.f, z.h, kld_samp, d_stats, s));
     Mat hx = f32(b, D);
     gemm(z, 0, pmat("latent/ex/kernel"), 1, hx, b, D, R, 1.f, p + pinfo("latent/ex/bias").off, 0);
@@ -1199,7 +1214,15 @@ void Engine::train_step_submit(const int32_t* src, const int32_t* tgt, int b, in
     DropoutSpec drop;
     drop.train = 1; drop.keep = keep; drop.rate_keepwd = ps.keepwd; drop.seed = seed; drop.step = (uint64_t)step; drop.row0 = row0;
     last.train = 1; last.n_tok_global = n_tok_global; last.b_global = b_global; last.row0 = row0;
+    if (!next_rows.empty()) {
+        if ((int)next_rows.size() != b) {
+            next_rows.clear();
+            throw std::runtime_error("train step: argsim_set_global_rows was given another number of rows than this batch has");
+        }
+        drop.rows = next_rows.data();
+    }
     stage(src, tgt, b, Ts, Tt, 1, drop, eps);
+    next_rows.clear();
     run_device(2, apply_update);
     CUDA_CHECK(cudaMemcpyAsync(ps.h_stats, d_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st[0]));
     CUDA_CHECK(cudaEventRecord(ps.done, st[0]));   // the comm and side streams have joined the main stream by now
@@ -1229,6 +1252,16 @@ void Engine::train_step_wait(argsim_step_stats* out) {
         out->n_tokens = (int64_t)ps.n_glob;
         out->step = ps.step_after;
     }
+}
+
+void Engine::set_global_rows(const int64_t* rows, int b) {
+    next_rows.clear();
+    if (rows && b > 0) next_rows.assign(rows, rows + b);
+    for (int64_t r : next_rows)
+        if (r < 0 || r > 0x7fffffffLL) {
+            next_rows.clear();
+            throw std::runtime_error("global row indices must be in [0, 2^31)");
+        }
 }
 
 void Engine::drain() {

@@ -82,11 +82,16 @@ public:
     void train_step_submit(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt, const uint8_t* keep, const float* eps,
                            int64_t n_tok_global, int64_t b_global, int64_t row0, bool apply_update);
     void train_step_wait(argsim_step_stats* out);
+    // global row index of every row of the NEXT submitted train step (consumed by it): keys the Philox streams of word
+    // dropout and eps, so that un-injected randomness does not depend on how the batch is dealt over the ranks
+    void set_global_rows(const int64_t* rows, int b);
+    std::vector<int64_t> next_rows;
     void drain();   // every submitted step complete on the device (their statistics stay queued for train_step_wait)
     void bench_resident(int iters, float* ms);
     void save(const char* path);
     void load(const char* path);
 
+    bool nvtx = false;   // argsim_profiler(on): NVTX range per device program, NVTX mark at every phase boundary
     std::vector<std::string> tnames;
     std::vector<float> tms;
     long long launches0 = 0;
@@ -137,7 +142,7 @@ private:
     uint64_t submit_seq = 0;   // steps submitted so far; slot = seq & 1
     int pend_n = 0;            // submitted and not yet waited for (oldest: slot (submit_seq - pend_n) & 1)
     struct DevPlan {
-        int *ids_src, *ids_lead, *labels, *enc_last, *dec_perm, *enc_off, *enc_nact, *dec_off, *dec_nact;
+        int *ids_src, *ids_lead, *labels, *enc_last, *dec_perm, *enc_off, *enc_nact, *dec_off, *dec_nact, *row_ids;
     } dp{};
     float* d_eps_in = nullptr;  // injected eps staging (b,R)
     size_t eps_cap = 0;

@@ -119,7 +119,7 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint64_t step, uin
 }
 __global__ void __launch_bounds__(256) k_latent_fwd(const float* __restrict__ mulv, const float* __restrict__ eps_in, int b,
                                                     int R, int train, uint64_t seed, uint64_t step, long long row0,
-                                                    float* __restrict__ eps_used, float* __restrict__ z_f,
+                                                    const int* __restrict__ row_ids, float* __restrict__ eps_used, float* __restrict__ z_f,
                                                     bf16* __restrict__ z_h, float* __restrict__ kld_samp,
                                                     double* __restrict__ stats) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k_latent_fwd(const float* __restrict__ mu
         float mu = mulv[(long long)r * 2 * R + c], lv = mulv[(long long)r * 2 * R + R + c];
         float z = mu;
         if (train) {
-            float e = eps_in ? eps_in[i] : philox_normal(seed, step, (uint32_t)(row0 + r), (uint32_t)c);
+            float e = eps_in ? eps_in[i] : philox_normal(seed, step, row_ids ? (uint32_t)row_ids[r] : (uint32_t)(row0 + r), (uint32_t)c);
             eps_used[i] = e;
             z = mu + expf(0.5f * lv) * e;
         }
@@ -149,8 +149,9 @@ __global__ void __launch_bounds__(256) k_latent_fwd(const float* __restrict__ mu
     }
 }
 void launch_latent_fwd(const float* mulv, const float* eps_in, int b, int R, int train, uint64_t seed, uint64_t step,
-                       long long row0, float* eps_used, float* z_f, bf16* z_h, float* kld_samp, double* stats, cudaStream_t s) {
-    k_latent_fwd<<<cdiv((long long)b * R, 256), 256, 0, s>>>(mulv, eps_in, b, R, train, seed, step, row0, eps_used, z_f, z_h,
+                       long long row0, const int* row_ids, float* eps_used, float* z_f, bf16* z_h, float* kld_samp, double* stats,
+                       cudaStream_t s) {
+    k_latent_fwd<<<cdiv((long long)b * R, 256), 256, 0, s>>>(mulv, eps_in, b, R, train, seed, step, row0, row_ids, eps_used, z_f, z_h,
                                                              kld_samp, stats);
     COUNT_LAUNCH();
 }

@@ -12,9 +12,10 @@ void launch_embed_scatter_add(const int* ids, long long n, const float* dx, int 
 // generic row gather: out[dst[i] or i, :] = in[src[i] or i, :]; reads fp32 or bf16, writes fp32 and/or bf16
 void launch_row_gather(const float* in_f, const bf16* in_h, int ld_in, const int* src_idx, float* out_f, bf16* out_h,
                        int ld_out, const int* dst_idx, int n, int cols, cudaStream_t s);
-// A9/A15: z = mu (+ exp(lv/2)*eps), kld_samp, sum(kld) -> stats[2]
+// A9/A15: z = mu (+ exp(lv/2)*eps), kld_samp, sum(kld) -> stats[2].  eps is injected (eps_in) or Philox keyed by the GLOBAL row
+// index of every row: row_ids[r] (device, b ints) or row0 + r
 void launch_latent_fwd(const float* mulv, const float* eps_in, int b, int R, int train, uint64_t seed, uint64_t step,
-                       long long row0, float* eps_used, float* z_f, bf16* z_h, float* kld_samp, double* stats, cudaStream_t s);
+                       long long row0, const int* row_ids, float* eps_used, float* z_f, bf16* z_h, float* kld_samp, double* stats, cudaStream_t s);
 // A18: dmu = dz + a*mu ; dlv = dz*.5*exp(lv/2)*eps + a*.5*(exp(lv)-1)   (a = anneal/(b_global*R))
 void launch_latent_bwd(const float* dz, const float* mulv, const float* eps, int b, int R, int train, float a,
                        float* dmulv_f, bf16* dmulv_h, cudaStream_t s);

@@ -90,7 +90,7 @@ std::string build_batch_plan(const int32_t* src, int b, int T_src, const int32_t
                     if (drop.keep) {
                         keep = drop.keep[(size_t)i * T_tgt + (t - 1)] != 0;
                     } else {
-                        uint32_t c[4] = {(uint32_t)(drop.row0 + i), (uint32_t)(t - 1), (uint32_t)PHILOX_STREAM_KEEP,
+                        uint32_t c[4] = {(uint32_t)(drop.rows ? drop.rows[i] : drop.row0 + i), (uint32_t)(t - 1), (uint32_t)PHILOX_STREAM_KEEP,
                                          (uint32_t)(drop.seed >> 32)};
                         philox4x32_10(c, (uint32_t)drop.seed, (uint32_t)drop.step);
                         keep = u01_24(c[0]) < drop.rate_keepwd;  // tf.random_uniform(...) < rate_keepwd

@@ -41,6 +41,8 @@ struct DropoutSpec {
     float rate_keepwd = 1.f;
     uint64_t seed = 0, step = 0;
     long long row0 = 0;          // global index of row 0 (data parallel)
+    const int64_t* rows = nullptr;  // (b) global index of every row (overrides row0 + i): the streams are then invariant
+                                    // to how the global batch is dealt over the ranks
 };
 
 // Builds the plan; returns "" on success or an error message.  need_dec = 0 builds the encoder

@@ -159,6 +159,11 @@ class Session:
         self.nranks, self.rank = nranks, rank
         self._last_stats = None
         self._inflight = 0     # train steps submitted and not yet waited for (<= 2)
+        # data parallel: every rank must train on rows of the SAME global batch.  'check' (default) compares a digest of
+        # the ranks' batches on the first steps and then every 256th; 'broadcast' ships rank 0's batch to everybody every
+        # step (what --sample needs: sentencepiece sampling is not seeded, the ranks' streams differ); None trusts the caller
+        self.sync_batches = 'check'
+        self._dp_steps = 0
         self.pipelined = True  # sess.run(model.train_step) returns once the step is enqueued (src/train.py:118 fetches nothing else)
         _state['session'] = self
 
@@ -239,8 +244,15 @@ class Session:
                 # every rank draws the same global batch (same seed, same generator) and keeps its rows; the two loss
                 # means are normalised by the GLOBAL counts (model.py:181,184), known from the lengths before launch
                 from . import parallel
-                src, tgt, _, n_tok, b_glob = parallel.shard_batch(src, tgt, self.nranks, self.rank, eos=model.config.get('eos', 1))
-                kw = dict(n_tokens_global=n_tok, b_global=b_glob, row0=parallel.row0_of(self.rank, self.nranks, b_glob))
+                if self.sync_batches == 'broadcast':
+                    src, tgt = parallel.broadcast_batch(src, tgt, self.rank)
+                elif self.sync_batches == 'check' and (self._dp_steps < 3 or self._dp_steps % 256 == 0):
+                    parallel.assert_same_batch(src, tgt)
+                self._dp_steps += 1
+                src, tgt, rows, n_tok, b_glob = parallel.shard_batch(src, tgt, self.nranks, self.rank, eos=model.config.get('eos', 1))
+                # rows = indices in the global batch: they key the Philox streams of word dropout and eps, so the
+                # un-injected randomness of a step is the same whatever the number of ranks
+                kw = dict(n_tokens_global=n_tok, b_global=b_glob, rows=rows)
             if self.pipelined:
                 # submit(n+1) before wait(n): the host plan + H2D of this step overlap the device's previous step
                 h.train_step_submit(src, tgt, **kw)

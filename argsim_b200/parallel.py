@@ -25,6 +25,9 @@ def shard_batch(src, tgt, nranks, rank, eos=1):
     """-> (src_r, tgt_r, rows_r, n_tokens_global, b_global): this rank's rows (padding re-trimmed),
     their global row indices (RNG keying), and the global normalisers."""
     src, tgt = np.asarray(src, np.int32), np.asarray(tgt, np.int32)
+    if len(src) < nranks:
+        raise ValueError('data parallel: the global batch has %d rows, fewer than the %d ranks (every rank needs >= 1 row)'
+                         % (len(src), nranks))
     ls, lt = lengths(src, eos), lengths(tgt, eos)
     rows = shard_rows(np.maximum(ls, lt), nranks)[rank]
     s, t = src[rows], tgt[rows]
@@ -52,6 +55,52 @@ def exchange_nccl_id(make_id, nranks, rank):
     obj = [make_id() if rank == 0 else None]
     dist.broadcast_object_list(obj, src=0)
     return bytes(obj[0])
+
+
+def broadcast_batch(src, tgt, rank):
+    """rank 0's (src, tgt) on every rank (gloo, host plumbing).  Needed whenever the batch stream is not a pure
+    function of the seed: `--sample` draws segmentations from sentencepiece's unseeded per-process RNG
+    (src/util_sp.py:66-111), so the ranks' own copies of a batch differ in ids AND lengths and the row sets of
+    shard_rows would not partition one batch."""
+    import torch
+    import torch.distributed as dist
+    hdr = torch.zeros(3, dtype=torch.int64)
+    if rank == 0:
+        src, tgt = np.ascontiguousarray(src, np.int32), np.ascontiguousarray(tgt, np.int32)
+        hdr = torch.tensor([src.shape[0], src.shape[1], tgt.shape[1]], dtype=torch.int64)
+    dist.broadcast(hdr, src=0)
+    b, ts, tt = (int(x) for x in hdr)
+    buf = torch.empty(b * (ts + tt), dtype=torch.int32)
+    if rank == 0:
+        buf[:b * ts] = torch.from_numpy(src.reshape(-1))
+        buf[b * ts:] = torch.from_numpy(tgt.reshape(-1))
+    dist.broadcast(buf, src=0)
+    a = buf.numpy()
+    return a[:b * ts].reshape(b, ts).copy(), a[b * ts:].reshape(b, tt).copy()
+
+
+def batch_digest(src, tgt):
+    """64-bit digest of a batch (shape + contents), for the cross-rank agreement check."""
+    import hashlib
+    h = hashlib.blake2b(digest_size=8)
+    for a in (src, tgt):
+        a = np.ascontiguousarray(a, np.int32)
+        h.update(np.asarray(a.shape, np.int64).tobytes())
+        h.update(a.tobytes())
+    return int.from_bytes(h.digest(), 'little') >> 1   # fits int64
+
+
+def assert_same_batch(src, tgt, what='batch'):
+    """raises unless every rank holds the same batch (all-reduce MIN/MAX of a digest over gloo)."""
+    import torch
+    import torch.distributed as dist
+    d = batch_digest(src, tgt)
+    lo, hi = torch.tensor([d], dtype=torch.int64), torch.tensor([d], dtype=torch.int64)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    if int(lo) != int(hi):
+        raise RuntimeError('data parallel: the ranks hold different %ss (a batch stream that is not a pure function of '
+                           'the seed, e.g. --sample, must be broadcast from rank 0: Session.sync_batches = "broadcast")' % what)
 
 
 def row0_of(rank, nranks, b_global):

@@ -24,9 +24,11 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def keep_mask(b, T, rate_keepwd, seed, step, row0=0):
-    """(b,T) uint8 mask the library draws for word dropout (model.py:94) when none is injected."""
-    rows = (np.arange(b, dtype=np.int64)[:, None] + row0).astype(np.uint32) + np.zeros((1, T), np.uint32)
+def keep_mask(b, T, rate_keepwd, seed, step, row0=0, rows=None):
+    """(b,T) uint8 mask the library draws for word dropout (model.py:94) when none is injected; rows = global row
+    index of every row (argsim_set_global_rows), default row0 + i."""
+    gid = np.arange(b, dtype=np.int64) + row0 if rows is None else np.asarray(rows, np.int64)
+    rows = gid[:, None].astype(np.uint32) + np.zeros((1, T), np.uint32)
     pos = np.zeros((b, 1), np.uint32) + np.arange(T, dtype=np.uint32)[None, :]
     c0, _, _, _ = philox4x32_10(rows, pos, np.uint32(STREAM_KEEP), np.uint32((seed >> 32) & 0xFFFFFFFF),
                                 seed & 0xFFFFFFFF, step & 0xFFFFFFFF)

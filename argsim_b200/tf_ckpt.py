@@ -393,7 +393,7 @@ def save_bundle(prefix, tensors, checksum=True):
 #   * tf.layers.dense(name=n) under scope s                -> s/n/kernel (in,out), s/n/bias            [= canonical]
 #   * tf.contrib.cudnn_rnn.CudnnGRU(L, H, name=n) in scope s saves through CudnnOpaqueParamsSaveable in the
 #     "cudnn-compatible" canonical form, per layer l:
-#       s/n/cudnn_gru/rnn/multi_rnn_cell/cell_l/cudnn_compatible_gru_cell/gates/kernel        (in+H, 2H)  cols [r | u]
+#       s/n/[cudnn_gru/]rnn/multi_rnn_cell/cell_l/cudnn_compatible_gru_cell/gates/kernel      (in+H, 2H)  cols [r | u]
 #       .../gates/bias (2H) = bW + bR of r,u   .../candidate/input_projection/{kernel (in,H), bias}  = W_n^T, bW_n
 #       .../candidate/hidden_projection/{kernel (H,H), bias} = R_n^T, bR_n
 #   * its Adam slots are slots of the OPAQUE variable s/n/opaque_kernel and are saved raw, in cuDNN's blob layout:
@@ -419,7 +419,12 @@ def _gru_scopes(cfg):
     return out
 
 
-_CELL = 'cudnn_gru/rnn/multi_rnn_cell/cell_%d/cudnn_compatible_gru_cell/'
+# The reference names its layers (CudnnGRU(..., name='fwd'), src/model.py:15,118-131), so the layer scope is the user's
+# name and the saveable most likely writes <scope>/rnn/multi_rnn_cell/...; 'cudnn_gru' is only the DEFAULT layer name and
+# would appear as an extra scope level if the saveable prefixes it regardless.  No TF-written file exists to settle it:
+# the reader accepts both forms (whichever is present), the writer emits the first.  UNVERIFIED either way.
+_CELL = 'rnn/multi_rnn_cell/cell_%d/cudnn_compatible_gru_cell/'
+_CELL_FORMS = (_CELL, 'cudnn_gru/' + _CELL)
 
 
 def canonical_to_tf(params, cfg, step=0, adam=None):
@@ -489,9 +494,10 @@ def tf_to_canonical(tensors, cfg, shapes):
 
     for scope, layers in _gru_scopes(cfg):
         opaque = scope + '/opaque_kernel'
-        if scope + '/' + _CELL % 0 + 'gates/kernel' in tensors:
+        form = next((f for f in _CELL_FORMS if scope + '/' + f % 0 + 'gates/kernel' in tensors), None)
+        if form is not None:
             for l, pre in enumerate(layers):
-                c = scope + '/' + _CELL % l
+                c = scope + '/' + form % l
                 gk, gb = take(c + 'gates/kernel'), take(c + 'gates/bias')
                 cin = gk.shape[0] - H
                 params[pre + 'W'] = np.concatenate([gk[:cin].T, take(c + 'candidate/input_projection/kernel').T], 0)

@@ -6,9 +6,9 @@
 
 Differences from the reference, all outside the hot path: summaries go to `<log>/<trial>.jsonl`
 (one JSON object per 250 steps with step_errt / step_loss_gen / step_loss_kld) instead of a
-TensorBoard event file; checkpoints use the library's own container; `--profile` brackets one
-validation forward pass with cudaProfilerStart/Stop-friendly warm-ups and prints per-phase
-device times instead of writing a TF RunMetadata.  `--precision fp32` selects the validation mode.
+TensorBoard event file; checkpoints use the library's own container; `--profile` runs three warm-up
+validation passes, then one between cudaProfilerStart/Stop with an NVTX range around the device program and an
+NVTX mark per phase (argsim_profiler), and prints per-phase device times instead of writing a TF RunMetadata.  `--precision fp32` selects the validation mode.
 Launched as `python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 -m argsim_b200.train ...`
 the same loop trains data parallel on N GPUs (rows of every batch sharded, gradients all-reduced by the library).
 """
@@ -96,6 +96,10 @@ def main(argv=None):
     model_train = M.vAe('train', src=src, tgt=tgt, **C)
 
     sess = M.Session(precision=A.precision)
+    if A.sample:
+        # sentencepiece's sampling RNG is per process and unseeded (src/util_sp.py:66-111): under data parallelism the
+        # ranks' batch streams differ, so rank 0's batch is the batch (Session.run broadcasts it before sharding)
+        sess.sync_batches = 'broadcast'
     saver = M.Saver()
     if A.ckpt:
         saver.restore(sess, pform(P.ckpt, A.ckpt))
@@ -106,7 +110,9 @@ def main(argv=None):
         feed = {model_valid.src: valid[:32], model_valid.tgt: valid[:32]}
         for _ in range(3):
             sess.run(model_valid.loss, feed)
+        sess.handle.profiler(True)    # cudaProfilerStart + NVTX ranges: `nsys/ncu --capture-range=cudaProfilerApi`
         sess.run(model_valid.loss, feed)
+        sess.handle.profiler(False)
         print(json.dumps(dict(profile=sess.handle.last_timings())))
         if not A.rounds:
             sys.exit("profiling done")

@@ -13,7 +13,12 @@ One rank per GPU.  Weak scaling: every rank owns 64 sequences of a seed-0 global
            argsim_train_step_submit(n+1) before argsim_train_step_wait(n); `e2e.blocking` is the same with
            one blocking argsim_train_step per step.
 `--impl reference`: the reference's TF graph cannot run (no TensorFlow; CudnnGRU is GPU-only), so the
-CPU arm is the torch-CPU port of the same graph (oracle/vae_torch.py) on all host threads.
+CPU arm is the torch-CPU port of the same graph (oracle/vae_torch.py) on all host threads: FULL-length steps of the
+same 64-row batch (no truncation, no extrapolation), same `config` as this arm's line.
+The default line also carries `embed` (BASELINE configs[3]: encoder-only mu of 4096 IBM-shaped rows through
+argsim_embed with host buffers), `strong_scaling` (BASELINE configs[2] read as a fixed global batch of 512 over the N
+ranks; at N = 1 that is the 1-GPU b = 512 number) and, for N > 1, `dp_check` (after the timed steps: the ranks' step
+statistics and a checksum of every parameter tensor agree).
 """
 import argparse
 import json
@@ -101,6 +106,21 @@ def dist_setup(n):
     return 0, 1, 0, None
 
 
+def workload_config(world, full=None, S_glob=None, N_glob=None):
+    """`config` of the JSON line: the SAME dict for both arms (the reference arm runs rank 0's N=1 workload)."""
+    gb = PER_GPU * world
+    if full is None:
+        from argsim_b200.synth import synth_batch
+        full = synth_batch(gb, 'iac', CFG['dim_tgt'], seed=0)
+        S_glob = int((full != 1).sum())
+        N_glob = int(((full != 1).sum(1) + 1).sum())
+    return dict(workload='config.json VAE (V=8192 D=512 R=1024 L=3), IAC-shaped synthetic sentencepiece batch, '
+                         'seed 0, %d sequences per GPU (BASELINE configs[%d])' % (PER_GPU, 1 if world == 1 else 2),
+                global_batch=gb, src_tokens=S_glob, tgt_rows=N_glob, max_len=int(full.shape[1]),
+                parallelism='dp%d' % world, l2='no flush needed: one step streams >1 GB of activations and 0.68 GB of '
+                'Adam state, far above the 126 MB L2')
+
+
 class CpuPort:
     """torch-CPU port of the reference graph (oracle/vae_torch.py) on the C1 batch.  The reference pads every
     row to the batch maximum and runs cuDNN over all padded steps, so the cost of a step is proportional to the
@@ -133,13 +153,16 @@ class CpuPort:
         return time.perf_counter() - t0
 
     def pick(self, nsteps, budget_s):
-        """largest power-of-two truncation whose nsteps steps fit the budget (calibrated on T'=8)"""
+        """full length unless a budget is given (ARGSIM_REF_BUDGET_S): then the largest power-of-two truncation whose
+        nsteps steps fit it (calibrated on T'=8); a truncated run is labelled as such and never extrapolated silently"""
+        if not budget_s:
+            return self.tmax
         self.step(8)
         t8 = self.step(8)
         tp = 8
         while tp * 2 <= self.tmax and nsteps * t8 * (tp * 2 / 8.0) <= budget_s:
             tp *= 2
-        return tp
+        return self.tmax if tp * 2 > self.tmax else tp
 
 
 def reference_arm(args, rank, world):
@@ -147,21 +170,25 @@ def reference_arm(args, rank, world):
     if rank != 0:
         return
     port = CpuPort()
-    tp = port.pick(args.steps + args.warmup, float(os.environ.get('ARGSIM_REF_BUDGET_S', 150)))
+    tp = port.pick(args.steps + args.warmup, float(os.environ.get('ARGSIM_REF_BUDGET_S', 0)))
     times = [port.step(tp) for _ in range(args.warmup + args.steps)][args.warmup:]
     ms = 1e3 * float(np.mean(times))
+    full = tp == port.tmax
     ms_full = ms * port.tmax / tp
     val = PER_GPU / (ms_full / 1e3)
-    sample = ('the 64-row C1 batch truncated to its first %d of %d time steps per step (padded graph: cost ~ time steps); '
-              'value extrapolated x%d/%d; %d steps of fwd+bwd+Adam, torch-CPU fp32' % (tp, port.tmax, tp, port.tmax, args.steps))
+    if full:
+        sample = ('one step = the whole 64-row C1 batch, all %d padded time steps, forward + backward + TF-form Adam in torch-CPU '
+                  'fp32 (library GRU + MKL GEMMs); %d timed steps after %d warm-up steps, nothing extrapolated'
+                  % (port.tmax, args.steps, args.warmup))
+    else:
+        sample = ('EXTRAPOLATED (ARGSIM_REF_BUDGET_S set): the 64-row C1 batch truncated to its first %d of %d time steps per '
+                  'step, value scaled x%d/%d' % (tp, port.tmax, tp, port.tmax))
     line = dict(metric=METRIC, value=val, unit='sequences/s', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_full, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                impl='reference',
-                config=dict(workload='config.json VAE (V=8192 D=512 R=1024 L=3), IAC-shaped synthetic sentencepiece batch, '
-                                     'seed 0, 64 sequences (BASELINE configs[0])', global_batch=PER_GPU,
-                            measured_ms_per_sample_step=ms, sample_time_steps=tp,
-                            note='the TF reference cannot run (no TensorFlow; CudnnGRU has no CPU kernel): torch-CPU port of '
-                                 'the same padded graph (oracle/vae_torch.py), library GRU + MKL GEMMs'),
+                impl='reference', config=workload_config(world),
+                note='the TF reference cannot run (no TensorFlow; CudnnGRU has no CPU kernel): torch-CPU port of the same padded '
+                     'graph (oracle/vae_torch.py); rank 0 runs the per-GPU workload of the other arm (64 sequences), '
+                     'sample_time_steps=%d of %d' % (tp, port.tmax),
                 cpu_baseline=dict(value=val, unit='sequences/s', cores=port.cores, kind='port', sample=sample),
                 e2e=dict(value=val, unit='sequences/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -170,13 +197,11 @@ def reference_arm(args, rank, world):
 def cpu_baseline_leg():
     """rank 0, N=1: the same port timed for ~20 s next to the GPU number."""
     port = CpuPort()
-    tp = port.pick(3, 20.0)
-    times = [port.step(tp) for _ in range(3)][1:]
-    ms_full = 1e3 * float(np.mean(times)) * port.tmax / tp
+    times = [port.step(port.tmax) for _ in range(3)][1:]
+    ms_full = 1e3 * float(np.mean(times))
     return dict(value=PER_GPU / (ms_full / 1e3), unit='sequences/s', cores=port.cores, kind='port',
-                sample='the 64-row C1 batch truncated to its first %d of %d time steps (padded graph: cost ~ time steps), '
-                       'extrapolated x%d/%d; 2 timed steps of fwd+bwd+Adam in torch-CPU fp32 (TF reference not runnable)'
-                       % (tp, port.tmax, tp, port.tmax))
+                sample='2 timed FULL steps (after 1 warm-up) of the same 64-row C1 batch, all %d padded time steps, forward + '
+                       'backward + TF-form Adam in torch-CPU fp32 (TF reference not runnable); nothing extrapolated' % port.tmax)
 
 
 def main():
@@ -188,6 +213,7 @@ def main():
     ap.add_argument('--workload', default='train', choices=('train', 'embed'))
     ap.add_argument('--precision', default='bf16', choices=('bf16', 'fp32'))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the embed / strong_scaling sub-records')
     ap.add_argument('--generic-gru', action='store_true', help='bf16 GEMMs with the per-step generic GRU (debug)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -256,7 +282,9 @@ def main():
     gb = PER_GPU * world
     full = synth_batch(gb, 'iac', CFG['dim_tgt'], seed=0)
     src, tgt, rows, n_tok_glob, b_glob = parallel.shard_batch(full, full, world, rank)
-    kw = dict(n_tokens_global=n_tok_glob, b_global=b_glob, row0=rank * PER_GPU) if world > 1 else {}
+    # rows = this rank's row indices in the global batch: they key the Philox streams (word dropout, eps), so the
+    # un-injected randomness of the step does not depend on the number of ranks
+    kw = dict(n_tokens_global=n_tok_glob, b_global=b_glob, rows=rows) if world > 1 else {}
     S_glob = int((full != 1).sum())
     N_glob = n_tok_glob
 
@@ -299,6 +327,67 @@ def main():
     clocks = clk.stop()
     ms = max_over_ranks(ms_local)
     tm = h.last_timings()   # phases + k: timers of the LAST step of the timed region
+
+    # ---- dp_check (N > 1): the data-parallel invariant after the timed steps, with the schedule that was timed --
+    # every rank's step statistics are the global ones and every parameter tensor is bit-identical across ranks
+    dp_check = None
+    if dist:
+        import zlib
+        sums = []
+        for name in sorted(h.param_shapes()):
+            a = h.get_param(name)
+            sums.append(float(zlib.crc32(a.tobytes())))
+            sums.append(float(np.abs(a.astype(np.float64)).sum()))
+        mine_v = torch.tensor([st['loss'], st['loss_gen'], st['loss_kld'], float(st['step'])] + sums, device='cuda', dtype=torch.float64)
+        lo, hi = mine_v.clone(), mine_v.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        bad = int((lo != hi).sum().item())
+        finite = bool(torch.isfinite(mine_v).all().item())
+        dp_check = 'ok' if bad == 0 and finite else 'FAILED: %d of %d values differ across ranks%s' % (bad, mine_v.numel(), '' if finite else ', non-finite')
+
+    # ---- strong scaling: BASELINE configs[2] as a FIXED global batch of 512 dealt over the N ranks (N = 1: b = 512 on one GPU)
+    strong = None
+    if args.workload == 'train' and not args.no_extra:
+        full512 = synth_batch(512, 'iac', CFG['dim_tgt'], seed=0)
+        s5, t5, rows5, ntok5, b5 = parallel.shard_batch(full512, full512, world, rank)
+        kw5 = dict(n_tokens_global=ntok5, b_global=b5, rows=rows5) if world > 1 else {}
+        for _ in range(3):
+            st5 = h.train_step(s5, t5, **kw5)
+        barrier()
+        ms5 = max_over_ranks(h.bench_resident(max(3, min(args.steps, 10))))
+        tm5 = h.last_timings()
+        strong = dict(global_batch=512, rows_per_gpu=int(len(s5)), n_gpus=world, ms_per_step=ms5, value=512 / (ms5 / 1e3), unit='sequences/s',
+                      src_tokens=int((full512 != 1).sum()), tgt_rows=int(ntok5),
+                      phases_ms={k: round(v, 4) for k, v in tm5.items() if not k.startswith('k:')},
+                      note='same model and data generator, global batch fixed at 512 sequences; device-timed, resident batch')
+
+    # ---- embed: BASELINE configs[3] / metric "embed seq/sec": mu of 4096 IBM-shaped rows per GPU through argsim_embed
+    embed = None
+    if args.workload == 'train' and not args.no_extra:
+        data = synth_batch(4096, 'ibm', CFG['dim_tgt'], seed=rank)
+        data = np.ascontiguousarray(data[:, :int((data != 1).sum(1).max())])
+        for _ in range(2):
+            h.embed(data)
+        barrier()
+        clk_e = Clocks(local)
+        t0 = time.perf_counter()
+        ne = 5
+        for _ in range(ne):
+            mu = h.embed(data)
+        dt = time.perf_counter() - t0
+        barrier()
+        ms_e = max_over_ranks(1e3 * dt / ne)
+        S_e = int((data != 1).sum())
+        H_ = CFG['dim_emb']
+        fl_e = (2 * 2 * 3 * H_ * (H_ + H_) + 2 * 2 * 2 * 3 * H_ * (2 * H_ + H_)) * S_e + 2 * (2 * H_) * CFG['dim_rep'] * 4096
+        embed = dict(metric='embed sequences/sec (encoder mu)', value=4096 * world / (ms_e / 1e3), unit='sequences/s', ms_per_batch=ms_e,
+                     batch_per_gpu=4096, tokens_per_gpu=S_e, h2d_bytes_per_step=int(data.nbytes), d2h_bytes_per_step=int(mu.nbytes),
+                     timer='host perf_counter around %d argsim_embed calls with host buffers (plan + H2D + encoder + D2H of mu)' % ne,
+                     roofline=dict(bound='tensor', achieved=round(fl_e / (ms_e * 1e-3) / 1e12, 3), peak=pk['tf_sust'], unit='TFLOP/s',
+                                   frac=round(fl_e / (ms_e * 1e-3) / 1e12 / pk['tf_sust'], 5),
+                                   note='algorithmic encoder flops (SURVEY 8d: 25.166 MFLOP per source token) over the e2e time'),
+                     clocks=clk_e.stop(), finite=bool(np.isfinite(mu).all()))
 
     if rank != 0:
         if dist:
@@ -376,11 +465,7 @@ def main():
     line = dict(metric=METRIC, value=value, unit='sequences/s', n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms, higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='bf16' if args.precision == 'bf16' else 'f32', data='synthetic',
-                config=dict(workload='config.json VAE (V=8192 D=512 R=1024 L=3), IAC-shaped synthetic sentencepiece batch, '
-                                     'seed 0, %d sequences per GPU (BASELINE configs[%d])' % (PER_GPU, 1 if world == 1 else 2),
-                            global_batch=gb, src_tokens=S_glob, tgt_rows=N_glob, max_len=int(full.shape[1]),
-                            parallelism='dp%d' % world, l2='no flush needed: one step streams >1 GB of activations and 0.68 GB of '
-                            'Adam state, far above the 126 MB L2'),
+                config=workload_config(world, full, S_glob, N_glob),
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=dict(value=gb / (e2e_ms / 1e3), unit='sequences/s', ms_per_step=e2e_ms, h2d_bytes_per_step=int(h2d),
                          d2h_bytes_per_step=d2h,
@@ -391,6 +476,12 @@ def main():
                 roofline=roofline, kernels=kernels, phases_ms=phases,
                 step_tflops=round(fl['train'] / (ms * 1e-3) / 1e12, 3), step_frac_of_tensor_peak=round(fl['train'] / (ms * 1e-3) / 1e12 / pk['tf_sust'], 5),
                 last_step=dict(loss=st['loss'], loss_gen=st['loss_gen'], loss_kld=st['loss_kld']))
+    if embed:
+        line['embed'] = embed
+    if strong:
+        line['strong_scaling'] = strong
+    if dp_check:
+        line['dp_check'] = dp_check
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline_leg()
     print(json.dumps(line), flush=True)

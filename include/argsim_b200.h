@@ -94,6 +94,12 @@ int  argsim_train_step_submit(argsim_handle*, const int32_t* src, const int32_t*
                               int32_t T_src, int32_t T_tgt, const uint8_t* keep_mask, const float* eps,
                               int64_t n_tokens_global, int64_t b_global, int64_t row0_global);
 int  argsim_train_step_wait(argsim_handle*, argsim_step_stats* out);
+/* Data parallel: global index of every row of the NEXT train / grad step (consumed by that call;
+ * NULL or b = 0 clears).  The Philox streams of word dropout (model.py:94) and eps (model.py:150) are keyed by
+ * (seed, step, global row, position), so with the rows' indices in the GLOBAL batch given here the un-injected
+ * randomness of a step does not depend on the number of ranks or on how the rows were dealt; without it rows are
+ * keyed row0_global + i. */
+int  argsim_set_global_rows(argsim_handle*, const int64_t* rows, int32_t b);
 /* same step but stops before Adam / step increment (gradient parity, test only) */
 int  argsim_grad_step(argsim_handle*, const int32_t* src, const int32_t* tgt, int32_t b,
                       int32_t T_src, int32_t T_tgt, const uint8_t* keep_mask, const float* eps,
@@ -132,6 +138,11 @@ int  argsim_load(argsim_handle*, const char* path);
 int  argsim_bench_resident(argsim_handle*, int32_t iters, float* ms_per_step);
 /* number of kernels this library launched since creation (bench.py's gpu_launches) */
 int  argsim_launch_count(argsim_handle*, int64_t* n);
+/* --profile of src/train.py:76-82 / profile() of src/util_tf.py:9-13 (one traced sess.run): on = 1 calls
+ * cudaProfilerStart() and makes every device program an NVTX range ("argsim:train_step" / "argsim:eval_step" /
+ * "argsim:embed") with an NVTX mark at each phase boundary; on = 0 calls cudaProfilerStop().  For
+ * `ncu / nsys --capture-range=cudaProfilerApi`. */
+int  argsim_profiler(argsim_handle*, int32_t on);
 /* per-phase device timings of the last step, name/ms pairs; returns count */
 int  argsim_last_timings(argsim_handle*, int32_t cap, const char** names, float* ms);
 /* unit-test hook for the GEMM kernels: C(M,N) = alpha * op(A) op(B)^T (+bias) ; layouts:

@@ -106,6 +106,7 @@ def test_session_shards_every_batch_under_torchrun(monkeypatch):
     cfg = dict(dim_tgt=64, dim_emb=16, dim_rep=24, rnn_layers=2)
     m = M.vAe('train', **cfg)
     sess = M.Session()
+    sess.sync_batches = None      # no process group in this test; the cross-rank checks have their own test below
     h = _FakeHandle.made[-1]
     assert (h.kw['nranks'], h.kw['rank'], h.kw['device'], h.kw['nccl_id']) == (2, 1, 1, b'\x07' * 128)
     src = ragged_batch(10, 9, 64, 1)
@@ -117,7 +118,8 @@ def test_session_shards_every_batch_under_torchrun(monkeypatch):
     es, et, rows, n_glob, b_glob = parallel.shard_batch(src, tgt, 2, 1)
     np.testing.assert_array_equal(s, es)
     np.testing.assert_array_equal(t, et)
-    assert kw == dict(n_tokens_global=n_glob, b_global=10, row0=5)
+    assert set(kw) == {'n_tokens_global', 'b_global', 'rows'} and kw['n_tokens_global'] == n_glob and kw['b_global'] == 10
+    np.testing.assert_array_equal(kw['rows'], rows)     # global row indices key the RNG streams
     other = parallel.shard_batch(src, tgt, 2, 0)[2]
     assert sorted(list(rows) + list(other)) == list(range(10))
     assert sess.last_stats == dict(step=3)      # waits for the steps in flight
@@ -147,3 +149,51 @@ def test_nccl_id_hand_over_between_two_ranks():
         p.join(60)
         assert p.exitcode == 0
     assert res == {0: True, 1: True}
+
+
+def _sync_worker(rank, world, port, q):
+    from argsim_b200 import parallel
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    same_s, same_t = ragged_batch(6, 9, 64, 1), ragged_batch(6, 7, 64, 2)
+    parallel.assert_same_batch(same_s, same_t)                       # identical batches pass
+    mine_s = ragged_batch(6, 9 + rank, 64, 10 + rank)                # --sample: ids AND lengths differ per rank
+    mine_t = ragged_batch(6, 8, 64, 20 + rank)
+    try:
+        parallel.assert_same_batch(mine_s, mine_t)
+        caught = False
+    except RuntimeError:
+        caught = True
+    bs, bt = parallel.broadcast_batch(mine_s, mine_t, rank)          # rank 0's batch everywhere
+    ref_s, ref_t = ragged_batch(6, 9, 64, 10), ragged_batch(6, 8, 64, 20)
+    ok = caught and np.array_equal(bs, ref_s) and np.array_equal(bt, ref_t) and bs.dtype == np.int32
+    parallel.assert_same_batch(bs, bt)
+    rows = parallel.shard_batch(bs, bt, world, rank)[2]
+    allrows = [None] * world
+    dist.all_gather_object(allrows, rows.tolist())
+    ok = ok and sorted(sum(allrows, [])) == list(range(6))            # the shards partition ONE batch again
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sampled_batches_are_broadcast_before_sharding():
+    """with --sample every rank draws other segmentations; rank 0's batch must be THE batch."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res == {0: True, 1: True}
+
+
+def test_shard_batch_needs_a_row_per_rank():
+    from argsim_b200 import parallel
+    src = ragged_batch(3, 5, 64, 1)
+    with pytest.raises(ValueError, match='fewer than'):
+        parallel.shard_batch(src, src, 4, 0)

@@ -78,5 +78,52 @@ def test_train_driver_resume_embed_decode(tmp_path):
     if y is not None:
         assert y.ndim == 2 and y.shape[0] == 4 and 1 <= y.shape[1] <= 12
         assert y.min() >= 0 and y.max() < 104
+
+    # src/eval_embed_reason.py:30-54: deterministic representation in partitions of 128 rows, and the averaged
+    # representation of ONE text from its sampled segmentations (one batch of `samples` rows -> mean mu)
+    from argsim_b200 import eval_embed
+    texts = [l.strip() for l in open(d + '/valid.txt')][:9]
+    det = eval_embed.embed_texts(sess, model, vocab, texts, batch=4)       # partitions of 4, 4, 1 rows
+    assert det.shape == (9, 128)
+    ids = vpack([vocab.encode_as_ids(t) for t in texts], (9, max(len(vocab.encode_as_ids(t)) for t in texts)), vocab.eos_id(), np.int32)
+    np.testing.assert_allclose(det, model.z.eval({model.src: ids}), rtol=0, atol=2e-2 * np.abs(det).max())   # bf16: rows land in other MMA tiles
+    avg = eval_embed.infer_avg(sess, model, vocab, texts[0], samples=32)
+    assert avg.shape == (128,) and np.isfinite(avg).all()
+    # sampled segmentations of a text encode the same sentence: their mean stays close to the deterministic embedding
+    # compared with the spread between different texts
+    d_same = np.linalg.norm(avg - det[0])
+    d_other = np.median([np.linalg.norm(det[i] - det[0]) for i in range(1, 9)])
+    assert d_same < d_other, (d_same, d_other)
     sess.close()
     M._state.update(config=None, session=None)
+
+    # --sample (src/train.py:56-63): src and tgt are two independent sampled segmentations of each text
+    train.main(['--rounds', '1', '--ckpt', 'unit0', '--sample', '--trial', 'kudo'] + common[2:])
+    log = [json.loads(l) for l in open(d + '/log/kudo.jsonl')]
+    assert [r['step'] for r in log] == [100, 125, 150]
+    assert all(np.isfinite([r['step_errt'], r['step_loss_gen'], r['step_loss_kld']]).all() for r in log)
+    M._state['session'].close()
+    M._state.update(config=None, session=None)
+
+
+def test_sample_batches_have_independent_src_and_tgt(tmp_path):
+    """the --sample feed (src/train.py:56-63, src/util_sp.py:90-111): the generator yields src != tgt of the same texts"""
+    from argsim_b200 import train, util_sp
+    from argsim_b200.util import Record
+    d = str(tmp_path)
+    _corpus(d + '/train.txt', 300, 0)
+    util_sp.spm(d + '/vocab', d + '/train.txt', size=100)
+    vocab = util_sp.load_spm(d + '/vocab.model')
+    T = Record(dict(batch_train=16, max_len=64))
+    P = Record(dict(train=d + '/train.txt'))
+    gen = train.make_batch_fn(T, P, vocab, 0, True, util_sp.encode_capped, util_sp.encode_capped_sample_pair)()
+    differ = 0
+    for _ in range(3):
+        src, tgt = next(gen)
+        assert src.shape[0] == tgt.shape[0] == 16 and src.dtype == tgt.dtype == np.int32
+        for a, b in zip(src, tgt):
+            ta = vocab.decode_ids([int(x) for x in a if x != vocab.eos_id()])
+            tb = vocab.decode_ids([int(x) for x in b if x != vocab.eos_id()])
+            assert ta == tb                                  # the same text ...
+            differ += int(len(a) != len(b) or (a != b).any())
+    assert differ > 0                                        # ... segmented differently at least sometimes

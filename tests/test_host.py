@@ -205,3 +205,56 @@ def test_shard_rows_balanced_and_complete():
         assert min(int(lens[s].max()) for s in sh) >= 0.9 * lens.max()
     s, t, rows, ntok, bglob = parallel.shard_batch(x, x, 4, 1)
     assert ntok == int((lens + 1).sum()) == 66266 + 512 and bglob == 512 and s.shape[0] == 128
+
+
+def test_eval_embed_flows_mirror_the_reference_scripts():
+    """src/eval_embed_reason.py:30-54 on a stub session: partitions of `batch` rows, eos-padded int32 matrices,
+    and the mean over sampled segmentations of one text."""
+    from argsim_b200 import eval_embed
+
+    class Vocab:
+        def eos_id(self):
+            return 1
+
+        def encode_as_ids(self, text):
+            return [3 + len(w) for w in text.split()]
+
+        def sample_encode_as_ids(self, text, nbest, alpha):
+            assert (nbest, alpha) == (-1, 0.5)            # src/util_sp.py:66-87
+            self.n = getattr(self, 'n', 0) + 1
+            ids = self.encode_as_ids(text)
+            return ids + [9] * (self.n % 3)               # segmentations of different lengths
+
+    class Model:
+        z, src = 'z', 'src'
+
+    class Sess:
+        def __init__(self):
+            self.feeds = []
+
+        def run(self, fetch, feed):
+            assert fetch == 'z'
+            x = feed['src']
+            assert x.dtype == np.int32 and x.ndim == 2
+            self.feeds.append(x)
+            return np.stack([(x != 1).sum(1), x.sum(1)], 1).astype(np.float32)
+
+    texts = ['a bb ccc', 'dd', 'e f g h i', 'jj kk', 'l']
+    sess = Sess()
+    out = eval_embed.embed_texts(sess, Model, Vocab(), texts, batch=2)
+    assert [f.shape for f in sess.feeds] == [(2, 5), (2, 5), (1, 5)]       # one vpack for all texts, partitions of 2
+    assert out.shape == (5, 2) and list(out[:, 0]) == [3, 1, 5, 2, 1]
+    assert (sess.feeds[0][1] == [5, 1, 1, 1, 1]).all()                      # eos padding
+    sess = Sess()
+    avg = eval_embed.infer_avg(sess, Model, Vocab(), 'a bb ccc', samples=6)
+    assert len(sess.feeds) == 1 and sess.feeds[0].shape == (6, 5)           # ONE batch of `samples` rows
+    assert avg.shape == (2,) and abs(avg[0] - np.mean([3 + (k % 3) for k in range(1, 7)])) < 1e-6
+    assert eval_embed.embed_texts_sampled(Sess(), Model, Vocab(), texts[:2], samples=4).shape == (2, 2)
+
+
+def test_keep_mask_streams_are_keyed_by_global_row():
+    from argsim_b200 import rng
+    a = rng.keep_mask(6, 11, 0.6, 1234, 77, row0=0)
+    b = rng.keep_mask(3, 11, 0.6, 1234, 77, rows=[4, 0, 5])
+    np.testing.assert_array_equal(b, a[[4, 0, 5]])                          # a row's stream follows its global index
+    np.testing.assert_array_equal(rng.keep_mask(3, 11, 0.6, 1234, 77, row0=3), a[3:6])

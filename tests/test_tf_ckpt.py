@@ -78,6 +78,15 @@ def test_name_and_layout_mapping_roundtrip(tmp_path, extra):
     a, _ = O.forward(P, cfg, src, src, 'valid')
     b, _ = O.forward({k: v.astype(np.float32) for k, v in params.items()}, cfg, src, src, 'valid')
     assert abs(a['loss'] - b['loss']) < 1e-5 * abs(a['loss'])
+    # both spellings of the canonical cell scope are read: '<scope>/rnn/multi_rnn_cell/...' (written) and
+    # '<scope>/cudnn_gru/rnn/multi_rnn_cell/...' (the default layer name as an extra level)
+    assert not any('/cudnn_gru/' in k for k in tf_vars)
+    alt = {k.replace('/rnn/multi_rnn_cell/', '/cudnn_gru/rnn/multi_rnn_cell/'): v for k, v in tf_vars.items()}
+    assert any('/cudnn_gru/' in k for k in alt)
+    params_alt, adam_alt, step_alt, unused_alt = T.tf_to_canonical(alt, cfg, shapes)
+    assert step_alt == 777 and unused_alt == [] and adam_alt is not None
+    for k in P:
+        np.testing.assert_array_equal(params_alt[k], params[k])
     # a checkpoint that only has the opaque blobs (weights in cuDNN order) is placed too
     blob_only = {k: v for k, v in tf_vars.items() if 'cudnn_compatible_gru_cell' not in k}
     for scope, layers in T._gru_scopes(cfg):

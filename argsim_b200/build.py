@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libargsim_b200.so')
-SOURCES = ['kernels.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'gru_generic.cu', 'gru_mma.cu', 'xbench.cu', 'plan.cpp', 'engine.cu', 'capi.cu']
+SOURCES = ['kernels.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'gru_generic.cu', 'gru_mma.cu', 'gru_tc.cu', 'xbench.cu', 'plan.cpp', 'engine.cu', 'capi.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
          '--expt-relaxed-constexpr']

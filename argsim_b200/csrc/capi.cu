@@ -275,6 +275,31 @@ int argsim_test_gemm(int32_t device, int32_t impl, int32_t M, int32_t N, int32_t
     return 0;
 }
 
+int argsim_test_ts_mma(int32_t device, int32_t N, int32_t K, const float* A, const float* B, float* D) {
+    try {
+        CUDA_CHECK(cudaSetDevice(device));
+        const size_t na = (size_t)128 * K, nb = (size_t)N * K, nd = (size_t)128 * N;
+        float *dA, *dB, *dD;
+        bf16 *hA, *hB;
+        CUDA_CHECK(cudaMalloc(&dA, na * 4)); CUDA_CHECK(cudaMalloc(&dB, nb * 4)); CUDA_CHECK(cudaMalloc(&dD, nd * 4));
+        CUDA_CHECK(cudaMalloc(&hA, na * 2)); CUDA_CHECK(cudaMalloc(&hB, nb * 2));
+        CUDA_CHECK(cudaMemcpy(dA, A, na * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemcpy(dB, B, nb * 4, cudaMemcpyHostToDevice));
+        CUDA_CHECK(cudaMemset(dD, 0, nd * 4));
+        launch_cast_bf16(dA, hA, (long long)na, 0);
+        launch_cast_bf16(dB, hB, (long long)nb, 0);
+        gru_tc_test_mma(hA, hB, dD, N, K, 0);
+        CUDA_CHECK(cudaDeviceSynchronize());
+        CUDA_CHECK(cudaMemcpy(D, dD, nd * 4, cudaMemcpyDeviceToHost));
+        cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(hA); cudaFree(hB);
+    } catch (const std::exception& ex) {
+        g_create_err = ex.what();
+        cudaGetLastError();
+        return -2;
+    }
+    return 0;
+}
+
 int argsim_bench_exchange(int32_t device, int32_t method, int32_t groups, int32_t rows, int32_t iters, double* cycles_per_round,
                           int32_t* max_clusters) {
     try {

@@ -75,6 +75,8 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_bucket, cudaEventDisableTiming));
     CUDA_CHECK(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
     if (use_mma) mma = gru_mma_create(c.device);
+    if (const char* ev = getenv("ARGSIM_GRU_TC")) gru_tc_mode = atoi(ev);
+    if (use_mma && gru_tc_mode) tc = gru_tc_create(c.device);
 
     auto add = [&](const std::string& name, int64_t r, int64_t cdim) {
         ParamInfo pi;
@@ -150,6 +152,7 @@ Engine::~Engine() {
     cudaDeviceSynchronize();
     if (nccl_comm) NcclApi::get().CommDestroy((NcclApi::comm_t)nccl_comm);
     if (mma) gru_mma_destroy(mma);
+    if (tc) gru_tc_destroy(tc);
     cudaFree(p); cudaFree(g); cudaFree(m); cudaFree(v); cudaFree(ph);
     cudaFree(arena.base); cudaFree(d_stage); cudaFreeHost(h_stage); cudaFree(d_eps_in);
     for (auto& ps : pend) { if (ps.done) cudaEventDestroy(ps.done); if (ps.h_stats) cudaFreeHost(ps.h_stats); }
@@ -321,10 +324,16 @@ void Engine::gather_embed(const int* ids, long long n, const Mat& out, cudaStrea
     if (out.h) launch_embed_gather_bf16(ids, n, ph + e.off, D, out.h, q);
     else launch_embed_gather_f32(ids, n, p + e.off, D, out.f, q);
 }
+void Engine::rec_fwd(const GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact, cudaStream_t q, int t0,
+                     int Tseg, int slot, int want8, int pad) {
+    if ((gru_tc_mode & 1) && tc) gru_tc_fwd(tc, dirs, ndir, P, d_off, d_nact, H, q, t0, Tseg, slot, 0, pad);
+    else gru_mma_fwd(mma, dirs, ndir, P, d_off, d_nact, H, q, t0, Tseg, slot, want8, pad);
+}
 void Engine::gru_fwd(GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact) {
     if (arena.dry) return;
     kbegin(ndir == 2 ? "k:gru_fwd_enc" : "k:gru_fwd_dec");
-    if (use_mma && gru_mma_fits(mma, ndir, P.b)) gru_mma_fwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0], 0, -1, 0, 0, /*pad: runs alone*/ 1);
+    if (use_mma && (gru_tc_mode & 1) && tc && gru_tc_fits(tc, ndir, P.b)) rec_fwd(dirs, ndir, P, d_off, d_nact, st[0], 0, -1, 0, 0, /*pad: runs alone*/ 1);
+    else if (use_mma && gru_mma_fits(mma, ndir, P.b)) gru_mma_fwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0], 0, -1, 0, 0, /*pad: runs alone*/ 1);
     else gru_generic_fwd(dirs, ndir, P, H, gru_work, st);
     kend();
 }
@@ -619,7 +628,7 @@ void Engine::program(int mode, bool apply_update) {
                         GruFwdArgs x = a[d];
                         x.h0 = (k > 0) ? hTe[d][(k - 1) & 1] : nullptr;
                         x.hT = (k + 1 < nsegE) ? hTe[d][k & 1] : nullptr;
-                        gru_mma_fwd(mma, &x, 1, E, dp.enc_off, dp.enc_nact, H, sw[d], t0, tl, d, want8[(size_t)d * nsegE + k], pad_wave);
+                        rec_fwd(&x, 1, E, dp.enc_off, dp.enc_nact, sw[d], t0, tl, d, want8[(size_t)d * nsegE + k], pad_wave);
                     }
                 for (int d = 0; d < 2; ++d) {
                     cudaEvent_t ev = next_event();
@@ -757,7 +766,7 @@ void Engine::program(int mode, bool apply_update) {
                     GruFwdArgs a = dec_fwd_args(j);
                     if (sg > 0) a.h0 = hT[j][(sg - 1) & 1];
                     a.hT = (sg + 1 < nseg) ? hT[j][sg & 1] : nullptr;
-                    gru_mma_fwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j, want8[(size_t)j * nseg + sg], pad_wave);
+                    rec_fwd(&a, 1, Dp, dp.dec_off, dp.dec_nact, q, t0, tl, j, want8[(size_t)j * nseg + sg], pad_wave);
                     done[j * nseg + sg] = next_event();
                     CUDA_CHECK(cudaEventRecord(done[j * nseg + sg], q));
                 }

@@ -124,6 +124,11 @@ private:
     cudaEvent_t ev_bucket = nullptr, ev_comm = nullptr;
     Arena arena;
     GruMmaCtx* mma = nullptr;
+    GruTcCtx* tc = nullptr;      // tensor-memory recurrence (gru_tc.cu)
+    int gru_tc_mode = 0;         // ARGSIM_GRU_TC: bit 0 = forward recurrences on the tcgen05 kernel
+    // one forward recurrence launch on whichever persistent kernel is selected (want8: the mma.sync kernel's slice request)
+    void rec_fwd(const GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact, cudaStream_t q, int t0,
+                 int Tseg, int slot, int want8, int pad);
     void* nccl_comm = nullptr;
 
     // staged plan

@@ -1,0 +1,580 @@
+// gru_tc.cu -- persistent GRU recurrence for H = 512 on the 5th-generation tensor cores (tcgen05, TS form).
+//
+// Same decomposition as gru_mma.cu (a GROUP of 16 CTAs owns one (direction, batch-slice); CTA c owns hidden units
+// [32c, 32c+32) = 96 rows of R), but the recurrent product runs on tcgen05 instead of mma.sync:
+//   * A = R_own lives in TENSOR MEMORY for the whole launch: TMEM lane = gate*32 + unit (96 of 128 lanes), the 512 k
+//     of a row packed two bf16 per 32-bit column -> 256 of the 512 columns, written once with tcgen05.st;
+//   * B = h_{t-1} of the slice's live rows (CN rows x 512 k, bf16) is staged in shared memory in the UMMA K-major
+//     128-byte-swizzle layout (8 k-blocks of [CN rows x 128 B]) straight from the exchange buffer;
+//   * D[128 x CN] (fp32) accumulates in TMEM: 32 tcgen05.mma (M=128, N=CN, K=16) issued by ONE thread, committed to an
+//     mbarrier; the gate warps read it back with tcgen05.ld (thread = one gate row, CN columns = batch rows).
+// What that buys over the register-stationary mma.sync kernel: the MMA time of a step is 32 * CN/2 cycles whatever the
+// number of live rows (16 rows cost what 8 do), the 8-way k-split reduction through shared memory (24 LDS + adds per
+// row) becomes 3 LDS, and a slice can hold 128 rows per step (N = 128) instead of 8 chunks of 16.
+// The exchange (all-gather of the new h among the 16 CTAs) is the same in-band-tag LL protocol through L2 as in
+// gru_mma.cu: 8-byte words of two bf16 + a 32-bit step tag.  Layout of the exchange buffer here: row-major,
+// [parity][row][256 words], so a publishing warp writes one 128-byte line per row and a polling thread reads the 32
+// bytes (4 words = 8 units) that make up one 16-byte chunk of the swizzled operand tile.
+#include "kernels.h"
+#include "plan.h"
+#include <vector>
+
+namespace {
+
+constexpr int HH = 512;
+constexpr int CL = 16;     // CTAs per group
+constexpr int UN = 32;     // hidden units per CTA
+constexpr int NTH = 256;
+constexpr int MAX_BSL = 256;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TM_A = 0;       // columns [0,256): R_own
+constexpr uint32_t TM_D = 256;     // columns [256, 256 + CN): accumulator
+
+struct TcDirP {
+    const float* gx; const bf16* R; const float* bR; const float* h0;
+    float* hs_f; bf16* hs_h; float* cache; float* hT;
+    int ld_gx, ld_hs, reverse;
+};
+struct TcFwdP {
+    TcDirP dir[2];
+    const int* off; const int* nact;
+    unsigned long long* xbuf;
+    int ndir, nslices, b, Ttot, t0, Tseg, bslr;
+    unsigned tag_base;
+    long long* prof;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem desc]   (TS form: the A operand is read from tensor memory)
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major tile, 128-byte swizzle (same encoding as gemm_tc.cu make_desc<0>)
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void ll_store(unsigned long long* p, uint32_t data, uint32_t tag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load2(const unsigned long long* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+__device__ __forceinline__ int slice_rows(int nat, int sl, int ns) { return nat > sl ? (nat - sl + ns - 1) / ns : 0; }
+#define POLL_GUARD(t0) if (clock64() - (t0) > 4000000000LL) __trap()
+#define NA(t) s_nact[(t) - P.t0 + 1]
+#define OFF(t) s_off[(t) - P.t0 + 1]
+#define PROF_MARK(i) do { if (P.prof && tid == 0) { const long long now_ = clock64(); pacc[i] += now_ - plast; plast = now_; } } while (0)
+
+// byte offset of the 16-byte chunk (row n, chunk c of 64: 8 units each) inside the operand tile
+template <int CN>
+__device__ __forceinline__ uint32_t hs_off(int n, int c) {
+    return (uint32_t)((c >> 3) * (CN * 128) + (n >> 3) * 1024 + (n & 7) * 128 + (((c & 7) ^ (n & 7)) << 4));
+}
+
+// =========================================================================================
+// forward.  CN = rows per MMA (N of the instruction): 16, 32, 64 or 128.
+// =========================================================================================
+template <int CN>
+__global__ void __launch_bounds__(NTH, 1) k_gru_tc_fwd(const __grid_constant__ TcFwdP P) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    if ((int)(blockIdx.x / CL) >= P.ndir * P.nslices) return;          // padding CTA: only there for the 128-block placement
+    const uint32_t sbase = (smem_u32(sm_raw) + 1023u) & ~1023u;
+    unsigned char* const sm = sm_raw + (sbase - smem_u32(sm_raw));
+    // [Hs: CN KB][G: 3*CN*32 f32][hst: bslr*32 f32][tables: 2*(Tseg+2) int][bar 8][slot 4]
+    const uint32_t Hs = sbase;
+    float* G = reinterpret_cast<float*>(sm + CN * 1024);
+    float* hst = G + 3 * CN * UN;
+    int* s_nact = reinterpret_cast<int*>(hst + (size_t)P.bslr * UN);
+    int* s_off = s_nact + P.Tseg + 2;
+    unsigned long long* barp = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(s_off + P.Tseg + 2) + 15) & ~uintptr_t(15));
+    const uint32_t dbar = smem_u32(barp);
+    const uint32_t tslot = dbar + 8;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = blockIdx.x / CL, c = blockIdx.x % CL;
+    const int ns = P.nslices, d = grp / ns, sl = grp % ns;
+    const TcDirP& A = P.dir[d];
+    for (int i = tid; i < P.Tseg + 2; i += NTH) {
+        const int tt = P.t0 - 1 + i;
+        s_nact[i] = (tt >= 0 && tt < P.Ttot) ? slice_rows(P.nact[tt], sl, ns) : 0;
+        s_off[i] = (tt >= 0 && tt <= P.Ttot) ? P.off[tt] : 0;
+    }
+    if (tid == 0) {
+        mbar_init(dbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot) : "memory");
+
+    // ---- R_own -> tensor memory: lane = gate*32 + unit, column j holds k = 2j, 2j+1.  Warps 0..3 own the four lane
+    // quadrants; quadrant 3 (lanes 96..127) is unused and zeroed.
+    if (warp < 4) {
+        const int gate = warp;
+        const uint4* src = gate < 3 ? reinterpret_cast<const uint4*>(A.R + (size_t)(gate * HH + UN * c + lane) * HH) : nullptr;
+        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + TM_A;
+#pragma unroll 1
+        for (int j = 0; j < 32; ++j) {   // 32 x 8 columns = 256 columns = 512 k
+            uint32_t r[8];
+            if (src) {
+                const uint4 v0 = src[2 * j], v1 = src[2 * j + 1];
+                r[0] = v0.x; r[1] = v0.y; r[2] = v0.z; r[3] = v0.w; r[4] = v1.x; r[5] = v1.y; r[6] = v1.z; r[7] = v1.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = 0u;
+            }
+            tc_st8(tbase + 8 * j, r);
+        }
+        tc_wait_st();
+    }
+    const int col = UN * c + lane;
+    const float bRr = A.bR[col], bRu = A.bR[HH + col], bRn = A.bR[2 * HH + col];
+    const int nloc = slice_rows(P.b, sl, ns);
+    for (int i = tid; i < nloc * UN; i += NTH) {
+        const int jl = i >> 5, u = i & 31;
+        hst[i] = A.h0 ? A.h0[(size_t)(jl * ns + sl) * HH + UN * c + u] : 0.f;
+    }
+    const size_t xpar = (size_t)P.bslr * (HH / 2);
+    unsigned long long* X = P.xbuf + (size_t)grp * 2 * xpar;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const uint32_t idesc = make_idesc(CN);
+    int na_prev = 0;
+    bool first = true;
+    uint32_t dphase = 0;
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long plast = clock64();
+    constexpr int NCHUNK16 = CN * 64;            // 16-byte operand chunks per MMA chunk
+    constexpr int PER_T = NCHUNK16 / NTH;        // per thread: CN / 4
+    constexpr int U = PER_T < 8 ? PER_T : 8;     // chunks polled together (2 x ld.v4 each)
+    constexpr int RPT = CN / 8;                  // rows per thread in the gate phase
+    for (int k = 0; k < P.Tseg; ++k) {
+        const int t = A.reverse ? P.t0 + P.Tseg - 1 - k : P.t0 + k;
+        const int na = NA(t);
+        if (na == 0) {
+            if (A.reverse) continue;
+            break;
+        }
+        PROF_MARK(0);
+        const long long row_base = OFF(t);
+        const int npoll = first ? 0 : min(na, na_prev);
+        const unsigned tag = P.tag_base + (unsigned)(k - 1), tagw = P.tag_base + (unsigned)k;
+        const unsigned long long* Xr = X + (size_t)((k - 1) & 1) * xpar;
+        unsigned long long* Xw = X + (size_t)(k & 1) * xpar;
+        for (int ch = 0; ch * CN < na; ++ch) {
+            const int nrows = min(CN, na - ch * CN);
+            // ---------------- operand staging: h_{t-1} of the chunk's rows -> swizzled shared memory
+#pragma unroll 1
+            for (int i0 = 0; i0 < PER_T; i0 += U) {
+                uint4 x[U][2];
+                bool need[U];
+                int nn[U], cc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int idx = (i0 + u) * NTH + tid;
+                    nn[u] = idx >> 6; cc[u] = idx & 63;
+                    need[u] = nn[u] < nrows && ch * CN + nn[u] < npoll;
+                }
+                if (!first) {
+                    bool ok;
+                    const long long tp0 = clock64();
+                    do {
+                        ok = true;
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            if (need[u]) {
+                                const unsigned long long* src = Xr + ((size_t)(ch * CN + nn[u]) * (HH / 2) + 4 * cc[u]);
+                                x[u][0] = ll_load2(src);
+                                x[u][1] = ll_load2(src + 2);
+                            }
+#pragma unroll
+                        for (int u = 0; u < U; ++u)
+                            if (need[u] && (x[u][0].y != tag || x[u][0].w != tag || x[u][1].y != tag || x[u][1].w != tag)) ok = false;
+                        POLL_GUARD(tp0);
+                    } while (!ok);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (nn[u] >= nrows) continue;
+                    uint32_t w0 = 0u, w1 = 0u, w2 = 0u, w3 = 0u;
+                    if (need[u]) {
+                        w0 = x[u][0].x; w1 = x[u][0].z; w2 = x[u][1].x; w3 = x[u][1].z;
+                    } else if (first && A.h0) {
+                        const float4* hp = reinterpret_cast<const float4*>(A.h0 + (size_t)((ch * CN + nn[u]) * ns + sl) * HH + 8 * cc[u]);
+                        const float4 a0 = hp[0], a1 = hp[1];
+                        w0 = pack2(a0.x, a0.y); w1 = pack2(a0.z, a0.w); w2 = pack2(a1.x, a1.y); w3 = pack2(a1.z, a1.w);
+                    }
+                    st_shared_v4(Hs + hs_off<CN>(nn[u], cc[u]), w0, w1, w2, w3);
+                }
+            }
+            PROF_MARK(1);   // poll + staging
+            // gx of the rows this thread finishes: L2 hits (prefetched two steps ago), complete under the MMAs
+            float gxv[RPT][3];
+#pragma unroll
+            for (int e = 0; e < RPT; ++e) {
+                const int n = warp + 8 * e;
+                gxv[e][0] = gxv[e][1] = gxv[e][2] = 0.f;
+                if (n < nrows) {
+                    const float* gp = A.gx + (size_t)(row_base + (long long)(ch * CN + n) * ns + sl) * A.ld_gx + col;
+                    gxv[e][0] = ld_f32(gp); gxv[e][1] = ld_f32(gp + HH); gxv[e][2] = ld_f32(gp + 2 * HH);
+                }
+            }
+            fence_async_smem();
+            __syncthreads();
+            PROF_MARK(2);   // barrier
+            // ---------------- D[128 x CN] = R_own[128 x 512] . h^T : one thread issues the 32 MMAs (warp 3: its lane
+            // quadrant holds no gate rows, so it does not wait for the accumulator below)
+            if (tid == 96) {
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const uint64_t db = make_desc_k(Hs + (uint32_t)((j >> 2) * (CN * 128) + (j & 3) * 32));
+                    tc_mma_ts(tmem + TM_D, tmem + TM_A + 8 * j, db, idesc, j > 0 ? 1u : 0u);
+                }
+                tc_commit(dbar);
+            }
+            // L2 prefetch of the gx rows of the step after next (one warp per row, round robin)
+            if (k + 2 < P.Tseg && ch == 0) {
+                const int tn = A.reverse ? t - 2 : t + 2;
+                const int nan = NA(tn);
+                const long long rbn = OFF(tn);
+                for (int n = warp; n < nan; n += NTH / 32) {
+                    const float* gp = A.gx + (size_t)(rbn + (long long)n * ns + sl) * A.ld_gx + UN * c;
+                    if (lane < 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + lane * HH));
+                }
+            }
+            // ---------------- accumulator -> registers -> G[gate][row][unit]: warps 0-2 read columns [0, CN/2), warps 4-6
+            // columns [CN/2, CN) of their lane quadrant (= gate)
+            if ((warp & 3) < 3) {
+                mbar_wait(dbar, dphase);
+                tc_fence_after();
+                const int gate = warp & 3, half = warp >> 2;
+                const uint32_t ta = tmem + ((uint32_t)(gate * 32) << 16) + TM_D + (uint32_t)(half * (CN / 2));
+                uint32_t r[CN / 2];
+#pragma unroll
+                for (int i = 0; i < CN / 16; ++i) tc_ld8(ta + 8 * i, r + 8 * i);
+                tc_wait_ld();
+                float* gp = G + ((size_t)gate * CN + half * (CN / 2)) * UN + lane;
+#pragma unroll
+                for (int i = 0; i < CN / 2; ++i) gp[i * UN] = __uint_as_float(r[i]);
+                tc_fence_before();
+            }
+            dphase ^= 1u;
+            PROF_MARK(3);   // MMA + accumulator read
+            __syncthreads();
+            PROF_MARK(4);
+            // ---------------- gates: lane = unit, warp -> rows w, w+8, ...
+#pragma unroll
+            for (int e = 0; e < RPT; ++e) {
+                const int n = warp + 8 * e;
+                if (n < nrows) {
+                    const float s0 = G[(0 * CN + n) * UN + lane], s1 = G[(1 * CN + n) * UN + lane], s2 = G[(2 * CN + n) * UN + lane];
+                    const float r = sigm(gxv[e][0] + s0 + bRr);
+                    const float z = sigm(gxv[e][1] + s1 + bRu);
+                    const float qq = s2 + bRn;
+                    const float nv = tanh_fast(gxv[e][2] + r * qq);
+                    const int jl = ch * CN + n;
+                    const float hp = hst[jl * UN + lane];
+                    const float h = (1.f - z) * nv + z * hp;
+                    const __nv_bfloat16 hb16 = __float2bfloat16(h);
+                    // publish first: this store is on every peer's critical path
+                    const uint32_t hb = (uint32_t)__bfloat16_as_ushort(hb16);
+                    const uint32_t ob = __shfl_down_sync(0xffffffffu, hb, 1);
+                    if (!(lane & 1)) ll_store(Xw + (size_t)jl * (HH / 2) + (col >> 1), hb | (ob << 16), tagw);
+                    hst[jl * UN + lane] = h;
+                    const size_t row = (size_t)(row_base + (long long)jl * ns + sl);
+                    if (A.hs_h) A.hs_h[row * A.ld_hs + col] = hb16;
+                    if (A.hs_f) A.hs_f[row * A.ld_hs + col] = h;
+                    if (A.cache) {
+                        float* cp = A.cache + row * 4 * HH + col;
+                        cp[0] = r; cp[HH] = z; cp[2 * HH] = nv; cp[3 * HH] = qq;
+                    }
+                }
+            }
+            PROF_MARK(5);   // gates + publish + bookkeeping
+        }
+        na_prev = na;
+        first = false;
+        PROF_MARK(6);
+    }
+    __syncthreads();
+    if (A.hT) {   // state handed to the next time segment of this layer
+        for (int i = tid; i < nloc * UN; i += NTH) {
+            const int jl = i >> 5, u = i & 31;
+            A.hT[(size_t)(jl * ns + sl) * HH + UN * c + u] = hst[i];
+        }
+    }
+    if (P.prof && tid == 0)
+        for (int i = 0; i < 8; ++i) P.prof[blockIdx.x * 8 + i] = pacc[i];
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+// =========================================================================================
+// unit test of the TS-form building blocks: D[128 x N] = A[128 x K] . B[N x K]^T with A written to tensor memory by
+// tcgen05.st, B staged in swizzled shared memory by plain stores, K = 64 * kblocks
+// =========================================================================================
+__global__ void __launch_bounds__(128, 1) k_test_ts_mma(const bf16* __restrict__ Ag, const bf16* __restrict__ Bg, float* __restrict__ Dg,
+                                                        int N, int K) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const uint32_t sbase = (smem_u32(sm_raw) + 1023u) & ~1023u;
+    const uint32_t Hs = sbase;
+    const uint32_t dbar = sbase + (uint32_t)(N * K * 2);
+    const uint32_t tslot = dbar + 8;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(dbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot) : "memory");
+    {   // A: thread = row (lane of tensor memory), K/2 columns
+        const uint4* src = reinterpret_cast<const uint4*>(Ag + (size_t)tid * K);
+        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + TM_A;
+        for (int j = 0; j < K / 16; ++j) {
+            const uint4 v0 = src[2 * j], v1 = src[2 * j + 1];
+            uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            tc_st8(tbase + 8 * j, r);
+        }
+        tc_wait_st();
+    }
+    // B: (N x K) row-major bf16 -> [k-block][N rows x 128 B], 128-byte swizzle
+    for (int idx = tid; idx < N * (K / 8); idx += 128) {
+        const int n = idx / (K / 8), cidx = idx % (K / 8);
+        const uint4 v = *reinterpret_cast<const uint4*>(Bg + (size_t)n * K + 8 * cidx);
+        const uint32_t off = (uint32_t)((cidx >> 3) * (N * 128) + (n >> 3) * 1024 + (n & 7) * 128 + (((cidx & 7) ^ (n & 7)) << 4));
+        st_shared_v4(Hs + off, v.x, v.y, v.z, v.w);
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(N);
+        for (int j = 0; j < K / 16; ++j) {
+            const uint64_t db = make_desc_k(Hs + (uint32_t)((j >> 2) * (N * 128) + (j & 3) * 32));
+            tc_mma_ts(tmem + TM_D, tmem + TM_A + 8 * j, db, idesc, j > 0 ? 1u : 0u);
+        }
+        tc_commit(dbar);
+    }
+    mbar_wait(dbar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t r[8];
+        tc_ld8(tmem + ((uint32_t)(warp * 32) << 16) + TM_D + c0, r);
+        tc_wait_ld();
+        for (int i = 0; i < 8; ++i) Dg[(size_t)tid * N + c0 + i] = __uint_as_float(r[i]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+template <int CN>
+size_t fwd_smem(int bslr, int Tseg) {
+    return 1024 + (size_t)CN * 1024 + (size_t)3 * CN * UN * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 16 + 16 + 16;
+}
+
+}  // namespace
+
+struct GruTcCtx {
+    int device = 0, num_sms = 148;
+    unsigned launch_id = 1;
+    static constexpr int NSLOT = 4;
+    unsigned long long* xbuf[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
+    size_t xcap[NSLOT] = {0, 0, 0, 0};
+    int pad_groups = 8;
+    int force_cn = 0;            // ARGSIM_GRU_TC_CN: rows per MMA chunk (16 / 32 / 64 / 128), 0 = by live rows
+    long long* prof = nullptr;   // ARGSIM_GRU_PROF=1
+};
+
+GruTcCtx* gru_tc_create(int device) {
+    GruTcCtx* c = new GruTcCtx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    const int max_smem = 232448;   // 227 KB: the launcher checks the actual request against it
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    if (const char* v = getenv("ARGSIM_GRU_PAD")) c->pad_groups = atoi(v);
+    if (const char* v = getenv("ARGSIM_GRU_TC_CN")) c->force_cn = atoi(v);
+    if (getenv("ARGSIM_GRU_PROF")) CUDA_CHECK(cudaMalloc(&c->prof, 160 * 8 * sizeof(long long)));
+    return c;
+}
+void gru_tc_destroy(GruTcCtx* c) {
+    if (!c) return;
+    for (int i = 0; i < GruTcCtx::NSLOT; ++i) cudaFree(c->xbuf[i]);
+    cudaFree(c->prof);
+    delete c;
+}
+bool gru_tc_supported(int H) { return H == HH; }
+
+// slices and rows per MMA chunk for `b` live rows of `ndir` directions: as many groups as fit (9 groups of 16 CTAs),
+// at least 16 rows per slice (N = 16 is the smallest M = 128 instruction); rows_per_slice > 0 forces the slice size
+static void tc_pick(const GruTcCtx* c, int ndir, int b, int rows_per_slice, int* ns, int* bslr, int* cn) {
+    const int max_groups = std::max(1, c->num_sms / CL);
+    const int per_want = rows_per_slice > 0 ? rows_per_slice : 16;
+    int s = std::max(1, std::min(max_groups / ndir, (b + per_want - 1) / per_want));
+    const int per = (b + s - 1) / s;
+    int n = per <= 16 ? 16 : per <= 32 ? 32 : per <= 64 ? 64 : 128;
+    if (c->force_cn == 16 || c->force_cn == 32 || c->force_cn == 64 || c->force_cn == 128) n = std::min(n, c->force_cn);
+    *ns = s;
+    *cn = n;
+    *bslr = (per + n - 1) / n * n;
+}
+bool gru_tc_fits(const GruTcCtx* c, int ndir, int b) {
+    int ns, bslr, cn;
+    tc_pick(c, ndir, b, 0, &ns, &bslr, &cn);
+    return ndir * CL <= c->num_sms && bslr <= MAX_BSL;
+}
+
+void gru_tc_fwd(GruTcCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& Pl, const int* d_off, const int* d_nact, int H,
+                cudaStream_t s, int t0, int Tseg, int slot, int rows_per_slice, int pad) {
+    if (H != HH) throw std::runtime_error("gru_tc: H must be 512");
+    if (Tseg < 0) { t0 = 0; Tseg = Pl.Tmax; }
+    if (Tseg >= 4096) throw std::runtime_error("gru_tc: more than 4095 steps per launch");
+    if (slot < 0 || slot >= GruTcCtx::NSLOT) throw std::runtime_error("gru_tc: bad slot");
+    TcFwdP P;
+    int ns, bslr, cn;
+    const int b_seg = (ndir == 1) ? Pl.nact[t0] : Pl.b;
+    tc_pick(c, ndir, b_seg, rows_per_slice, &ns, &bslr, &cn);
+    if (bslr > MAX_BSL) throw std::runtime_error("gru_tc: batch too large for the persistent kernel");
+    for (int d = 0; d < ndir; ++d) {
+        const GruFwdArgs& a = dirs[d];
+        if (!a.R_h) throw std::runtime_error("gru_tc: bf16 weights missing");
+        if (a.h0 && a.reverse && ndir != 1) throw std::runtime_error("gru_tc: a reverse direction takes h0 only in a single-direction (segment) launch");
+        P.dir[d] = TcDirP{a.gx, a.R_h, a.bR, a.h0, a.hs_f, a.hs_h, a.cache, a.hT, a.ld_gx, a.ld_hs, a.reverse};
+    }
+    if (ndir == 1) P.dir[1] = P.dir[0];
+    const int groups = ndir * ns;
+    const size_t need = (size_t)groups * 2 * bslr * (HH / 2);
+    if (need > c->xcap[slot]) {
+        CUDA_CHECK(cudaDeviceSynchronize());
+        cudaFree(c->xbuf[slot]);
+        CUDA_CHECK(cudaMalloc(&c->xbuf[slot], need * 8));
+        CUDA_CHECK(cudaMemset(c->xbuf[slot], 0, need * 8));
+        CUDA_CHECK(cudaDeviceSynchronize());
+        c->xcap[slot] = need;
+    }
+    P.off = d_off; P.nact = d_nact; P.xbuf = c->xbuf[slot];
+    P.ndir = ndir; P.nslices = ns; P.b = b_seg; P.Ttot = Pl.Tmax; P.t0 = t0; P.Tseg = Tseg; P.bslr = bslr;
+    P.tag_base = (c->launch_id++) << 12;
+    if (c->launch_id >= (1u << 20)) c->launch_id = 1;
+    P.prof = c->prof;
+    void* args[] = {&P};
+    const int grid_groups = pad ? std::max(groups, c->pad_groups) : groups;
+    void* fn; size_t smem;
+    switch (cn) {
+        case 16: fn = (void*)k_gru_tc_fwd<16>; smem = fwd_smem<16>(bslr, Tseg); break;
+        case 32: fn = (void*)k_gru_tc_fwd<32>; smem = fwd_smem<32>(bslr, Tseg); break;
+        case 64: fn = (void*)k_gru_tc_fwd<64>; smem = fwd_smem<64>(bslr, Tseg); break;
+        default: fn = (void*)k_gru_tc_fwd<128>; smem = fwd_smem<128>(bslr, Tseg); break;
+    }
+    if (smem > 232448) throw std::runtime_error("gru_tc: shared memory request exceeds 227 KB (segment too long for this slice size)");
+    if (pad == 2) CUDA_CHECK(cudaLaunchKernel(fn, dim3(grid_groups * CL), dim3(NTH), args, smem, s));
+    else CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid_groups * CL), dim3(NTH), args, smem, s));
+    COUNT_LAUNCH();
+    if (c->prof) {
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        std::vector<long long> h((size_t)groups * CL * 8);
+        CUDA_CHECK(cudaMemcpy(h.data(), c->prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        double avg[8] = {0};
+        for (int b2 = 0; b2 < groups * CL; ++b2)
+            for (int i = 0; i < 8; ++i) avg[i] += (double)h[b2 * 8 + i] / (groups * CL);
+        fprintf(stderr, "[gru_tc_prof] fwd ndir=%d ns=%d cn=%d steps=%d cycles/step:", ndir, ns, cn, Tseg);
+        for (int i = 0; i < 8; ++i) fprintf(stderr, " p%d=%.0f", i, avg[i] / Tseg);
+        fprintf(stderr, "\n");
+    }
+}
+
+// D(128,N) = A(128,K) . B(N,K)^T through tensor memory (TS form); device pointers, bf16 operands, fp32 out
+void gru_tc_test_mma(const bf16* A, const bf16* B, float* D, int N, int K, cudaStream_t s) {
+    if (N % 16 || N < 16 || N > 128 || K % 64 || K < 64 || K > 512) throw std::runtime_error("gru_tc_test_mma: N in 16..128 step 16, K in 64..512 step 64");
+    const size_t smem = 1024 + (size_t)N * K * 2 + 64;
+    CUDA_CHECK(cudaFuncSetAttribute(k_test_ts_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_test_ts_mma<<<1, 128, smem, s>>>(A, B, D, N, K);
+    CUDA_CHECK(cudaGetLastError());
+    COUNT_LAUNCH();
+}

@@ -113,5 +113,15 @@ void gru_mma_fwd(GruMmaCtx*, const GruFwdArgs* dirs, int ndir, const SeqPlan& P,
 // chunk: rows per chunk of this launch, 0 = the context's default (16, or 8 with ARGSIM_GRU_CHUNK=8), 8, 16
 void gru_mma_bwd(GruMmaCtx*, const GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
                  int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0, int alone = 0, int pad = 0, int chunk = 0);
+// tensor-memory path (gru_tc.cu): the same recurrence on tcgen05, R_own resident in TMEM (TS form), N = 16..128 rows
+// per MMA.  rows_per_slice: 0 = as many 16-row slices as groups fit, else the wanted slice size
+struct GruTcCtx;
+GruTcCtx* gru_tc_create(int device);
+void gru_tc_destroy(GruTcCtx*);
+bool gru_tc_supported(int H);
+bool gru_tc_fits(const GruTcCtx*, int ndir, int b);
+void gru_tc_fwd(GruTcCtx*, const GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
+                int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0, int rows_per_slice = 0, int pad = 0);
+void gru_tc_test_mma(const bf16* A, const bf16* B, float* D, int N, int K, cudaStream_t s);
 // xbench.cu: exchange-latency measurement hook
 int xbench_run(int device, int method, int groups, int rows, int iters, double* cycles_per_iter, int* max_clusters);

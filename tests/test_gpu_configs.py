@@ -73,6 +73,10 @@ def test_c1_full_size_all_gradients_match_torch_autograd(c1):
             if name == 'fp32':
                 err = np.abs(g - r).max() / (np.abs(r).max() + 1e-30)
                 assert err < 2e-4, (name, k, err)
+            elif np.linalg.norm(r) < 1e-12:
+                # exactly zero in the oracle too: the top layer's reverse GRU feeds the latent only through its output at
+                # t = len-1 (src/model.py:135), its FIRST step, where h_prev = 0 -- so d R of encode/rnn3/bwd vanishes
+                assert np.linalg.norm(g) < 1e-9, (name, k, np.linalg.norm(g))
             else:
                 cos = float(g @ r) / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30)
                 ratio = np.linalg.norm(g) / (np.linalg.norm(r) + 1e-30)
@@ -93,7 +97,8 @@ def test_c1_bf16_ten_step_trajectory_matches_oracle(c1):
     h.set_params(P)
     h.step = STEP
     worst = 0.0
-    for i in range(10):
+    import os
+    for i in range(int(os.environ.get('ARGSIM_TRAJ_STEPS', 10))):
         keep, eps = _draw(src, 100 + i)
         o = T.train_step(Pt, M, V, C1, src, src, STEP + i, _oracle_keep(keep, src, 1).astype(np.int64), eps)
         st = h.train_step(src, src, keep=keep, eps=eps)
@@ -148,6 +153,8 @@ def test_scaled_config_dims_match_oracle():
             if name == 'fp32':
                 err = np.abs(g - r).max() / (np.abs(r).max() + 1e-30)
                 assert err < 2e-4, (name, k, err)
+            elif np.linalg.norm(r) < 1e-12:
+                assert np.linalg.norm(g) < 1e-9, (name, k, np.linalg.norm(g))
             else:
                 cos = float(g @ r) / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30)
                 assert cos > 0.995, (name, k, cos)

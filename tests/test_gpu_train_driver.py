@@ -98,7 +98,7 @@ def test_train_driver_resume_embed_decode(tmp_path):
     M._state.update(config=None, session=None)
 
     # --sample (src/train.py:56-63): src and tgt are two independent sampled segmentations of each text
-    train.main(['--rounds', '1', '--ckpt', 'unit0', '--sample', '--trial', 'kudo'] + common[2:])
+    train.main(['--rounds', '1', '--ckpt', 'unit0', '--sample'] + [('kudo' if a == 'unit' else a) for a in common])
     log = [json.loads(l) for l in open(d + '/log/kudo.jsonl')]
     assert [r['step'] for r in log] == [100, 125, 150]
     assert all(np.isfinite([r['step_errt'], r['step_loss_gen'], r['step_loss_kld']]).all() for r in log)

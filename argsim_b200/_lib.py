@@ -72,7 +72,7 @@ SIGNATURES = {
                                    _f32p, _f32p, C.c_float, C.c_int32, _f32p, _f32p]),
     'argsim_test_softmax_ce': (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, _f32p, _i32p, C.c_float, C.c_int32, _f32p,
                                          _f32p, _f32p, _i32p, C.POINTER(C.c_double)]),
-    'argsim_test_ts_mma': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _f32p]),
+    'argsim_test_ts_mma': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _f32p, _i64p]),
     'argsim_bench_exchange': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), _i32p]),
     'argsim_bench_kernel': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, _f32p, C.POINTER(C.c_double),
                                       C.POINTER(C.c_double)]),
@@ -192,16 +192,18 @@ def test_softmax_ce(logits, labels=None, gscale=1.0, bf16=True, write_grad=True,
     return dict(grad=grad, loss_samp=loss, err_samp=err, pred=pred, stats=np.array(stats[:]))
 
 
-def test_ts_mma(A, B, device=0):
-    """D = A . B^T through tensor memory (TS-form tcgen05.mma); A (128,K), B (N,K), operands rounded to bf16."""
+def test_ts_mma(A, B, nacc=1, device=0, want_cycles=False):
+    """D = A . B^T through tensor memory (TS-form tcgen05.mma); A (128,K), B (N,K), operands rounded to bf16; the K/16
+    instructions go round robin over `nacc` accumulators."""
     A = np.ascontiguousarray(A, np.float32)
     B = np.ascontiguousarray(B, np.float32)
     assert A.shape[0] == 128 and A.shape[1] == B.shape[1]
     D = np.zeros((128, B.shape[0]), np.float32)
-    rc = lib().argsim_test_ts_mma(device, B.shape[0], A.shape[1], _p(A, _f32p), _p(B, _f32p), _p(D, _f32p))
+    cyc = np.zeros(1, np.int64)
+    rc = lib().argsim_test_ts_mma(device, B.shape[0], A.shape[1], nacc, _p(A, _f32p), _p(B, _f32p), _p(D, _f32p), _p(cyc, _i64p))
     if rc != 0:
         raise RuntimeError(lib().argsim_last_error(None).decode())
-    return D
+    return (D, int(cyc[0])) if want_cycles else D
 
 
 def bench_exchange(method, groups, rows, iters=2000, device=0):

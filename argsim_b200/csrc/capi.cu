@@ -275,7 +275,7 @@ int argsim_test_gemm(int32_t device, int32_t impl, int32_t M, int32_t N, int32_t
     return 0;
 }
 
-int argsim_test_ts_mma(int32_t device, int32_t N, int32_t K, const float* A, const float* B, float* D) {
+int argsim_test_ts_mma(int32_t device, int32_t N, int32_t K, int32_t nacc, const float* A, const float* B, float* D, int64_t* cycles) {
     try {
         CUDA_CHECK(cudaSetDevice(device));
         const size_t na = (size_t)128 * K, nb = (size_t)N * K, nd = (size_t)128 * N;
@@ -288,7 +288,8 @@ int argsim_test_ts_mma(int32_t device, int32_t N, int32_t K, const float* A, con
         CUDA_CHECK(cudaMemset(dD, 0, nd * 4));
         launch_cast_bf16(dA, hA, (long long)na, 0);
         launch_cast_bf16(dB, hB, (long long)nb, 0);
-        gru_tc_test_mma(hA, hB, dD, N, K, 0);
+        const long long cyc = gru_tc_test_mma(hA, hB, dD, N, K, nacc, 0);
+        if (cycles) *cycles = cyc;
         CUDA_CHECK(cudaDeviceSynchronize());
         CUDA_CHECK(cudaMemcpy(D, dD, nd * 4, cudaMemcpyDeviceToHost));
         cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(hA); cudaFree(hB);

@@ -337,10 +337,16 @@ void Engine::gru_fwd(GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_
     else gru_generic_fwd(dirs, ndir, P, H, gru_work, st);
     kend();
 }
+void Engine::rec_bwd(const GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact, cudaStream_t q, int t0,
+                     int Tseg, int slot, int want8, int pad, int chunk) {
+    if ((gru_tc_mode & 2) && tc) gru_tc_bwd(tc, dirs, ndir, P, d_off, d_nact, H, q, t0, Tseg, slot, 0, pad);
+    else gru_mma_bwd(mma, dirs, ndir, P, d_off, d_nact, H, q, t0, Tseg, slot, want8, pad, chunk);
+}
 void Engine::gru_bwd(GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact) {
     if (arena.dry) return;
     kbegin(ndir == 2 ? "k:gru_bwd_enc" : "k:gru_bwd_dec");
-    if (use_mma && gru_mma_fits(mma, ndir, P.b)) gru_mma_bwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0], 0, -1, 0, 0, /*pad: runs alone*/ 1);
+    if (use_mma && (gru_tc_mode & 2) && tc && gru_tc_fits(tc, ndir, P.b)) rec_bwd(dirs, ndir, P, d_off, d_nact, st[0], 0, -1, 0, 0, /*pad: runs alone*/ 1, 0);
+    else if (use_mma && gru_mma_fits(mma, ndir, P.b)) gru_mma_bwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0], 0, -1, 0, 0, /*pad: runs alone*/ 1);
     else gru_generic_bwd(dirs, ndir, P, H, gru_work, st);
     kend();
 }
@@ -937,7 +943,7 @@ void Engine::program(int mode, bool apply_update) {
                     GruBwdArgs a = dec_bwd_args(j, dYl[j], dGXl[j], dGHl[j], HPl[j], dh0l[j]);
                     a.dh_in = (sg + 1 < nseg) ? carry[j][(sg + 1) & 1] : nullptr;
                     a.dh_out = (sg > 0) ? carry[j][sg & 1] : nullptr;
-                    gru_mma_bwd(mma, &a, 1, Dp, dp.dec_off, dp.dec_nact, H, q, t0, tl, j, want8[(size_t)j * nseg + sg], pad_wave);   // the reverse wavefront pairs the same (j, sg) launches
+                    rec_bwd(&a, 1, Dp, dp.dec_off, dp.dec_nact, q, t0, tl, j, want8[(size_t)j * nseg + sg], pad_wave, 0);   // the reverse wavefront pairs the same (j, sg) launches
                     done[j * nseg + sg] = next_event();
                     CUDA_CHECK(cudaEventRecord(done[j * nseg + sg], q));
                 }
@@ -1112,7 +1118,7 @@ void Engine::program(int mode, bool apply_update) {
                         GruBwdArgs x = a[d];
                         x.dh_in = (k > 0) ? carry[d][(k - 1) & 1] : nullptr;
                         x.dh_out = (k + 1 < nsegE) ? carry[d][k & 1] : nullptr;
-                        gru_mma_bwd(mma, &x, 1, E, dp.enc_off, dp.enc_nact, H, sw[d], t0, tl, d, want8[(size_t)d * nsegE + k], pad_wave, enc_bwd_chunk);
+                        rec_bwd(&x, 1, E, dp.enc_off, dp.enc_nact, sw[d], t0, tl, d, want8[(size_t)d * nsegE + k], pad_wave, enc_bwd_chunk);
                         if (seg_wgrad) {
                             // the segment's rows of d gates are final: their share of the weight / bias gradients goes to
                             // the side stream now, so only the last segment's share is left when the chains end

@@ -125,7 +125,9 @@ private:
     Arena arena;
     GruMmaCtx* mma = nullptr;
     GruTcCtx* tc = nullptr;      // tensor-memory recurrence (gru_tc.cu)
-    int gru_tc_mode = 0;         // ARGSIM_GRU_TC: bit 0 = forward recurrences on the tcgen05 kernel
+    int gru_tc_mode = 0;         // ARGSIM_GRU_TC: bit 0 = forward, bit 1 = backward recurrences on the tcgen05 kernels
+    void rec_bwd(const GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact, cudaStream_t q, int t0,
+                 int Tseg, int slot, int want8, int pad, int chunk);
     // one forward recurrence launch on whichever persistent kernel is selected (want8: the mma.sync kernel's slice request)
     void rec_fwd(const GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact, cudaStream_t q, int t0,
                  int Tseg, int slot, int want8, int pad);

@@ -122,6 +122,9 @@ bool gru_tc_supported(int H);
 bool gru_tc_fits(const GruTcCtx*, int ndir, int b);
 void gru_tc_fwd(GruTcCtx*, const GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
                 int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0, int rows_per_slice = 0, int pad = 0);
-void gru_tc_test_mma(const bf16* A, const bf16* B, float* D, int N, int K, cudaStream_t s);
+void gru_tc_bwd(GruTcCtx*, const GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
+                int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0, int rows_per_slice = 0, int pad = 0);
+// returns the cycles from the first MMA issue to the completion of the last (K/16 MMAs round robin over nacc accumulators)
+long long gru_tc_test_mma(const bf16* A, const bf16* B, float* D, int N, int K, int nacc, cudaStream_t s);
 // xbench.cu: exchange-latency measurement hook
 int xbench_run(int device, int method, int groups, int rows, int iters, double* cycles_per_iter, int* max_clusters);

@@ -160,8 +160,10 @@ int  argsim_test_softmax_ce(int32_t device, int32_t bf16_mode, int64_t n, int32_
                             float* loss_samp, float* err_samp, int32_t* pred, double stats[2]);
 /* unit-test hook for the building blocks of the tensor-memory recurrence (csrc/gru_tc.cu): D(128,N) = A(128,K) . B(N,K)^T
  * with A written to TMEM by tcgen05.st and read by the TS form of tcgen05.mma, B staged in 128-byte-swizzled shared
- * memory; operands rounded to bf16, fp32 out.  N in 16..128 (step 16), K in 64..512 (step 64). */
-int  argsim_test_ts_mma(int32_t device, int32_t N, int32_t K, const float* A, const float* B, float* D);
+ * memory; operands rounded to bf16, fp32 out.  N in 16..128 (step 16), K in 64..512 (step 64).  The K/16 instructions
+ * go round robin over `nacc` accumulators (summed on read-back); *cycles = first issue -> completion of the last. */
+int  argsim_test_ts_mma(int32_t device, int32_t N, int32_t K, int32_t nacc, const float* A, const float* B, float* D,
+                        int64_t* cycles);
 /* measurement hook: cycles per all-gather round among the 16 CTAs of a recurrence group (every CTA publishes
  * rows x 32 bf16 units and needs all 512 before going on), `groups` groups running side by side.  method 0: L2 words
  * with in-band tags, volatile; 1: the same, relaxed.gpu; 2: cluster, tagged words into the peers' shared memory;

@@ -17,13 +17,13 @@ def _bf16(x):
     return u.astype(np.uint32).view(np.float32)
 
 
-@pytest.mark.parametrize('N,K', [(16, 64), (16, 512), (32, 128), (64, 256), (128, 512)])
-def test_ts_form_mma_matches_numpy(N, K):
+@pytest.mark.parametrize('N,K,nacc', [(16, 64, 1), (16, 512, 1), (16, 512, 8), (32, 128, 2), (32, 512, 8), (64, 256, 4), (128, 512, 2)])
+def test_ts_form_mma_matches_numpy(N, K, nacc):
     from argsim_b200 import _lib
     rng = np.random.default_rng(N * 1000 + K)
     A = rng.standard_normal((128, K)).astype(np.float32)
     B = rng.standard_normal((N, K)).astype(np.float32)
-    D = _lib.test_ts_mma(A, B)
+    D = _lib.test_ts_mma(A, B, nacc=nacc)
     ref = _bf16(A).astype(np.float64) @ _bf16(B).astype(np.float64).T
     err = np.abs(D - ref).max() / np.abs(ref).max()
     assert err < 1e-5, (N, K, err)
@@ -32,18 +32,19 @@ def test_ts_form_mma_matches_numpy(N, K):
     A2 = np.zeros((128, K), np.float32)
     A2[np.arange(128), (np.arange(128) * 7) % K] = 1.0
     B2 = (np.arange(N * K, dtype=np.float32).reshape(N, K) % 251) / 8.0       # exactly representable in bf16
-    D2 = _lib.test_ts_mma(A2, B2)
+    D2 = _lib.test_ts_mma(A2, B2, nacc=nacc)
     np.testing.assert_array_equal(D2, B2[:, (np.arange(128) * 7) % K].T)
 
 
+@pytest.mark.parametrize('mode', [1, 3])    # 1: forward recurrences on gru_tc.cu, backward on gru_mma.cu; 3: both on gru_tc.cu
 @pytest.mark.parametrize('b,tmax', [(3, 9), (64, 40), (100, 23), (150, 23), (257, 12), (512, 9)])
-def test_tensor_memory_recurrence_matches_generic(monkeypatch, b, tmax):
-    """forward recurrences on gru_tc.cu (ARGSIM_GRU_TC=1; the backward stays on gru_mma.cu) against the per-step generic
-    GRU: losses, every gradient (the gate cache and hs the backward reads come from the new kernel), mu"""
+def test_tensor_memory_recurrence_matches_generic(monkeypatch, b, tmax, mode):
+    """recurrences on gru_tc.cu (ARGSIM_GRU_TC) against the per-step generic GRU: losses, every gradient (the gate cache
+    and hs the backward reads come from the new forward kernel), mu"""
     from argsim_b200 import _lib
     cfg = dict(dim_tgt=1024, dim_emb=512, dim_rep=256, rnn_layers=2, accelerate=1e-4, learn_rate=1e-3, bos=2, eos=1)
     hg, P = _mk(cfg, _lib.BF16, flags=4)
-    monkeypatch.setenv('ARGSIM_GRU_TC', '1')
+    monkeypatch.setenv('ARGSIM_GRU_TC', str(mode))
     hm, _ = _mk(cfg, _lib.BF16, flags=0)
     src = ragged_batch(b, tmax, cfg['dim_tgt'], 60 + b)
     tgt = ragged_batch(b, max(2, tmax - 3), cfg['dim_tgt'], 61 + b)
@@ -72,14 +73,16 @@ def test_tensor_memory_recurrence_matches_generic(monkeypatch, b, tmax):
     assert rel(m['loss'], a['loss']) < 2e-3
 
 
+@pytest.mark.parametrize('mode', [1, 3])
 @pytest.mark.parametrize('seg,b,tmax', [(8, 40, 37), (5, 130, 21)])
-def test_tensor_memory_recurrence_in_the_decoder_wavefront(monkeypatch, seg, b, tmax):
+def test_tensor_memory_recurrence_in_the_decoder_wavefront(monkeypatch, seg, b, tmax, mode):
     """time-segmented launches (state hand-over through hT / h0, one stream per decoder layer) on the tcgen05 kernel"""
     from argsim_b200 import _lib
     cfg = dict(dim_tgt=1024, dim_emb=512, dim_rep=256, rnn_layers=3, accelerate=1e-4, learn_rate=1e-3, bos=2, eos=1)
     hg, P = _mk(cfg, _lib.BF16, flags=4)
     monkeypatch.setenv('ARGSIM_DEC_SEG', str(seg))
-    monkeypatch.setenv('ARGSIM_GRU_TC', '1')
+    monkeypatch.setenv('ARGSIM_ENC_SEG', str(2 * seg))      # the encoder's BPTT as two chains of segment launches too
+    monkeypatch.setenv('ARGSIM_GRU_TC', str(mode))
     hm, _ = _mk(cfg, _lib.BF16, flags=0)
     src = ragged_batch(b, tmax, cfg['dim_tgt'], 70 + b)
     tgt = ragged_batch(b, tmax, cfg['dim_tgt'], 71 + b)
@@ -90,5 +93,15 @@ def test_tensor_memory_recurrence_in_the_decoder_wavefront(monkeypatch, seg, b, 
     m = hm.grad_step(src, tgt, keep=keep, eps=eps)
     for name in ('loss', 'loss_gen', 'loss_kld'):
         assert rel(m[name], a[name]) < 2e-3, (name, m[name], a[name])
+    bad = {}
+    for k in P:
+        g, r = hm.get_grad(k).astype(np.float64).ravel(), hg.get_grad(k).astype(np.float64).ravel()
+        if np.linalg.norm(r) < 1e-12:
+            continue
+        cos = g @ r / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30)
+        ratio = np.linalg.norm(g) / np.linalg.norm(r)
+        if not (cos > 0.998 and abs(ratio - 1) < 0.02):
+            bad[k] = (round(float(cos), 4), round(float(ratio), 4))
+    assert not bad, bad
     e1, e2 = hm.eval_step(src, tgt), hg.eval_step(src, tgt)
     assert rel(e1['loss_gen_samp'].mean(), e2['loss_gen_samp'].mean()) < 2e-3

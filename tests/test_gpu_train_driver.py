@@ -100,7 +100,7 @@ def test_train_driver_resume_embed_decode(tmp_path):
     # --sample (src/train.py:56-63): src and tgt are two independent sampled segmentations of each text
     train.main(['--rounds', '1', '--ckpt', 'unit0', '--sample'] + [('kudo' if a == 'unit' else a) for a in common])
     log = [json.loads(l) for l in open(d + '/log/kudo.jsonl')]
-    assert [r['step'] for r in log] == [100, 125, 150]
+    assert [r['step'] for r in log] == [175, 200, 225]      # 'unit0' was overwritten by the resumed run at step 150
     assert all(np.isfinite([r['step_errt'], r['step_loss_gen'], r['step_loss_kld']]).all() for r in log)
     M._state['session'].close()
     M._state.update(config=None, session=None)

@@ -42,6 +42,7 @@ struct TcFwdP {
     int ndir, nslices, b, Ttot, t0, Tseg, bslr;
     unsigned tag_base;
     long long* prof;
+    int poll_delay;    // cycles a stage warp lets pass after the local publish before its first poll round
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_tc_fwd(const __grid_constant__ T
         s_off[i] = (tt >= 0 && tt <= P.Ttot) ? P.off[tt] : 0;
     }
     if (tid == 0) {
-        mbar_init(dbar, 1);
+        mbar_init(dbar, CN <= 32 ? 4 : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_tc_fwd(const __grid_constant__ T
     tc_fence_after();
 
     const uint32_t idesc = make_idesc(CN);
+    constexpr int NACC1 = CN <= 32 ? 4 : 1;
     int na_prev = 0;
     bool first = true;
     uint32_t dphase = 0;
@@ -301,9 +303,24 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_tc_fwd(const __grid_constant__ T
             fence_async_smem();
             __syncthreads();
             PROF_MARK(2);   // barrier
-            // ---------------- D[128 x CN] = R_own[128 x 512] . h^T : one thread issues the 32 MMAs (warp 3: its lane
-            // quadrant holds no gate rows, so it does not wait for the accumulator below)
-            if (warp == 3) {
+            // ---------------- D[128 x CN] = R_own[128 x 512] . h^T.  CN <= 32: warps 0..3 issue 8 MMAs each (their own quarter
+            // of K) into their own accumulator -- one thread needs ~19 cycles per tcgen05.mma, the tensor pipe 8 at N = 16;
+            // the gate warps add the four partial sums.  CN >= 64: tensor-bound, one issuer (warp 3), one accumulator.
+            if (NACC1 == 4) {
+                if (warp < 4) {
+                    if (elect_one()) {
+                        tc_fence_after();
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int jj = 8 * warp + j;
+                            const uint64_t db = make_desc_k(Hs + (uint32_t)((jj >> 2) * (CN * 128) + (jj & 3) * 32));
+                            tc_mma_ts(tmem + TM_D + (uint32_t)(warp * CN), tmem + TM_A + 8 * jj, db, idesc, j > 0 ? 1u : 0u);
+                        }
+                        tc_commit(dbar);
+                    }
+                    __syncwarp();
+                }
+            } else if (warp == 3) {
                 if (elect_one()) {
                     tc_fence_after();
 #pragma unroll
@@ -332,13 +349,20 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_tc_fwd(const __grid_constant__ T
                 tc_fence_after();
                 const int gate = warp & 3, half = warp >> 2;
                 const uint32_t ta = tmem + ((uint32_t)(gate * 32) << 16) + TM_D + (uint32_t)(half * (CN / 2));
-                uint32_t r[CN / 2];
+                uint32_t r[NACC1][CN / 2];
 #pragma unroll
-                for (int i = 0; i < CN / 16; ++i) tc_ld8(ta + 8 * i, r + 8 * i);
+                for (int a = 0; a < NACC1; ++a)
+#pragma unroll
+                    for (int i = 0; i < CN / 16; ++i) tc_ld8(ta + (uint32_t)(a * CN) + 8 * i, r[a] + 8 * i);
                 tc_wait_ld();
                 float* gp = G + ((size_t)gate * CN + half * (CN / 2)) * UN + lane;
 #pragma unroll
-                for (int i = 0; i < CN / 2; ++i) gp[i * UN] = __uint_as_float(r[i]);
+                for (int i = 0; i < CN / 2; ++i) {
+                    float v = __uint_as_float(r[0][i]);
+#pragma unroll
+                    for (int a = 1; a < NACC1; ++a) v += __uint_as_float(r[a][i]);
+                    gp[i * UN] = v;
+                }
                 tc_fence_before();
             }
             dphase ^= 1u;
@@ -393,6 +417,377 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_tc_fwd(const __grid_constant__ T
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
+
+// =========================================================================================
+// forward, warp-specialised (the default): three roles that hand chunks of CN rows to each other through mbarriers
+//   warps 8..11  STAGE : warp w polls k-blocks 2(w-8), 2(w-8)+1 (128 units = the slices of 4 CTAs) of the chunk's rows
+//                        from the exchange buffer and writes them into the operand tile (slot = chunk number & 1);
+//   warp  12     MMA   : as each pair of k-blocks lands, one lane issues its 8 tcgen05.mma (K = 16 each) into the slot's
+//                        accumulator; after the 32nd it commits to the slot's "accumulator full" mbarrier;
+//   warps 0..7   GATE  : read the accumulator (lane quadrant = gate, two column halves), combine the three gates of a
+//                        unit through shared memory, finish the GRU cell, publish the new h, write the bookkeeping.
+// No block-wide barrier in the loop.  With one chunk per step (few live rows: the latency regime) the roles simply take
+// turns and the MMAs of a k-block start while the other k-blocks are still in flight; with several chunks per step
+// (many rows) the staging of chunk i+1 and the gate math of chunk i-1 run under the MMAs of chunk i.
+// CN = 16, 32 or 64 (two operand slots of CN KB, two accumulators of CN columns).
+// =========================================================================================
+constexpr int NTH2 = 416;    // 13 warps: 8 gate, 4 stage, 1 MMA
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void gate_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int CN>
+__global__ void __launch_bounds__(NTH2, 1) k_gru_tc_fwd2(const __grid_constant__ TcFwdP P) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    if ((int)(blockIdx.x / CL) >= P.ndir * P.nslices) return;
+    const uint32_t sbase = (smem_u32(sm_raw) + 1023u) & ~1023u;
+    unsigned char* const sm = sm_raw + (sbase - smem_u32(sm_raw));
+    // [Hs: 2 x CN KB][G: 2 x 3*CN*32 f32][hst: bslr*32 f32][tables: 2*(Tseg+2) int][barriers: 12 x 8 B][slot 4]
+    const uint32_t Hs0 = sbase;
+    float* G0 = reinterpret_cast<float*>(sm + 2 * CN * 1024);
+    float* hst = G0 + 2 * 3 * CN * UN;
+    int* s_nact = reinterpret_cast<int*>(hst + (size_t)P.bslr * UN);
+    int* s_off = s_nact + P.Tseg + 2;
+    unsigned long long* barp = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(s_off + P.Tseg + 2) + 15) & ~uintptr_t(15));
+    const uint32_t bars = smem_u32(barp);
+    auto kfull = [&](int slot, int kp) { return bars + 8u * (uint32_t)(slot * 4 + kp); };
+    auto dfull = [&](int slot) { return bars + 8u * (uint32_t)(8 + slot); };
+    auto dfree = [&](int slot) { return bars + 8u * (uint32_t)(10 + slot); };
+    const uint32_t tslot = bars + 8u * 12;
+    // chunks whose new h this CTA's own gate warps have published (8 increments per chunk): the stage warps start to
+    // poll a chunk only when its predecessor has been published HERE -- the peers run in lock step, so their words are
+    // then in flight; polling any earlier only loads the L2 (measured: 3,400 instead of 1,000 cycles until the data shows)
+    volatile int* s_pub = reinterpret_cast<volatile int*>(barp + 13);
+    // CN <= 32: every stage warp issues the 8 MMAs of its own k-blocks into its own accumulator (4 per slot, summed by the
+    // gate warps): the issue of 32 MMAs (~19 cycles each from one thread) is spread over 4 threads.  CN = 64: the MMAs
+    // are tensor-bound (32 cycles each), one accumulator per slot, issued by the MMA warp.
+    constexpr bool SPLIT = CN <= 32;
+    constexpr int NACC = SPLIT ? 4 : 1;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = blockIdx.x / CL, c = blockIdx.x % CL;
+    const int ns = P.nslices, d = grp / ns, sl = grp % ns;
+    const TcDirP& A = P.dir[d];
+    if (tid == 0) *s_pub = 0;
+    for (int i = tid; i < P.Tseg + 2; i += NTH2) {
+        const int tt = P.t0 - 1 + i;
+        s_nact[i] = (tt >= 0 && tt < P.Ttot) ? slice_rows(P.nact[tt], sl, ns) : 0;
+        s_off[i] = (tt >= 0 && tt <= P.Ttot) ? P.off[tt] : 0;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 8; ++i) mbar_init(bars + 8u * i, 1);
+        mbar_init(dfull(0), SPLIT ? 4 : 1); mbar_init(dfull(1), SPLIT ? 4 : 1);
+        mbar_init(dfree(0), 6); mbar_init(dfree(1), 6);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot) : "memory");
+
+    if (warp < 4) {   // R_own -> tensor memory (see k_gru_tc_fwd)
+        const int gate = warp;
+        const uint4* src = gate < 3 ? reinterpret_cast<const uint4*>(A.R + (size_t)(gate * HH + UN * c + lane) * HH) : nullptr;
+        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + TM_A;
+#pragma unroll 1
+        for (int j = 0; j < 32; ++j) {
+            uint32_t r[8];
+            if (src) {
+                const uint4 v0 = src[2 * j], v1 = src[2 * j + 1];
+                r[0] = v0.x; r[1] = v0.y; r[2] = v0.z; r[3] = v0.w; r[4] = v1.x; r[5] = v1.y; r[6] = v1.z; r[7] = v1.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = 0u;
+            }
+            tc_st8(tbase + 8 * j, r);
+        }
+        tc_wait_st();
+    }
+    const int nloc = slice_rows(P.b, sl, ns);
+    for (int i = tid; i < nloc * UN; i += NTH2) {
+        const int jl = i >> 5, u = i & 31;
+        hst[i] = A.h0 ? A.h0[(size_t)(jl * ns + sl) * HH + UN * c + u] : 0.f;
+    }
+    const size_t xpar = (size_t)P.bslr * (HH / 2);
+    unsigned long long* X = P.xbuf + (size_t)grp * 2 * xpar;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long plast = clock64();
+#define PROF_MARK_L(i) do { if (P.prof && lane == 0) { const long long now_ = clock64(); pacc[i] += now_ - plast; plast = now_; } } while (0)
+    if (warp < 8) {
+        // =========================== GATE warps ===========================
+        const int gw = warp, quad = warp & 3, half = warp >> 2;
+        const int col = UN * c + lane;
+        const float bRr = A.bR[col], bRu = A.bR[HH + col], bRn = A.bR[2 * HH + col];
+        constexpr int RPT = CN / 8;
+        int q = 0;
+        for (int k = 0; k < P.Tseg; ++k) {
+            const int t = A.reverse ? P.t0 + P.Tseg - 1 - k : P.t0 + k;
+            const int na = NA(t);
+            if (na == 0) {
+                if (A.reverse) continue;
+                break;
+            }
+            const long long row_base = OFF(t);
+            const unsigned tagw = P.tag_base + (unsigned)k;
+            unsigned long long* Xw = X + (size_t)(k & 1) * xpar;
+            for (int ch = 0; ch * CN < na; ++ch, ++q) {
+                const int slot = q & 1, u = q >> 1;
+                const int nrows = min(CN, na - ch * CN);
+                PROF_MARK(0);
+                float gxv[RPT][3];
+#pragma unroll
+                for (int e = 0; e < RPT; ++e) {
+                    const int n = gw + 8 * e;
+                    gxv[e][0] = gxv[e][1] = gxv[e][2] = 0.f;
+                    if (n < nrows) {
+                        const float* gp = A.gx + (size_t)(row_base + (long long)(ch * CN + n) * ns + sl) * A.ld_gx + col;
+                        gxv[e][0] = ld_f32(gp); gxv[e][1] = ld_f32(gp + HH); gxv[e][2] = ld_f32(gp + 2 * HH);
+                    }
+                }
+                float* G = G0 + (size_t)slot * 3 * CN * UN;
+                if (quad < 3) {
+                    mbar_wait(dfull(slot), (uint32_t)(u & 1));
+                    tc_fence_after();
+                    PROF_MARK(1);   // waiting for the accumulator: exchange + staging + MMA
+                    const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + TM_D + (uint32_t)(slot * NACC * CN + half * (CN / 2));
+                    uint32_t r[NACC][CN / 2];
+#pragma unroll
+                    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+                        for (int i = 0; i < CN / 16; ++i) tc_ld8(ta + (uint32_t)(a * CN) + 8 * i, r[a] + 8 * i);
+                    tc_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(dfree(slot));
+                    float* gp = G + ((size_t)quad * CN + half * (CN / 2)) * UN + lane;
+#pragma unroll
+                    for (int i = 0; i < CN / 2; ++i) {
+                        float v = __uint_as_float(r[0][i]);
+#pragma unroll
+                        for (int a = 1; a < NACC; ++a) v += __uint_as_float(r[a][i]);
+                        gp[i * UN] = v;
+                    }
+                }
+                gate_bar();
+                PROF_MARK(2);   // accumulator read + gate exchange through shared memory
+#pragma unroll
+                for (int e = 0; e < RPT; ++e) {
+                    const int n = gw + 8 * e;
+                    if (n < nrows) {
+                        const float s0 = G[(0 * CN + n) * UN + lane], s1 = G[(1 * CN + n) * UN + lane], s2 = G[(2 * CN + n) * UN + lane];
+                        const float r = sigm(gxv[e][0] + s0 + bRr);
+                        const float z = sigm(gxv[e][1] + s1 + bRu);
+                        const float qq = s2 + bRn;
+                        const float nv = tanh_fast(gxv[e][2] + r * qq);
+                        const int jl = ch * CN + n;
+                        const float hp = hst[jl * UN + lane];
+                        const float h = (1.f - z) * nv + z * hp;
+                        const __nv_bfloat16 hb16 = __float2bfloat16(h);
+                        const uint32_t hb = (uint32_t)__bfloat16_as_ushort(hb16);
+                        const uint32_t ob = __shfl_down_sync(0xffffffffu, hb, 1);
+                        if (!(lane & 1)) ll_store(Xw + (size_t)jl * (HH / 2) + (col >> 1), hb | (ob << 16), tagw);
+                        hst[jl * UN + lane] = h;
+                        const size_t row = (size_t)(row_base + (long long)jl * ns + sl);
+                        if (A.hs_h) A.hs_h[row * A.ld_hs + col] = hb16;
+                        if (A.hs_f) A.hs_f[row * A.ld_hs + col] = h;
+                        if (A.cache) {
+                            float* cp = A.cache + row * 4 * HH + col;
+                            cp[0] = r; cp[HH] = z; cp[2 * HH] = nv; cp[3 * HH] = qq;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) atomicAdd(const_cast<int*>(s_pub), 1);
+                PROF_MARK(3);   // gates + publish + bookkeeping
+                if (k + 2 < P.Tseg && ch == 0) {   // gx rows of the step after next -> L2
+                    const int tn = A.reverse ? t - 2 : t + 2;
+                    const int nan = NA(tn);
+                    const long long rbn = OFF(tn);
+                    for (int n = gw; n < nan; n += 8) {
+                        const float* gp = A.gx + (size_t)(rbn + (long long)n * ns + sl) * A.ld_gx + UN * c;
+                        if (lane < 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + lane * HH));
+                    }
+                }
+                PROF_MARK(4);
+            }
+        }
+    } else if (warp < 12) {
+        // =========================== STAGE warps ===========================
+        const int kp = warp - 8;                       // pair of k-blocks 2 kp, 2 kp + 1: units [128 kp, 128 kp + 128)
+        constexpr int U = CN < 16 ? CN : 16;           // rows polled together (one ld.v4 per row and lane)
+        const uint32_t idesc = make_idesc(CN);
+        int q = 0, na_prev = 0, q_prev_step = 0;
+        bool first = true;
+        for (int k = 0; k < P.Tseg; ++k) {
+            const int t = A.reverse ? P.t0 + P.Tseg - 1 - k : P.t0 + k;
+            const int na = NA(t);
+            if (na == 0) {
+                if (A.reverse) continue;
+                break;
+            }
+            const int npoll = first ? 0 : min(na, na_prev);
+            const unsigned tag = P.tag_base + (unsigned)(k - 1);
+            const unsigned long long* Xr = X + (size_t)((k - 1) & 1) * xpar;
+            const int q_this_step = q;
+            for (int ch = 0; ch * CN < na; ++ch, ++q) {
+                const int slot = q & 1, u = q >> 1;
+                const int nrows = min(CN, na - ch * CN);
+                const uint32_t Hs = Hs0 + (uint32_t)(slot * CN * 1024);
+                PROF_MARK_L(0);
+                if (u >= 1) mbar_wait(dfull(slot), (uint32_t)((u - 1) & 1));   // the MMAs that read this slot last are complete
+                if (ch * CN < npoll) {   // the predecessor chunk (previous step, same rows) has been published by this CTA
+                    const int want = 8 * (q_prev_step + ch + 1);
+                    const long long tw0 = clock64();
+                    bool waited = false;
+                    while (*s_pub < want) { waited = true; POLL_GUARD(tw0); }
+                    // the peers publish within a few hundred cycles of this CTA and their words need an L2 round trip to show:
+                    // a poll round issued right away comes back empty and the next one costs a full round (~700 cycles
+                    // chip-wide for 32 KB of LL words per SM); one round issued a little later finds everything
+                    if (waited && P.poll_delay > 0) {
+                        const long long td0 = clock64();
+                        while (clock64() - td0 < P.poll_delay) {}
+                    }
+                }
+                PROF_MARK_L(1);   // stage: waiting for the slot and for the local publish
+                // one ld.v4 per row: the warp reads the 512 contiguous bytes (64 LL words = 128 units) of this k-block pair,
+                // lane l the words of units 4l .. 4l+3 -> every load instruction is 4 full lines, nothing is fetched twice
+#pragma unroll 1
+                for (int r0 = 0; r0 < CN; r0 += U) {
+                    if (r0 >= nrows) break;
+                    uint4 x[U];
+                    bool miss[U];
+#pragma unroll
+                    for (int uu = 0; uu < U; ++uu) miss[uu] = !first && (r0 + uu) < nrows && ch * CN + r0 + uu < npoll;   // warp-uniform
+                    if (!first) {
+                        bool ok;
+                        const long long tp0 = clock64();
+                        do {
+                            ok = true;
+                            if (P.prof && lane == 0) pacc[4] += 1;    // poll rounds
+#pragma unroll
+                            for (int uu = 0; uu < U; ++uu)
+                                if (miss[uu]) x[uu] = ll_load2(Xr + ((size_t)(ch * CN + r0 + uu) * (HH / 2) + 64 * kp + 2 * lane));
+#pragma unroll
+                            for (int uu = 0; uu < U; ++uu)
+                                if (miss[uu]) {
+                                    const bool m = __any_sync(0xffffffffu, x[uu].y != tag || x[uu].w != tag);
+                                    if (m) ok = false;
+                                    else {   // the row is complete: operand store, then it is not polled again
+                                        miss[uu] = false;
+                                        const uint32_t a = Hs + hs_off<CN>(r0 + uu, 16 * kp + (lane >> 1)) + ((lane & 1) << 3);
+                                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(x[uu].x), "r"(x[uu].z) : "memory");
+                                    }
+                                }
+                            POLL_GUARD(tp0);
+                        } while (!ok);
+                    }
+                    // rows that are not polled: initial state (first step) or zeros (rows that join here, reverse direction)
+#pragma unroll
+                    for (int uu = 0; uu < U; ++uu) {
+                        const int r = r0 + uu;
+                        if (r >= nrows || (!first && ch * CN + r < npoll)) continue;
+                        uint32_t w0 = 0u, w1 = 0u;
+                        if (first && A.h0) {
+                            const float4 a0 = *reinterpret_cast<const float4*>(A.h0 + (size_t)((ch * CN + r) * ns + sl) * HH + 128 * kp + 4 * lane);
+                            w0 = pack2(a0.x, a0.y); w1 = pack2(a0.z, a0.w);
+                        }
+                        const uint32_t a = Hs + hs_off<CN>(r, 16 * kp + (lane >> 1)) + ((lane & 1) << 3);
+                        asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(w0), "r"(w1) : "memory");
+                    }
+                }
+                PROF_MARK_L(2);   // stage: poll + operand stores
+                fence_async_smem();
+                __syncwarp();
+                if (SPLIT) {
+                    if (u >= 1) {   // the gate warps have read the previous use of this slot's accumulators
+                        mbar_wait(dfree(slot), (uint32_t)((u - 1) & 1));
+                    }
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t td = tmem + TM_D + (uint32_t)((slot * NACC + kp) * CN);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint64_t db = make_desc_k(Hs + (uint32_t)((2 * kp + (j >> 2)) * (CN * 128) + (j & 3) * 32));
+                            tc_mma_ts(td, tmem + TM_A + 8 * (8 * kp + j), db, idesc, j > 0 ? 1u : 0u);
+                        }
+                        tc_commit(dfull(slot));
+                    }
+                    __syncwarp();
+                } else if (lane == 0) {
+                    mbar_arrive(kfull(slot, kp));
+                }
+                PROF_MARK_L(3);
+            }
+            q_prev_step = q_this_step;
+            na_prev = na;
+            first = false;
+        }
+        if (P.prof && warp == 8 && lane == 0)
+            for (int i = 0; i < 5; ++i) P.prof[(size_t)blockIdx.x * 16 + 8 + i] = pacc[i];
+    } else if (!SPLIT) {
+        // =========================== MMA warp ===========================
+        const uint32_t idesc = make_idesc(CN);
+        int q = 0;
+        for (int k = 0; k < P.Tseg; ++k) {
+            const int t = A.reverse ? P.t0 + P.Tseg - 1 - k : P.t0 + k;
+            const int na = NA(t);
+            if (na == 0) {
+                if (A.reverse) continue;
+                break;
+            }
+            for (int ch = 0; ch * CN < na; ++ch, ++q) {
+                const int slot = q & 1, u = q >> 1;
+                const uint32_t Hs = Hs0 + (uint32_t)(slot * CN * 1024);
+                const uint32_t td = tmem + TM_D + (uint32_t)(slot * CN);
+                PROF_MARK_L(0);
+                if (u >= 1) {   // the gate warps have read the previous use of this accumulator
+                    mbar_wait(dfree(slot), (uint32_t)((u - 1) & 1));
+                    tc_fence_after();
+                }
+                PROF_MARK_L(1);   // MMA warp: waiting for the accumulator to be free
+#pragma unroll
+                for (int p4 = 0; p4 < 4; ++p4) {
+                    mbar_wait(kfull(slot, p4), (uint32_t)(u & 1));
+                    tc_fence_after();
+                    if (p4 == 0) PROF_MARK_L(2);   // ... for the first pair of k-blocks
+                    if (elect_one()) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const uint64_t db = make_desc_k(Hs + (uint32_t)((2 * p4 + (j >> 2)) * (CN * 128) + (j & 3) * 32));
+                            tc_mma_ts(td, tmem + TM_A + 8 * (8 * p4 + j), db, idesc, (p4 > 0 || j > 0) ? 1u : 0u);
+                        }
+                        if (p4 == 3) tc_commit(dfull(slot));
+                    }
+                    __syncwarp();
+                }
+                PROF_MARK_L(3);   // ... for the other three pairs + issue
+            }
+        }
+        if (P.prof && lane == 0)
+            for (int i = 0; i < 4; ++i) P.prof[(size_t)blockIdx.x * 16 + 12 + i] = pacc[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (A.hT) {
+        for (int i = tid; i < nloc * UN; i += NTH2) {
+            const int jl = i >> 5, u = i & 31;
+            A.hT[(size_t)(jl * ns + sl) * HH + UN * c + u] = hst[i];
+        }
+    }
+    if (P.prof && tid == 0)
+        for (int i = 0; i < 8; ++i) P.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
 
 // =========================================================================================
 // backward (BPTT).  Dual decomposition as in gru_mma.cu: dh_prev^T[512 x n] = R_own^T[512 x 96] . dgh_own^T[96 x n] from
@@ -843,6 +1238,10 @@ __global__ void __launch_bounds__(128, 1) k_test_ts_mma(const bf16* __restrict__
 }
 
 template <int CN>
+size_t fwd2_smem(int bslr, int Tseg) {
+    return 1024 + (size_t)2 * CN * 1024 + (size_t)2 * 3 * CN * UN * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 16 + 14 * 8 + 16;
+}
+template <int CN>
 size_t bwd_smem(int bslr, int Tseg) {
     return 1024 + (size_t)2 * CN * 128 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 16 + 16 + 16;
 }
@@ -863,6 +1262,8 @@ struct GruTcCtx {
     size_t ycap[NSLOT] = {0, 0, 0, 0};
     int pad_groups = 8;
     int force_cn = 0;            // ARGSIM_GRU_TC_CN: rows per MMA chunk (16 / 32 / 64 / 128), 0 = by live rows
+    int fwd_version = 2;         // ARGSIM_GRU_TC_FWD=1: the first (block-synchronous) forward kernel, for A/B runs
+    int poll_delay = 300;        // ARGSIM_GRU_TC_DELAY: cycles between the local publish and a stage warp's first poll round
     long long* prof = nullptr;   // ARGSIM_GRU_PROF=1
 };
 
@@ -877,12 +1278,20 @@ GruTcCtx* gru_tc_create(int device) {
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    if (const char* v = getenv("ARGSIM_GRU_TC_FWD")) c->fwd_version = atoi(v);
+    if (const char* v = getenv("ARGSIM_GRU_TC_DELAY")) c->poll_delay = atoi(v);
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_bwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     if (const char* v = getenv("ARGSIM_GRU_PAD")) c->pad_groups = atoi(v);
     if (const char* v = getenv("ARGSIM_GRU_TC_CN")) c->force_cn = atoi(v);
-    if (getenv("ARGSIM_GRU_PROF")) CUDA_CHECK(cudaMalloc(&c->prof, 160 * 8 * sizeof(long long)));
+    if (getenv("ARGSIM_GRU_PROF")) {
+        CUDA_CHECK(cudaMalloc(&c->prof, 160 * 16 * sizeof(long long)));
+        CUDA_CHECK(cudaMemset(c->prof, 0, 160 * 16 * sizeof(long long)));
+    }
     return c;
 }
 void gru_tc_destroy(GruTcCtx* c) {
@@ -922,6 +1331,11 @@ void gru_tc_fwd(GruTcCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& Pl
     int ns, bslr, cn;
     const int b_seg = (ndir == 1) ? Pl.nact[t0] : Pl.b;
     tc_pick(c, ndir, b_seg, rows_per_slice, &ns, &bslr, &cn);
+    if (c->fwd_version == 2 && cn > 64) {   // two operand slots of CN KB each
+        cn = 64;
+        const int per = (b_seg + ns - 1) / ns;
+        bslr = (per + 63) / 64 * 64;
+    }
     if (bslr > MAX_BSL) throw std::runtime_error("gru_tc: batch too large for the persistent kernel");
     for (int d = 0; d < ndir; ++d) {
         const GruFwdArgs& a = dirs[d];
@@ -945,28 +1359,40 @@ void gru_tc_fwd(GruTcCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& Pl
     P.tag_base = (c->launch_id++) << 12;
     if (c->launch_id >= (1u << 20)) c->launch_id = 1;
     P.prof = c->prof;
+    P.poll_delay = c->poll_delay;
     void* args[] = {&P};
     const int grid_groups = pad ? std::max(groups, c->pad_groups) : groups;
     void* fn; size_t smem;
-    switch (cn) {
-        case 16: fn = (void*)k_gru_tc_fwd<16>; smem = fwd_smem<16>(bslr, Tseg); break;
-        case 32: fn = (void*)k_gru_tc_fwd<32>; smem = fwd_smem<32>(bslr, Tseg); break;
-        case 64: fn = (void*)k_gru_tc_fwd<64>; smem = fwd_smem<64>(bslr, Tseg); break;
-        default: fn = (void*)k_gru_tc_fwd<128>; smem = fwd_smem<128>(bslr, Tseg); break;
+    int nth = NTH;
+    if (c->fwd_version == 2) {
+        nth = NTH2;
+        switch (cn) {
+            case 16: fn = (void*)k_gru_tc_fwd2<16>; smem = fwd2_smem<16>(bslr, Tseg); break;
+            case 32: fn = (void*)k_gru_tc_fwd2<32>; smem = fwd2_smem<32>(bslr, Tseg); break;
+            default: fn = (void*)k_gru_tc_fwd2<64>; smem = fwd2_smem<64>(bslr, Tseg); break;
+        }
+    } else {
+        switch (cn) {
+            case 16: fn = (void*)k_gru_tc_fwd<16>; smem = fwd_smem<16>(bslr, Tseg); break;
+            case 32: fn = (void*)k_gru_tc_fwd<32>; smem = fwd_smem<32>(bslr, Tseg); break;
+            case 64: fn = (void*)k_gru_tc_fwd<64>; smem = fwd_smem<64>(bslr, Tseg); break;
+            default: fn = (void*)k_gru_tc_fwd<128>; smem = fwd_smem<128>(bslr, Tseg); break;
+        }
     }
     if (smem > 232448) throw std::runtime_error("gru_tc: shared memory request exceeds 227 KB (segment too long for this slice size)");
-    if (pad == 2) CUDA_CHECK(cudaLaunchKernel(fn, dim3(grid_groups * CL), dim3(NTH), args, smem, s));
-    else CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid_groups * CL), dim3(NTH), args, smem, s));
+    if (pad == 2) CUDA_CHECK(cudaLaunchKernel(fn, dim3(grid_groups * CL), dim3(nth), args, smem, s));
+    else CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid_groups * CL), dim3(nth), args, smem, s));
     COUNT_LAUNCH();
     if (c->prof) {
         CUDA_CHECK(cudaStreamSynchronize(s));
-        std::vector<long long> h((size_t)groups * CL * 8);
+        const int W = c->fwd_version == 2 ? 16 : 8;
+        std::vector<long long> h((size_t)groups * CL * W);
         CUDA_CHECK(cudaMemcpy(h.data(), c->prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-        double avg[8] = {0};
+        double avg[16] = {0};
         for (int b2 = 0; b2 < groups * CL; ++b2)
-            for (int i = 0; i < 8; ++i) avg[i] += (double)h[b2 * 8 + i] / (groups * CL);
-        fprintf(stderr, "[gru_tc_prof] fwd ndir=%d ns=%d cn=%d steps=%d cycles/step:", ndir, ns, cn, Tseg);
-        for (int i = 0; i < 8; ++i) fprintf(stderr, " p%d=%.0f", i, avg[i] / Tseg);
+            for (int i = 0; i < W; ++i) avg[i] += (double)h[b2 * W + i] / (groups * CL);
+        fprintf(stderr, "[gru_tc_prof] fwd v%d ndir=%d ns=%d cn=%d steps=%d cycles/step:", c->fwd_version, ndir, ns, cn, Tseg);
+        for (int i = 0; i < W; ++i) fprintf(stderr, " p%d=%.0f", i, avg[i] / Tseg);
         fprintf(stderr, "\n");
     }
 }

@@ -332,7 +332,8 @@ void Engine::rec_fwd(const GruFwdArgs* dirs, int ndir, const SeqPlan& P, const i
 void Engine::gru_fwd(GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact) {
     if (arena.dry) return;
     kbegin(ndir == 2 ? "k:gru_fwd_enc" : "k:gru_fwd_dec");
-    if (use_mma && (gru_tc_mode & 1) && tc && gru_tc_fits(tc, ndir, P.b)) rec_fwd(dirs, ndir, P, d_off, d_nact, st[0], 0, -1, 0, 0, /*pad: runs alone*/ 1);
+    const bool want_tc = use_mma && tc && ((gru_tc_mode & 1) || ((gru_tc_mode & 4) && gru_tc_throughput(tc, ndir, P.b) && !dirs[0].h0));
+    if (want_tc && gru_tc_fits(tc, ndir, P.b)) gru_tc_fwd(tc, dirs, ndir, P, d_off, d_nact, H, st[0], 0, -1, 0, 0, /*pad: runs alone*/ 1);
     else if (use_mma && gru_mma_fits(mma, ndir, P.b)) gru_mma_fwd(mma, dirs, ndir, P, d_off, d_nact, H, st[0], 0, -1, 0, 0, /*pad: runs alone*/ 1);
     else gru_generic_fwd(dirs, ndir, P, H, gru_work, st);
     kend();
@@ -1359,7 +1360,10 @@ void Engine::embed_one(const int32_t* src, int b, int T, float* mu_out) {
 // (4 slices x 128 rows) is processed as length-sorted micro-batches: each one's step count is its own longest
 // row, not the batch maximum (eval_embed*.py feed 128 rows per call; BASELINE configs[3] feeds 4096).
 void Engine::embed(const int32_t* src, int b, int T, float* mu_out) {
-    const int cap = 512;
+    // micro-batch: 512 rows fill the mma.sync kernel's 4 slices x 128 rows per direction; the tensor-memory kernel holds 256
+    // rows per slice (4 chunks of 64 in flight through its two operand slots)
+    static const int cap_env = getenv("ARGSIM_EMBED_CAP") ? atoi(getenv("ARGSIM_EMBED_CAP")) : 0;
+    const int cap = cap_env > 0 ? cap_env : (tc && (gru_tc_mode & 5)) ? 1024 : 512;
     if (!use_mma || b <= cap) {
         embed_one(src, b, T, mu_out);
         return;

@@ -103,8 +103,9 @@ private:
                                                         // run on the SMs the recurrence launches of the layer below leave free
     int group_cap = 0;                                  // ARGSIM_GROUP_CAP: groups of 16 CTAs the slice planners may use (0 = 9, or 8 under data parallel)
     int side_units = 32;                                // ARGSIM_SIDE_UNITS: k-blocks per work unit of the side stream's GEMMs (0 = persistent CTAs; 32: 10.50 -> 10.41 ms/step)
-    int enc_bwd_chunk = 0;                              // ARGSIM_ENC_BWD_CHUNK=8: 8-row chunks in the encoder's BPTT segment launches only (one measurement at the end
-                                                        // of round 1: encoder BPTT 3.56 -> 3.36 ms; the decoder wavefront is slower with them: 1.33 -> 1.42 / 1.86 -> 1.92 ms)
+    int enc_bwd_chunk = 8;                              // 8-row chunks in the encoder's BPTT segment launches (ARGSIM_ENC_BWD_CHUNK=16: 16-row chunks there too).
+                                                        // Encoder BPTT 3.53 -> 3.36 ms, step 10.34 -> 10.15 ms; the decoder wavefront is slower with them (1.33 -> 1.42 /
+                                                        // 1.86 -> 1.92 ms) and keeps 16-row chunks
     int dec_early_on = 1;                               // ARGSIM_DEC_EARLY=0: decoder layer-0 gather + projection on the main stream after the encoder (10.66 vs 10.64 ms/step)
     bool slice_budget = true;                           // ARGSIM_NO_SLICE_BUDGET: every wavefront launch takes 16-row slices
     bool early_adam = true;                             // ARGSIM_NO_EARLY_ADAM: one Adam launch after the last gradient
@@ -125,7 +126,9 @@ private:
     Arena arena;
     GruMmaCtx* mma = nullptr;
     GruTcCtx* tc = nullptr;      // tensor-memory recurrence (gru_tc.cu)
-    int gru_tc_mode = 0;         // ARGSIM_GRU_TC: bit 0 = forward, bit 1 = backward recurrences on the tcgen05 kernels
+    int gru_tc_mode = 4;         // ARGSIM_GRU_TC: bit 0 = all forward, bit 1 = all backward recurrences on the tcgen05 kernels; bit 2 (default) =
+                                 // whole-layer forward launches with many rows per slice (embedding batches, large training batches) take the
+                                 // TMA-fed tcgen05 kernel, everything else the register-stationary mma.sync kernels
     void rec_bwd(const GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact, cudaStream_t q, int t0,
                  int Tseg, int slot, int want8, int pad, int chunk);
     // one forward recurrence launch on whichever persistent kernel is selected (want8: the mma.sync kernel's slice request)

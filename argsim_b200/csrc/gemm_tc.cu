@@ -68,6 +68,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// one lane of a CONVERGED warp.  Guarding tcgen05 / TMA issue with `lane == 0` makes ptxas wrap every such instruction in
+// an ELECT / BRA.U.ANY loop (operands not provably warp-uniform, ~59 cycles per instruction measured in gru_tc.cu);
+// a predicate that comes from elect.sync lets it issue them back to back from uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -390,8 +398,9 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
     if (warp == 0) {
-        // ---------------------------------------------------------------- TMA producer
-        if (lane == 0) {
+        // ---------------------------------------------------------------- TMA producer (whole warp walks the loop, one lane issues)
+        {
+            const bool leader = elect_one();
             uint32_t it = 0;
             for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
                 int m0, n0, kb0, nkb, split;
@@ -400,27 +409,31 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_expect_tx(full_bar(s), STAGE_BYTES);
-                    const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
-                    const int k = (kb0 + i) * BK;
-                    if (!A_MN) {
-                        tma_load_2d(sa, &tmA, k, m0, full_bar(s));
-                    } else {
+                    if (leader) {
+                        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+                        const int k = (kb0 + i) * BK;
+                        if (!A_MN) {
+                            tma_load_2d(sa, &tmA, k, m0, full_bar(s));
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, m0 + 64 * j, k, full_bar(s));
-                    }
-                    if (!B_MN) {
-                        tma_load_2d(sb, &tmB, k, n0, full_bar(s));
-                    } else {
+                            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmA, m0 + 64 * j, k, full_bar(s));
+                        }
+                        if (!B_MN) {
+                            tma_load_2d(sb, &tmB, k, n0, full_bar(s));
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, n0 + 64 * j, k, full_bar(s));
+                            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * (BK * 128), &tmB, n0 + 64 * j, k, full_bar(s));
+                        }
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        // ---------------------------------------------------------------- MMA issuer (whole warp waits, one lane issues)
+        {
+            const bool leader = elect_one();
             const uint32_t idesc = make_idesc2<A_MN, B_MN>();
             uint32_t it = 0, tl = 0;
             for (int u = blockIdx.x; u < nunits; u += gridDim.x, ++tl) {
@@ -435,21 +448,26 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     const uint32_t ph = (it / STAGES) & 1u;
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
-                    const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
+                    if (leader) {
+                        const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
-                    for (int k16 = 0; k16 < BK / 16; ++k16) {
-                        const uint64_t da = make_desc2<A_MN>(sa + (A_MN ? k16 * 2048 : k16 * 32));
-                        const uint64_t db = make_desc2<B_MN>(sb + (B_MN ? k16 * 2048 : k16 * 32));
-                        tc_mma(tacc, da, db, idesc, (i > 0 || k16 > 0) ? 1u : 0u);
+                        for (int k16 = 0; k16 < BK / 16; ++k16) {
+                            const uint64_t da = make_desc2<A_MN>(sa + (A_MN ? k16 * 2048 : k16 * 32));
+                            const uint64_t db = make_desc2<B_MN>(sb + (B_MN ? k16 * 2048 : k16 * 32));
+                            tc_mma(tacc, da, db, idesc, (i > 0 || k16 > 0) ? 1u : 0u);
+                        }
+                        tc_commit(empty_bar(s));
                     }
-                    tc_commit(empty_bar(s));
+                    __syncwarp();
                 }
-                tc_commit(tfull_bar(acc));
+                if (leader) tc_commit(tfull_bar(acc));
+                __syncwarp();
             }
         }
     } else {
         // ---------------------------------------------------------------- epilogue (4 warps)
         const int lg = warp & 3;
+        const bool leader = elect_one();   // the lane that owns this warp's TMA-store bulk groups
         const int et = threadIdx.x - 64;
         const uint32_t slab0 = epi_base + (uint32_t)(warp - 2) * 2 * SLAB_BYTES;
         const uint32_t row_off = (uint32_t)lane * 128u;
@@ -500,7 +518,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 if (out_bf16) {
                     // one slab: 32 rows x 64 columns of bf16 (128 B per row), 128B-swizzled like the TMA box expects
                     const uint32_t slab = slab0 + slab_sel * SLAB_BYTES;
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     __syncwarp();
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
@@ -511,7 +529,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                                      pack_bf16(__uint_as_float(r[8 * q + 6]), __uint_as_float(r[8 * q + 7])));
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) tma_store_2d(&tmC, slab, col0, row0, reduce);
+                    if (leader) tma_store_2d(&tmC, slab, col0, row0, reduce);
                     slab_sel ^= 1u;
                 } else {
                     // two slabs of 32 rows x 32 fp32 columns
@@ -519,7 +537,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     for (int hf = 0; hf < 2; ++hf) {
                         if (col0 + 32 * hf < N) {
                             const uint32_t slab = slab0 + slab_sel * SLAB_BYTES;
-                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                            if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                             __syncwarp();
 #pragma unroll
                             for (int q = 0; q < 8; ++q)
@@ -527,7 +545,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                                              r[32 * hf + 4 * q + 2], r[32 * hf + 4 * q + 3]);
                             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                             __syncwarp();
-                            if (lane == 0) tma_store_2d(&tmC, slab, col0 + 32 * hf, row0, reduce);
+                            if (leader) tma_store_2d(&tmC, slab, col0 + 32 * hf, row0, reduce);
                             slab_sel ^= 1u;
                         }
                     }
@@ -536,9 +554,9 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             // accumulator fully read into registers: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (leader) mbar_arrive(tempty_bar(acc));
         }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -602,6 +620,21 @@ void launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc
     COUNT_LAUNCH();
 }
 }  // namespace
+
+// Tensor map over the rows of an activation matrix (rows, ld) bf16 whose rows are dealt round robin over `ns` slices:
+// 3D view {x = column, y = row % ns, z = row / ns}, box {64 columns, 1, box_rows} with the 128-byte swizzle -- the rows
+// r0, r0 + ns, r0 + 2 ns, ... of one slice arrive as one K-major UMMA operand tile (gru_tc.cu, forward kernel 3)
+void tma_encode_slice_rows_bf16(void* map_out, const bf16* base, int ld, long long rows, int ns, int box_rows) {
+    if (!g_ready) throw std::runtime_error("TMA descriptors unavailable (gemm_tc_init)");
+    if (((uintptr_t)base & 15) || (ld % 8)) throw std::runtime_error("tma_encode_slice_rows: base must be 16-byte aligned with ld % 8 == 0");
+    cuuint64_t dims[3] = {(cuuint64_t)ld, (cuuint64_t)ns, (cuuint64_t)((rows + ns - 1) / ns)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * sizeof(bf16), (cuuint64_t)ld * sizeof(bf16) * (cuuint64_t)ns};
+    cuuint32_t box[3] = {64u, 1u, (cuuint32_t)box_rows}, estr[3] = {1, 1, 1};
+    CUresult rc = g_encode((CUtensorMap*)map_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled (slice rows) failed with code " + std::to_string((int)rc));
+}
 
 void gemm_tc_init(int device) {
     static std::mutex mu;

@@ -17,6 +17,7 @@
 // bytes (4 words = 8 units) that make up one 16-byte chunk of the swizzled operand tile.
 #include "kernels.h"
 #include "plan.h"
+#include <cuda.h>
 #include <vector>
 
 namespace {
@@ -790,6 +791,272 @@ __global__ void __launch_bounds__(NTH2, 1) k_gru_tc_fwd2(const __grid_constant__
 }
 
 // =========================================================================================
+// forward, throughput form (many rows per slice): the exchange is NOT a polled LL buffer.  The new h a gate warp writes
+// to the layer's output matrix hs (bf16) IS the published value; a CTA raises a flag (release) per (chunk, step) once
+// its 32 columns of the chunk's rows are written, the producer warp of every CTA waits for the 16 flags of the
+// predecessor chunk (acquire) and then lets the TMA engine copy the chunk's rows of h_{t-1} -- all 512 columns, straight
+// from hs through a 3-D tensor map {column, row % ns, row / ns} -- into the swizzled operand tile: 1 KB per row instead
+// of 2 KB of tagged words, no load/store instructions, no registers.  Roles: warps 0..7 gate, warp 8 producer (flags +
+// TMA), warp 9 MMA; two operand slots and two accumulators of CN = 64 rows, so the copy of chunk i+1, the 32 MMAs
+// (N = 64, tensor-bound) of chunk i and the gate math of chunk i-1 overlap.  Latency per chunk is worse than the LL
+// exchange (a release fence and two L2 round trips); with >= 2 chunks per step in flight that is hidden.
+// Used when no initial / final state is handed over (h0 == hT == null: whole-layer launches).
+// =========================================================================================
+constexpr int NTH3 = 320;
+struct TcFwd3X {
+    unsigned* flags;     // [group][CL][MAXCH3]
+    int xcol[2];         // column of the direction's first unit in the hs matrix the tensor map covers
+};
+constexpr int MAXCH3 = 4;
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+template <int CN>
+__global__ void __launch_bounds__(NTH3, 1) k_gru_tc_fwd3(const __grid_constant__ TcFwdP P, const __grid_constant__ CUtensorMap tmH,
+                                                         const __grid_constant__ TcFwd3X XP) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    if ((int)(blockIdx.x / CL) >= P.ndir * P.nslices) return;
+    const uint32_t sbase = (smem_u32(sm_raw) + 1023u) & ~1023u;
+    unsigned char* const sm = sm_raw + (sbase - smem_u32(sm_raw));
+    // [Hs: 2 x CN KB][G: 2 x 3*CN*32 f32][hst: bslr*32 f32][tables][barriers: full[2], dfull[2], dfree[2]][slot]
+    const uint32_t Hs0 = sbase;
+    float* G0 = reinterpret_cast<float*>(sm + 2 * CN * 1024);
+    float* hst = G0 + 2 * 3 * CN * UN;
+    int* s_nact = reinterpret_cast<int*>(hst + (size_t)P.bslr * UN);
+    int* s_off = s_nact + P.Tseg + 2;
+    unsigned long long* barp = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(s_off + P.Tseg + 2) + 15) & ~uintptr_t(15));
+    const uint32_t bars = smem_u32(barp);
+    auto full = [&](int slot) { return bars + 8u * (uint32_t)slot; };
+    auto dfull = [&](int slot) { return bars + 8u * (uint32_t)(2 + slot); };
+    auto dfree = [&](int slot) { return bars + 8u * (uint32_t)(4 + slot); };
+    const uint32_t tslot = bars + 8u * 6;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = blockIdx.x / CL, c = blockIdx.x % CL;
+    const int ns = P.nslices, d = grp / ns, sl = grp % ns;
+    const TcDirP& A = P.dir[d];
+    for (int i = tid; i < P.Tseg + 2; i += NTH3) {
+        const int tt = P.t0 - 1 + i;
+        s_nact[i] = (tt >= 0 && tt < P.Ttot) ? slice_rows(P.nact[tt], sl, ns) : 0;
+        s_off[i] = (tt >= 0 && tt <= P.Ttot) ? P.off[tt] : 0;
+    }
+    if (tid == 0) {
+        mbar_init(full(0), 1); mbar_init(full(1), 1);
+        mbar_init(dfull(0), 1); mbar_init(dfull(1), 1);
+        mbar_init(dfree(0), 6); mbar_init(dfree(1), 6);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmH) : "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot) : "memory");
+    if (warp < 4) {   // R_own -> tensor memory (see k_gru_tc_fwd)
+        const int gate = warp;
+        const uint4* src = gate < 3 ? reinterpret_cast<const uint4*>(A.R + (size_t)(gate * HH + UN * c + lane) * HH) : nullptr;
+        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + TM_A;
+#pragma unroll 1
+        for (int j = 0; j < 32; ++j) {
+            uint32_t r[8];
+            if (src) {
+                const uint4 v0 = src[2 * j], v1 = src[2 * j + 1];
+                r[0] = v0.x; r[1] = v0.y; r[2] = v0.z; r[3] = v0.w; r[4] = v1.x; r[5] = v1.y; r[6] = v1.z; r[7] = v1.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = 0u;
+            }
+            tc_st8(tbase + 8 * j, r);
+        }
+        tc_wait_st();
+    }
+    const int nloc = slice_rows(P.b, sl, ns);
+    for (int i = tid; i < nloc * UN; i += NTH3) hst[i] = 0.f;
+    unsigned* const flags = XP.flags + (size_t)grp * CL * MAXCH3;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp < 8) {
+        // =========================== GATE warps ===========================
+        const int gw = warp, quad = warp & 3, half = warp >> 2;
+        const int col = UN * c + lane;
+        const float bRr = A.bR[col], bRu = A.bR[HH + col], bRn = A.bR[2 * HH + col];
+        constexpr int RPT = CN / 8;
+        int q = 0, na_prev = 0, a = 0;
+        for (int k = 0; k < P.Tseg; ++k) {
+            const int t = A.reverse ? P.t0 + P.Tseg - 1 - k : P.t0 + k;
+            const int na = NA(t);
+            if (na == 0) {
+                if (A.reverse) continue;
+                break;
+            }
+            const long long row_base = OFF(t);
+            const int npoll = a == 0 ? 0 : min(na, na_prev);
+            for (int ch = 0; ch * CN < na; ++ch, ++q) {
+                const int slot = q & 1, u = q >> 1;
+                const int nrows = min(CN, na - ch * CN);
+                float gxv[RPT][3];
+#pragma unroll
+                for (int e = 0; e < RPT; ++e) {
+                    const int n = gw + 8 * e;
+                    gxv[e][0] = gxv[e][1] = gxv[e][2] = 0.f;
+                    if (n < nrows) {
+                        const float* gp = A.gx + (size_t)(row_base + (long long)(ch * CN + n) * ns + sl) * A.ld_gx + col;
+                        gxv[e][0] = ld_f32(gp); gxv[e][1] = ld_f32(gp + HH); gxv[e][2] = ld_f32(gp + 2 * HH);
+                    }
+                }
+                float* G = G0 + (size_t)slot * 3 * CN * UN;
+                if (quad < 3) {
+                    mbar_wait(dfull(slot), (uint32_t)(u & 1));
+                    tc_fence_after();
+                    const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + TM_D + (uint32_t)(slot * CN + half * (CN / 2));
+                    uint32_t r[CN / 2];
+#pragma unroll
+                    for (int i = 0; i < CN / 16; ++i) tc_ld8(ta + 8 * i, r + 8 * i);
+                    tc_wait_ld();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(dfree(slot));
+                    float* gp = G + ((size_t)quad * CN + half * (CN / 2)) * UN + lane;
+#pragma unroll
+                    for (int i = 0; i < CN / 2; ++i) gp[i * UN] = __uint_as_float(r[i]);
+                }
+                gate_bar();
+#pragma unroll
+                for (int e = 0; e < RPT; ++e) {
+                    const int n = gw + 8 * e;
+                    if (n < nrows) {
+                        const int jl = ch * CN + n;
+                        // rows without a predecessor (first step; rows that join here) start from h = 0: R h = 0, whatever the
+                        // copy engine brought into their operand rows
+                        const bool live = jl < npoll;
+                        const float s0 = live ? G[(0 * CN + n) * UN + lane] : 0.f, s1 = live ? G[(1 * CN + n) * UN + lane] : 0.f,
+                                    s2 = live ? G[(2 * CN + n) * UN + lane] : 0.f;
+                        const float r = sigm(gxv[e][0] + s0 + bRr);
+                        const float z = sigm(gxv[e][1] + s1 + bRu);
+                        const float qq = s2 + bRn;
+                        const float nv = tanh_fast(gxv[e][2] + r * qq);
+                        const float hp = hst[jl * UN + lane];
+                        const float h = (1.f - z) * nv + z * hp;
+                        hst[jl * UN + lane] = h;
+                        const size_t row = (size_t)(row_base + (long long)jl * ns + sl);
+                        A.hs_h[row * A.ld_hs + col] = __float2bfloat16(h);     // the publish
+                        if (A.hs_f) A.hs_f[row * A.ld_hs + col] = h;
+                        if (A.cache) {
+                            float* cp = A.cache + row * 4 * HH + col;
+                            cp[0] = r; cp[HH] = z; cp[2 * HH] = nv; cp[3 * HH] = qq;
+                        }
+                    }
+                }
+                gate_bar();   // all 8 gate warps have written their rows of the chunk (and are done with G[slot])
+                if (tid == 0) {
+                    const unsigned val = P.tag_base + (unsigned)a + 1u;
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + c * MAXCH3 + ch), "r"(val) : "memory");
+                }
+                if (k + 2 < P.Tseg && ch == 0) {   // gx rows of the step after next -> L2
+                    const int tn = A.reverse ? t - 2 : t + 2;
+                    const int nan = NA(tn);
+                    const long long rbn = OFF(tn);
+                    for (int n = gw; n < nan; n += 8) {
+                        const float* gp = A.gx + (size_t)(rbn + (long long)n * ns + sl) * A.ld_gx + UN * c;
+                        if (lane < 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + lane * HH));
+                    }
+                }
+            }
+            na_prev = na;
+            ++a;
+        }
+    } else if (warp == 8) {
+        // =========================== PRODUCER warp: flags + TMA ===========================
+        const bool leader = elect_one();
+        int q = 0, na_prev = 0, a = 0;
+        for (int k = 0; k < P.Tseg; ++k) {
+            const int t = A.reverse ? P.t0 + P.Tseg - 1 - k : P.t0 + k;
+            const int na = NA(t);
+            if (na == 0) {
+                if (A.reverse) continue;
+                break;
+            }
+            const int npoll = a == 0 ? 0 : min(na, na_prev);
+            const int tp = A.reverse ? t + 1 : t - 1;                      // the step whose output rows are h_prev
+            const long long prev_base = (tp >= 0 && tp < P.Ttot) ? OFF(tp) : 0;
+            for (int ch = 0; ch * CN < na; ++ch, ++q) {
+                const int slot = q & 1, u = q >> 1;
+                if (u >= 1) mbar_wait(dfull(slot), (uint32_t)((u - 1) & 1));   // the MMAs that read this slot last are complete
+                if (ch * CN < npoll) {
+                    const unsigned want = P.tag_base + (unsigned)a;            // written after active step a - 1
+                    if (lane < CL) {
+                        const unsigned* fp = flags + lane * MAXCH3 + ch;
+                        const long long tp0 = clock64();
+                        unsigned f;
+                        do {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(fp) : "memory");
+                            POLL_GUARD(tp0);
+                        } while ((int)(f - want) < 0 || (f >> 12) != (P.tag_base >> 12));
+                    }
+                    __syncwarp();
+                }
+                if (leader) {
+                    asm volatile("fence.proxy.async.global;" ::: "memory");
+                    mbar_expect_tx(full(slot), (uint32_t)(CN * 1024));
+                    const long long row0 = prev_base + (long long)(ch * CN) * ns + sl;
+                    const int y0 = (int)(row0 % ns), z0 = (int)(row0 / ns);
+                    const uint32_t Hs = Hs0 + (uint32_t)(slot * CN * 1024);
+#pragma unroll
+                    for (int kb = 0; kb < 8; ++kb) tma_load_3d(Hs + (uint32_t)(kb * CN * 128), &tmH, XP.xcol[d] + 64 * kb, y0, z0, full(slot));
+                }
+                __syncwarp();
+            }
+            na_prev = na;
+            ++a;
+        }
+    } else {
+        // =========================== MMA warp ===========================
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc(CN);
+        int q = 0;
+        for (int k = 0; k < P.Tseg; ++k) {
+            const int t = A.reverse ? P.t0 + P.Tseg - 1 - k : P.t0 + k;
+            const int na = NA(t);
+            if (na == 0) {
+                if (A.reverse) continue;
+                break;
+            }
+            for (int ch = 0; ch * CN < na; ++ch, ++q) {
+                const int slot = q & 1, u = q >> 1;
+                const uint32_t Hs = Hs0 + (uint32_t)(slot * CN * 1024);
+                const uint32_t td = tmem + TM_D + (uint32_t)(slot * CN);
+                if (u >= 1) mbar_wait(dfree(slot), (uint32_t)((u - 1) & 1));
+                mbar_wait(full(slot), (uint32_t)(u & 1));
+                tc_fence_after();
+                if (leader) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const uint64_t db = make_desc_k(Hs + (uint32_t)((j >> 2) * (CN * 128) + (j & 3) * 32));
+                        tc_mma_ts(td, tmem + TM_A + 8 * j, db, idesc, j > 0 ? 1u : 0u);
+                    }
+                    tc_commit(dfull(slot));
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+}
+
+// =========================================================================================
 // backward (BPTT).  Dual decomposition as in gru_mma.cu: dh_prev^T[512 x n] = R_own^T[512 x 96] . dgh_own^T[96 x n] from
 // the CTA's OWN 96 dgh columns, the 512 partial sums reduce-scattered to their owner CTAs through LL words.  Here
 // A = R_own^T sits in tensor memory as 4 M-tiles of 128 output units x 96 k (48 columns each), B = dgh_own (CN rows x
@@ -1260,6 +1527,8 @@ struct GruTcCtx {
     size_t xcap[NSLOT] = {0, 0, 0, 0};
     unsigned long long* ybuf[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
     size_t ycap[NSLOT] = {0, 0, 0, 0};
+    unsigned* flags[NSLOT] = {nullptr, nullptr, nullptr, nullptr};   // forward kernel 3: [group][CL][MAXCH3] step flags
+    int fwd3_min_rows = 48;      // ARGSIM_GRU_TC_FWD3_ROWS: rows per slice from which whole-layer launches take the TMA-fed kernel
     int pad_groups = 8;
     int force_cn = 0;            // ARGSIM_GRU_TC_CN: rows per MMA chunk (16 / 32 / 64 / 128), 0 = by live rows
     int fwd_version = 2;         // ARGSIM_GRU_TC_FWD=1: the first (block-synchronous) forward kernel, for A/B runs
@@ -1282,6 +1551,8 @@ GruTcCtx* gru_tc_create(int device) {
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     if (const char* v = getenv("ARGSIM_GRU_TC_FWD")) c->fwd_version = atoi(v);
+    if (const char* v = getenv("ARGSIM_GRU_TC_FWD3_ROWS")) c->fwd3_min_rows = atoi(v);
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     if (const char* v = getenv("ARGSIM_GRU_TC_DELAY")) c->poll_delay = atoi(v);
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -1296,7 +1567,7 @@ GruTcCtx* gru_tc_create(int device) {
 }
 void gru_tc_destroy(GruTcCtx* c) {
     if (!c) return;
-    for (int i = 0; i < GruTcCtx::NSLOT; ++i) { cudaFree(c->xbuf[i]); cudaFree(c->ybuf[i]); }
+    for (int i = 0; i < GruTcCtx::NSLOT; ++i) { cudaFree(c->xbuf[i]); cudaFree(c->ybuf[i]); cudaFree(c->flags[i]); }
     cudaFree(c->prof);
     delete c;
 }
@@ -1314,6 +1585,13 @@ static void tc_pick(const GruTcCtx* c, int ndir, int b, int rows_per_slice, int*
     *ns = s;
     *cn = n;
     *bslr = (per + n - 1) / n * n;
+}
+// true when a whole-layer launch of `b` rows would take the TMA-fed throughput kernel (rows per slice >= fwd3_min_rows)
+bool gru_tc_throughput(const GruTcCtx* c, int ndir, int b) {
+    int ns, bslr, cn;
+    tc_pick(c, ndir, b, 0, &ns, &bslr, &cn);
+    const int per = (b + ns - 1) / ns;
+    return c->fwd_version >= 2 && per >= c->fwd3_min_rows && (per + 63) / 64 * 64 <= MAX_BSL;
 }
 bool gru_tc_fits(const GruTcCtx* c, int ndir, int b) {
     int ns, bslr, cn;
@@ -1345,6 +1623,42 @@ void gru_tc_fwd(GruTcCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& Pl
     }
     if (ndir == 1) P.dir[1] = P.dir[0];
     const int groups = ndir * ns;
+    {   // throughput form: whole-layer launches with many rows per slice read h_{t-1} from the layer's output through TMA
+        bool ok3 = c->fwd_version >= 2 && rows_per_slice == 0 && (b_seg + ns - 1) / ns >= c->fwd3_min_rows && t0 == 0 && Tseg == Pl.Tmax;
+        for (int d = 0; d < ndir; ++d) ok3 = ok3 && dirs[d].hs_h && !dirs[d].h0 && !dirs[d].hT && dirs[d].ld_hs == dirs[0].ld_hs;
+        long long xc1 = 0;
+        if (ok3 && ndir == 2) {
+            xc1 = dirs[1].hs_h - dirs[0].hs_h;
+            ok3 = xc1 >= 0 && xc1 + HH <= dirs[0].ld_hs;
+        }
+        if (ok3) {
+            const int per = (b_seg + ns - 1) / ns;
+            const int bslr3 = (per + 63) / 64 * 64;
+            if (bslr3 > MAX_BSL) throw std::runtime_error("gru_tc: batch too large for the persistent kernel");
+            if (!c->flags[slot]) {
+                CUDA_CHECK(cudaMalloc(&c->flags[slot], (size_t)(c->num_sms / CL + 1) * CL * MAXCH3 * sizeof(unsigned)));
+                CUDA_CHECK(cudaMemset(c->flags[slot], 0, (size_t)(c->num_sms / CL + 1) * CL * MAXCH3 * sizeof(unsigned)));
+                CUDA_CHECK(cudaDeviceSynchronize());
+            }
+            P.off = d_off; P.nact = d_nact; P.xbuf = nullptr;
+            P.ndir = ndir; P.nslices = ns; P.b = b_seg; P.Ttot = Pl.Tmax; P.t0 = 0; P.Tseg = Tseg; P.bslr = bslr3;
+            P.tag_base = (c->launch_id++) << 12;
+            if (c->launch_id >= (1u << 20)) c->launch_id = 1;
+            P.prof = nullptr; P.poll_delay = 0;
+            CUtensorMap tm;
+            tma_encode_slice_rows_bf16(&tm, dirs[0].hs_h, dirs[0].ld_hs, Pl.rows, ns, 64);
+            TcFwd3X X3;
+            X3.flags = c->flags[slot]; X3.xcol[0] = 0; X3.xcol[1] = (int)xc1;
+            void* args3[] = {&P, &tm, &X3};
+            const size_t smem3 = fwd2_smem<64>(bslr3, Tseg);
+            if (smem3 > 232448) throw std::runtime_error("gru_tc: shared memory request exceeds 227 KB");
+            const int gg = pad ? std::max(groups, c->pad_groups) : groups;
+            if (pad == 2) CUDA_CHECK(cudaLaunchKernel((void*)k_gru_tc_fwd3<64>, dim3(gg * CL), dim3(NTH3), args3, smem3, s));
+            else CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gru_tc_fwd3<64>, dim3(gg * CL), dim3(NTH3), args3, smem3, s));
+            COUNT_LAUNCH();
+            return;
+        }
+    }
     const size_t need = (size_t)groups * 2 * bslr * (HH / 2);
     if (need > c->xcap[slot]) {
         CUDA_CHECK(cudaDeviceSynchronize());

@@ -54,6 +54,7 @@ void gemm_simt(const float* A, int lda, int a_mn, const float* B, int ldb, int b
 void gemm_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, float* Cf, bf16* Ch, int ldc,
              int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s, int short_units = 0);
 void gemm_tc_init(int device);
+void tma_encode_slice_rows_bf16(void* map_out /* CUtensorMap, 128 bytes */, const bf16* base, int ld, long long rows, int ns, int box_rows);
 bool gemm_tc_available();
 
 // ---- gru_generic.cu / gru_mma.cu ---------------------------------------------------------
@@ -120,6 +121,7 @@ GruTcCtx* gru_tc_create(int device);
 void gru_tc_destroy(GruTcCtx*);
 bool gru_tc_supported(int H);
 bool gru_tc_fits(const GruTcCtx*, int ndir, int b);
+bool gru_tc_throughput(const GruTcCtx*, int ndir, int b);   // rows per slice large enough for the TMA-fed forward kernel
 void gru_tc_fwd(GruTcCtx*, const GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
                 int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0, int rows_per_slice = 0, int pad = 0);
 void gru_tc_bwd(GruTcCtx*, const GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,

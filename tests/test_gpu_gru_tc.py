@@ -36,8 +36,10 @@ def test_ts_form_mma_matches_numpy(N, K, nacc):
     np.testing.assert_array_equal(D2, B2[:, (np.arange(128) * 7) % K].T)
 
 
-@pytest.mark.parametrize('mode', [1, 3])    # 1: forward recurrences on gru_tc.cu, backward on gru_mma.cu; 3: both on gru_tc.cu
-@pytest.mark.parametrize('b,tmax', [(3, 9), (64, 40), (100, 23), (150, 23), (257, 12), (512, 9)])
+# mode 1: forward recurrences on gru_tc.cu, backward on gru_mma.cu; 3: both on gru_tc.cu; 4 (the default): whole-layer
+# forward launches with many rows per slice take the TMA-fed tensor-memory kernel (flags + hs as the exchange), the rest mma.sync
+@pytest.mark.parametrize('mode', [1, 3, 4])
+@pytest.mark.parametrize('b,tmax', [(3, 9), (64, 40), (100, 23), (150, 23), (257, 12), (512, 9), (500, 33)])
 def test_tensor_memory_recurrence_matches_generic(monkeypatch, b, tmax, mode):
     """recurrences on gru_tc.cu (ARGSIM_GRU_TC) against the per-step generic GRU: losses, every gradient (the gate cache
     and hs the backward reads come from the new forward kernel), mu"""

@@ -67,6 +67,7 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     for (int i = 0; i < 3; ++i) CUDA_CHECK(cudaStreamCreateWithPriority(&st[i], cudaStreamNonBlocking, i == 2 ? prio_comm : prio_chain));
     for (auto& s : sw) CUDA_CHECK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio_chain));
     CUDA_CHECK(cudaStreamCreateWithPriority(&swg, cudaStreamNonBlocking, prio_least));
+    CUDA_CHECK(cudaStreamCreateWithPriority(&sad, cudaStreamNonBlocking, prio_least));
     if (const char* ev = getenv("ARGSIM_DEC_SEG")) dec_seg = atoi(ev);
     if (const char* ev = getenv("ARGSIM_ENC_SEG")) enc_seg = atoi(ev);
     enc_seg_fwd = getenv("ARGSIM_ENC_SEG_FWD") != nullptr;
@@ -160,9 +161,11 @@ Engine::~Engine() {
     for (auto& e : pev) cudaEventDestroy(e);
     for (auto& k : ktimers) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
     cudaEventDestroy(ev_bucket); cudaEventDestroy(ev_comm);
+    for (auto& e : ev_embed) if (e) cudaEventDestroy(e);
     for (auto& s : st) if (s) cudaStreamDestroy(s);
     for (auto& s : sw) if (s) cudaStreamDestroy(s);
     if (swg) cudaStreamDestroy(swg);
+    if (sad) cudaStreamDestroy(sad);
     for (auto& e : evpool) cudaEventDestroy(e);
 }
 
@@ -270,6 +273,11 @@ void Engine::gemm(const Mat& A, int a_mn, const Mat& B, int b_mn, const Mat& C, 
     }
 }
 
+// two long-lived events for the embedding pipeline (not part of the per-step pool that run_device() resets)
+cudaEvent_t Engine::next_event_persistent(int i) {
+    if (!ev_embed[i]) CUDA_CHECK(cudaEventCreateWithFlags(&ev_embed[i], cudaEventDisableTiming));
+    return ev_embed[i];
+}
 cudaEvent_t Engine::next_event() {
     if (evcount == evpool.size()) {
         cudaEvent_t e;
@@ -448,8 +456,9 @@ void Engine::stage(const int32_t* src, const int32_t* tgt, int b, int Ts, int Tt
         CUDA_CHECK(cudaMalloc(&d_stage, 2 * stage_cap * sizeof(int)));
     }
     // slot of the step being staged: the previous step's tables stay in the other one while it runs
-    int* const hs = h_stage + (submit_seq & 1) * stage_cap;
-    int* const ds = d_stage + (submit_seq & 1) * stage_cap;
+    const size_t slot_ = stage_slot >= 0 ? (size_t)stage_slot : (size_t)(submit_seq & 1);
+    int* const hs = h_stage + slot_ * stage_cap;
+    int* const ds = d_stage + slot_ * stage_cap;
     size_t o = 0;
     auto put = [&](const std::vector<int>& vsrc, int** dev) {
         *dev = ds + o;
@@ -859,6 +868,16 @@ void Engine::program(int mode, bool apply_update) {
     }
     phase("logits_ce");
     if (!train) return;
+    if (cfg.nranks > 1 && !arena.dry) {
+        // the step statistics (loss / error / KL sums) are final once the forward pass is: their 32-byte all-reduce goes
+        // out now, not at the end of the step where it would sit behind the last gradient bucket on the tail
+        NcclApi& n = NcclApi::get();
+        cudaEvent_t ev = next_event();
+        CUDA_CHECK(cudaEventRecord(ev, s));
+        CUDA_CHECK(cudaStreamWaitEvent(st[2], ev, 0));
+        n.check(n.AllReduce(d_stats, d_stats, 4, NcclApi::Float64, NcclApi::Sum, (NcclApi::comm_t)nccl_comm, st[2]),
+                "ncclAllReduce(stats)");
+    }
 
     // ---------------- backward: out affine
     Mat dY = f32(N, D);   // H == D (model.py:160: the decoder GRUs are dim_emb wide)
@@ -1183,10 +1202,18 @@ void Engine::program(int mode, bool apply_update) {
             // parallel: the NCCL stream, behind the layer-2 bucket's all-reduce) gets here, and no reader left on the
             // chain after the dgrad above: their Adam update (70 % of the 683 MB the update moves) runs under the last
             // layer's recurrence instead of after it.
-            cudaStream_t qa = cfg.nranks > 1 ? st[2] : swg;
+            // single GPU: on the side stream (behind the layer-2 weight gradients).  Data parallel: on a stream of its own
+            // that waits for the layer-2 bucket's all-reduce -- NOT on the NCCL stream, where the 0.3 ms this bandwidth-bound
+            // kernel takes on the few SMs the recurrence leaves free would sit in front of the last buckets' all-reduces
+            cudaStream_t qa = cfg.nranks > 1 ? sad : swg;
             cudaEvent_t ev = next_event();
             CUDA_CHECK(cudaEventRecord(ev, s));
             CUDA_CHECK(cudaStreamWaitEvent(qa, ev, 0));
+            if (cfg.nranks > 1) {
+                cudaEvent_t evc = next_event();
+                CUDA_CHECK(cudaEventRecord(evc, st[2]));
+                CUDA_CHECK(cudaStreamWaitEvent(qa, evc, 0));
+            }
             adam_split = end;
             adam_range(0, adam_split, qa, "k:adam_side");
         }
@@ -1202,11 +1229,13 @@ void Engine::program(int mode, bool apply_update) {
     allreduce_bucket(bucket_lo, nflat);
     bucket_lo = nflat;
     if (cfg.nranks > 1 && !arena.dry) {
-        NcclApi& n = NcclApi::get();
-        n.check(n.AllReduce(d_stats, d_stats, 4, NcclApi::Float64, NcclApi::Sum, (NcclApi::comm_t)nccl_comm, st[2]),
-                "ncclAllReduce(stats)");
         CUDA_CHECK(cudaEventRecord(ev_comm, st[2]));
         CUDA_CHECK(cudaStreamWaitEvent(s, ev_comm, 0));
+        if (adam_split) {   // the early Adam ran on its own stream behind the layer-2 bucket's all-reduce
+            cudaEvent_t ev = next_event();
+            CUDA_CHECK(cudaEventRecord(ev, sad));
+            CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));
+        }
     }
     phase("allreduce_wait");
 
@@ -1376,18 +1405,48 @@ void Engine::embed(const int32_t* src, int b, int T, float* mu_out) {
         order[i] = i;
     }
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return len[x] > len[y]; });
-    std::vector<int32_t> rows;
-    std::vector<float> out;
-    for (int i0 = 0; i0 < b; i0 += cap) {
-        const int n = std::min(cap, b - i0);
-        const int Tm = std::max(1, len[order[i0]]);     // longest row of this micro-batch (sorted descending)
-        rows.assign((size_t)n * Tm, cfg.eos);
-        for (int r = 0; r < n; ++r) memcpy(rows.data() + (size_t)r * Tm, src + (size_t)order[i0 + r] * T, sizeof(int32_t) * std::min(Tm, T));
-        // a row with eos inside its first Tm tokens keeps it and fails the trim() contract check, as it must
-        out.resize((size_t)n * R);
-        embed_one(rows.data(), n, Tm, out.data());
-        for (int r = 0; r < n; ++r) memcpy(mu_out + (size_t)order[i0 + r] * R, out.data() + (size_t)r * R, sizeof(float) * R);
+    // The micro-batches are pipelined: the host plan + H2D of micro-batch i+1 are issued while the device runs i, every
+    // mu lands in one pinned buffer and the stream is synchronised once at the end (two staging slots, one event each)
+    const size_t need = (size_t)b * R;
+    if (need > h_out_cap) {
+        CUDA_CHECK(cudaStreamSynchronize(st[0]));
+        cudaFreeHost(h_out);
+        CUDA_CHECK(cudaMallocHost(&h_out, need * sizeof(float)));
+        h_out_cap = need;
     }
+    cudaEvent_t ev_slot[2] = {next_event_persistent(0), next_event_persistent(1)};
+    std::vector<int32_t> rows;
+    DropoutSpec drop;
+    last = StepArgs();
+    int mb = 0;
+    try {
+        for (int i0 = 0; i0 < b; i0 += cap, ++mb) {
+            const int n = std::min(cap, b - i0);
+            const int Tm = std::max(1, len[order[i0]]);     // longest row of this micro-batch (sorted descending)
+            rows.assign((size_t)n * Tm, cfg.eos);
+            for (int r = 0; r < n; ++r) memcpy(rows.data() + (size_t)r * Tm, src + (size_t)order[i0 + r] * T, sizeof(int32_t) * std::min(Tm, T));
+            // a row with eos inside its first Tm tokens keeps it and fails the trim() contract check, as it must
+            stage_slot = mb & 1;
+            if (mb >= 2) CUDA_CHECK(cudaEventSynchronize(ev_slot[stage_slot]));   // the slot's previous H2D copy has been consumed
+            stage(rows.data(), nullptr, n, Tm, 0, 0, drop, nullptr);
+            run_device(0, false);
+            CUDA_CHECK(cudaMemcpy2DAsync(h_out + (size_t)i0 * R, (size_t)R * sizeof(float), outp.mulv, (size_t)2 * R * sizeof(float),
+                                         (size_t)R * sizeof(float), n, cudaMemcpyDeviceToHost, st[0]));
+            CUDA_CHECK(cudaEventRecord(ev_slot[stage_slot], st[0]));
+            if (mb >= 1) {   // the previous micro-batch's mu has landed: hand its rows out while the device runs this one
+                CUDA_CHECK(cudaEventSynchronize(ev_slot[(mb - 1) & 1]));
+                for (int r = i0 - cap; r < i0; ++r) memcpy(mu_out + (size_t)order[r] * R, h_out + (size_t)r * R, sizeof(float) * R);
+            }
+        }
+    } catch (...) {
+        stage_slot = -1;
+        cudaStreamSynchronize(st[0]);
+        throw;
+    }
+    stage_slot = -1;
+    CUDA_CHECK(cudaStreamSynchronize(st[0]));
+    collect_timings();
+    for (int r = (mb - 1) * cap; r < b; ++r) memcpy(mu_out + (size_t)order[r] * R, h_out + (size_t)r * R, sizeof(float) * R);
 }
 
 // decode(), model.py:204-219: fp32 SIMT path (host-driven single steps, batch <= a few hundred)

@@ -99,6 +99,7 @@ public:
 private:
     cudaStream_t st[3] = {nullptr, nullptr, nullptr};  // main, second GRU direction, comm
     cudaStream_t sw[8] = {};                            // decoder wavefront: one stream per layer
+    cudaStream_t sad = nullptr;                         // data parallel: the early Adam update (behind the layer-2 bucket's all-reduce)
     cudaStream_t swg = nullptr;                         // lowest-priority side stream: weight-gradient GEMMs and bias column sums
                                                         // run on the SMs the recurrence launches of the layer below leave free
     int group_cap = 0;                                  // ARGSIM_GROUP_CAP: groups of 16 CTAs the slice planners may use (0 = 9, or 8 under data parallel)
@@ -115,6 +116,8 @@ private:
     std::vector<cudaEvent_t> evpool;
     size_t evcount = 0;
     cudaEvent_t next_event();
+    cudaEvent_t ev_embed[2] = {nullptr, nullptr};
+    cudaEvent_t next_event_persistent(int i);
     int dec_seg = 64;                                   // time steps per wavefront segment (0 = off)
     int enc_seg = 171;                                  // encoder BPTT: time steps per (direction, segment) launch (0 = one launch per layer)
     int pad_wave = 0;                                   // 2: concurrent segment launches are padded to 128 blocks (plain launch), 0: not
@@ -141,6 +144,7 @@ private:
     int* h_stage = nullptr;  // pinned; two slots of stage_cap ints (one per step in flight)
     int* d_stage = nullptr;
     size_t stage_cap = 0;
+    int stage_slot = -1;        // >= 0: staging slot to use instead of submit_seq & 1 (pipelined embedding micro-batches)
     struct PendingStep {
         cudaEvent_t done = nullptr;
         double* h_stats = nullptr;   // pinned, 4 doubles

@@ -807,7 +807,7 @@ struct TcFwd3X {
     unsigned* flags;     // [group][CL][MAXCH3]
     int xcol[2];         // column of the direction's first unit in the hs matrix the tensor map covers
 };
-constexpr int MAXCH3 = 4;
+constexpr int MAXCH3 = 8;
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
@@ -816,25 +816,26 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, int c
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-template <int CN>
+template <int CN, int NS>
 __global__ void __launch_bounds__(NTH3, 1) k_gru_tc_fwd3(const __grid_constant__ TcFwdP P, const __grid_constant__ CUtensorMap tmH,
                                                          const __grid_constant__ TcFwd3X XP) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     if ((int)(blockIdx.x / CL) >= P.ndir * P.nslices) return;
     const uint32_t sbase = (smem_u32(sm_raw) + 1023u) & ~1023u;
     unsigned char* const sm = sm_raw + (sbase - smem_u32(sm_raw));
-    // [Hs: 2 x CN KB][G: 2 x 3*CN*32 f32][hst: bslr*32 f32][tables][barriers: full[2], dfull[2], dfree[2]][slot]
+    // NS operand slots / accumulators / gate-exchange buffers of CN rows each
+    // [Hs: NS x CN KB][G: NS x 3*CN*32 f32][hst: bslr*32 f32][tables][barriers: full[NS], dfull[NS], dfree[NS]][slot]
     const uint32_t Hs0 = sbase;
-    float* G0 = reinterpret_cast<float*>(sm + 2 * CN * 1024);
-    float* hst = G0 + 2 * 3 * CN * UN;
+    float* G0 = reinterpret_cast<float*>(sm + NS * CN * 1024);
+    float* hst = G0 + NS * 3 * CN * UN;
     int* s_nact = reinterpret_cast<int*>(hst + (size_t)P.bslr * UN);
     int* s_off = s_nact + P.Tseg + 2;
     unsigned long long* barp = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(s_off + P.Tseg + 2) + 15) & ~uintptr_t(15));
     const uint32_t bars = smem_u32(barp);
     auto full = [&](int slot) { return bars + 8u * (uint32_t)slot; };
-    auto dfull = [&](int slot) { return bars + 8u * (uint32_t)(2 + slot); };
-    auto dfree = [&](int slot) { return bars + 8u * (uint32_t)(4 + slot); };
-    const uint32_t tslot = bars + 8u * 6;
+    auto dfull = [&](int slot) { return bars + 8u * (uint32_t)(NS + slot); };
+    auto dfree = [&](int slot) { return bars + 8u * (uint32_t)(2 * NS + slot); };
+    const uint32_t tslot = bars + 8u * (3 * NS);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int grp = blockIdx.x / CL, c = blockIdx.x % CL;
@@ -846,9 +847,7 @@ __global__ void __launch_bounds__(NTH3, 1) k_gru_tc_fwd3(const __grid_constant__
         s_off[i] = (tt >= 0 && tt <= P.Ttot) ? P.off[tt] : 0;
     }
     if (tid == 0) {
-        mbar_init(full(0), 1); mbar_init(full(1), 1);
-        mbar_init(dfull(0), 1); mbar_init(dfull(1), 1);
-        mbar_init(dfree(0), 6); mbar_init(dfree(1), 6);
+        for (int i = 0; i < NS; ++i) { mbar_init(full(i), 1); mbar_init(dfull(i), 1); mbar_init(dfree(i), 6); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmH) : "memory");
     }
@@ -903,7 +902,7 @@ __global__ void __launch_bounds__(NTH3, 1) k_gru_tc_fwd3(const __grid_constant__
             const long long row_base = OFF(t);
             const int npoll = a == 0 ? 0 : min(na, na_prev);
             for (int ch = 0; ch * CN < na; ++ch, ++q) {
-                const int slot = q & 1, u = q >> 1;
+                const int slot = q % NS, u = q / NS;
                 const int nrows = min(CN, na - ch * CN);
                 float gxv[RPT][3];
 #pragma unroll
@@ -991,7 +990,7 @@ __global__ void __launch_bounds__(NTH3, 1) k_gru_tc_fwd3(const __grid_constant__
             const int tp = A.reverse ? t + 1 : t - 1;                      // the step whose output rows are h_prev
             const long long prev_base = (tp >= 0 && tp < P.Ttot) ? OFF(tp) : 0;
             for (int ch = 0; ch * CN < na; ++ch, ++q) {
-                const int slot = q & 1, u = q >> 1;
+                const int slot = q % NS, u = q / NS;
                 if (u >= 1) mbar_wait(dfull(slot), (uint32_t)((u - 1) & 1));   // the MMAs that read this slot last are complete
                 if (ch * CN < npoll) {
                     const unsigned want = P.tag_base + (unsigned)a;            // written after active step a - 1
@@ -1033,7 +1032,7 @@ __global__ void __launch_bounds__(NTH3, 1) k_gru_tc_fwd3(const __grid_constant__
                 break;
             }
             for (int ch = 0; ch * CN < na; ++ch, ++q) {
-                const int slot = q & 1, u = q >> 1;
+                const int slot = q % NS, u = q / NS;
                 const uint32_t Hs = Hs0 + (uint32_t)(slot * CN * 1024);
                 const uint32_t td = tmem + TM_D + (uint32_t)(slot * CN);
                 if (u >= 1) mbar_wait(dfree(slot), (uint32_t)((u - 1) & 1));
@@ -1508,6 +1507,10 @@ template <int CN>
 size_t fwd2_smem(int bslr, int Tseg) {
     return 1024 + (size_t)2 * CN * 1024 + (size_t)2 * 3 * CN * UN * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 16 + 14 * 8 + 16;
 }
+template <int CN, int NS>
+size_t fwd3_smem(int bslr, int Tseg) {
+    return 1024 + (size_t)NS * CN * 1024 + (size_t)NS * 3 * CN * UN * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 16 + (3 * NS + 2) * 8 + 16;
+}
 template <int CN>
 size_t bwd_smem(int bslr, int Tseg) {
     return 1024 + (size_t)2 * CN * 128 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 16 + 16 + 16;
@@ -1528,6 +1531,8 @@ struct GruTcCtx {
     unsigned long long* ybuf[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
     size_t ycap[NSLOT] = {0, 0, 0, 0};
     unsigned* flags[NSLOT] = {nullptr, nullptr, nullptr, nullptr};   // forward kernel 3: [group][CL][MAXCH3] step flags
+    int fwd3_cn = 64;            // ARGSIM_GRU_TC_FWD3_CN: 64 = two slots of 64 rows in flight (embed micro-batch 0: 3.09 ms), 32 = four slots of
+                                 // 32 rows (3.56 ms: the per-chunk costs -- flag round trip, 32 MMA issues -- do not shrink with the chunk)
     int fwd3_min_rows = 48;      // ARGSIM_GRU_TC_FWD3_ROWS: rows per slice from which whole-layer launches take the TMA-fed kernel
     int pad_groups = 8;
     int force_cn = 0;            // ARGSIM_GRU_TC_CN: rows per MMA chunk (16 / 32 / 64 / 128), 0 = by live rows
@@ -1552,7 +1557,9 @@ GruTcCtx* gru_tc_create(int device) {
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     if (const char* v = getenv("ARGSIM_GRU_TC_FWD")) c->fwd_version = atoi(v);
     if (const char* v = getenv("ARGSIM_GRU_TC_FWD3_ROWS")) c->fwd3_min_rows = atoi(v);
-    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd3<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd3<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd3<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    if (const char* v = getenv("ARGSIM_GRU_TC_FWD3_CN")) c->fwd3_cn = atoi(v);
     if (const char* v = getenv("ARGSIM_GRU_TC_DELAY")) c->poll_delay = atoi(v);
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -1645,16 +1652,18 @@ void gru_tc_fwd(GruTcCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& Pl
             P.tag_base = (c->launch_id++) << 12;
             if (c->launch_id >= (1u << 20)) c->launch_id = 1;
             P.prof = nullptr; P.poll_delay = 0;
+            const bool c32 = c->fwd3_cn == 32;
             CUtensorMap tm;
-            tma_encode_slice_rows_bf16(&tm, dirs[0].hs_h, dirs[0].ld_hs, Pl.rows, ns, 64);
+            tma_encode_slice_rows_bf16(&tm, dirs[0].hs_h, dirs[0].ld_hs, Pl.rows, ns, c32 ? 32 : 64);
             TcFwd3X X3;
             X3.flags = c->flags[slot]; X3.xcol[0] = 0; X3.xcol[1] = (int)xc1;
             void* args3[] = {&P, &tm, &X3};
-            const size_t smem3 = fwd2_smem<64>(bslr3, Tseg);
+            const size_t smem3 = c32 ? fwd3_smem<32, 4>(bslr3, Tseg) : fwd3_smem<64, 2>(bslr3, Tseg);
             if (smem3 > 232448) throw std::runtime_error("gru_tc: shared memory request exceeds 227 KB");
             const int gg = pad ? std::max(groups, c->pad_groups) : groups;
-            if (pad == 2) CUDA_CHECK(cudaLaunchKernel((void*)k_gru_tc_fwd3<64>, dim3(gg * CL), dim3(NTH3), args3, smem3, s));
-            else CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_gru_tc_fwd3<64>, dim3(gg * CL), dim3(NTH3), args3, smem3, s));
+            void* fn3 = c32 ? (void*)k_gru_tc_fwd3<32, 4> : (void*)k_gru_tc_fwd3<64, 2>;
+            if (pad == 2) CUDA_CHECK(cudaLaunchKernel(fn3, dim3(gg * CL), dim3(NTH3), args3, smem3, s));
+            else CUDA_CHECK(cudaLaunchCooperativeKernel(fn3, dim3(gg * CL), dim3(NTH3), args3, smem3, s));
             COUNT_LAUNCH();
             return;
         }

@@ -301,7 +301,10 @@ bool Engine::enc_segmented(const SeqPlan& E) const {
 // BPTT: the other way round.  Launch i of both chains run side by side.
 void Engine::enc_slice_plan(const SeqPlan& E, int nseg, bool bptt, std::vector<int>* want8) const {
     want8->assign((size_t)2 * nseg, 0);
-    const int cap = group_cap ? group_cap : cfg.nranks > 1 ? 8 : 9;   // groups of 16 CTAs; data parallel leaves 20 SMs to the NCCL kernels of the overlapped buckets
+    // groups of 16 CTAs.  Round 1 gave data-parallel runs 8 so that 20 SMs stay free for the NCCL kernels of the overlapped
+    // buckets; measured on 2 GPUs with the tail fixed (statistics / early Adam off the NCCL stream) 9 is faster: step 10.83 ->
+    // 10.66 ms, encoder BPTT 4.25 -> 3.77 ms, exposed all-reduce wait 0.10 ms either way (ARGSIM_GROUP_CAP=8 restores it)
+    const int cap = group_cap ? group_cap : 9;
     for (int i = 0; i < nseg; ++i) {
         int rows[2], g16[2], g8[2];
         for (int d = 0; d < 2; ++d) {
@@ -725,7 +728,7 @@ void Engine::program(int mode, bool apply_update) {
     // 8-row slices first.  want8[j * nseg + sg] = 1 -> 8 rows per slice.
     std::vector<int> want8((size_t)L * nseg, 0);
     if (wave && slice_budget) {
-        const int max_groups = group_cap ? group_cap : cfg.nranks > 1 ? 8 : 9;   // data parallel: leave 20 SMs to the NCCL kernels of the overlapped buckets
+        const int max_groups = group_cap ? group_cap : 9;
         for (int stage = 0; stage < nseg + L - 1; ++stage) {
             std::vector<std::pair<int, int>> items;   // (live rows, j)
             int total = 0;

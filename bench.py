@@ -210,7 +210,7 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=('ours', 'reference'))
-    ap.add_argument('--workload', default='train', choices=('train', 'embed'))
+    ap.add_argument('--workload', default='train', choices=('train', 'embed', 'scaled'))
     ap.add_argument('--precision', default='bf16', choices=('bf16', 'fp32'))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extra', action='store_true', help='skip the embed / strong_scaling sub-records')
@@ -237,7 +237,9 @@ def main():
         nccl_id = obj[0]
     flags = _lib.FLAG_KERNEL_TIMERS | (_lib.FLAG_GENERIC_GRU if args.generic_gru else 0)
     prec = _lib.BF16 if args.precision == 'bf16' else _lib.FP32_VALIDATE
-    h = _lib.Handle(precision=prec, device=local, nranks=world, rank=rank, nccl_id=nccl_id, flags=flags, **CFG)
+    cfg4 = dict(CFG, dim_tgt=32768, dim_emb=2048, dim_rep=4096)     # BASELINE configs[4]
+    h = _lib.Handle(precision=prec, device=local, nranks=world, rank=rank, nccl_id=nccl_id, flags=flags,
+                    **(cfg4 if args.workload == 'scaled' else CFG))
     h.init_params(0)
     h.set_seed(0)
 
@@ -253,6 +255,39 @@ def main():
         t = torch.tensor([x], device='cuda', dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    if args.workload == 'scaled':
+        # BASELINE configs[4]: scaled VAE (4x hidden width, 32k vocabulary, every row 512 tokens), data parallel, 64 rows per GPU
+        full4 = synth_batch(PER_GPU * world, 'full', cfg4['dim_tgt'], seed=0, cap=512)
+        s4, t4, rows4, ntok4, b4 = parallel.shard_batch(full4, full4, world, rank)
+        kw4 = dict(n_tokens_global=ntok4, b_global=b4, rows=rows4) if world > 1 else {}
+        for _ in range(max(2, min(args.warmup, 3))):
+            st4 = h.train_step(s4, t4, **kw4)
+        barrier()
+        clk = Clocks(local)
+        k4 = max(2, min(args.steps, 5))
+        ms4 = max_over_ranks(h.bench_resident(k4))
+        clocks4 = clk.stop()
+        tm4 = h.last_timings()
+        barrier()
+        if rank == 0:
+            S4 = int((full4 != 1).sum())
+            H4, V4, R4 = 2048, 32768, 4096
+            fl4 = 3.0 * ((2 * 2 * 3 * H4 * (H4 + H4) + 2 * 2 * 2 * 3 * H4 * (2 * H4 + H4)) * S4 + (3 * 2 * 3 * H4 * (H4 + H4) + 2 * H4 * H4) * ntok4
+                         + 2 * H4 * V4 * ntok4 + (2 * 2 * (2 * H4) * R4 + 2 * R4 * H4) * b4)
+            print(json.dumps(dict(metric=METRIC + ', scaled config', value=PER_GPU * world / (ms4 / 1e3), unit='sequences/s', n_gpus=world, steps=k4,
+                                  warmup=3, ms_per_step=ms4, higher_is_better=True, scaling='weak', vs_baseline=None, dtype=args.precision,
+                                  data='synthetic',
+                                  config=dict(workload='scaled VAE (V=32768 D=2048 R=4096 L=3), every row 512 tokens, 64 sequences per GPU '
+                                                       '(BASELINE configs[4])', global_batch=PER_GPU * world, src_tokens=S4, tgt_rows=int(ntok4),
+                                              parallelism='dp%d' % world),
+                                  clocks=clocks4, phases_ms={k: round(v, 3) for k, v in tm4.items() if not k.startswith('k:')},
+                                  kernels_ms={k[2:]: round(v, 3) for k, v in tm4.items() if k.startswith('k:') and '#' not in k},
+                                  step_tflops=round(fl4 / (ms4 * 1e-3) / 1e12, 2), step_frac_of_tensor_peak=round(fl4 / (ms4 * 1e-3) / 1e12 / pk['tf_sust'] / world, 4),
+                                  last_step=dict(loss=st4['loss'], loss_gen=st4['loss_gen'], loss_kld=st4['loss_kld']))), flush=True)
+        if dist:
+            dist.destroy_process_group()
+        return
 
     if args.workload == 'embed':
         data = synth_batch(4096 * world, 'ibm', CFG['dim_tgt'], seed=0)

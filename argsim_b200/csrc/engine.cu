@@ -807,6 +807,13 @@ void Engine::program(int mode, bool apply_update) {
     const float scale = 1.0f / sqrtf((float)D);
     long long chunk = use_tc ? 4096 : 2048;
     if (logit_chunk) chunk = logit_chunk;
+    else if (use_tc && N > 0) {
+        // equal chunks of at most 4608 rows (75 MB of bf16 logits: L2 resident) instead of 4096-row chunks plus a tail: the C1
+        // batch (N = 8,872) ran 4096 + 4096 + 680 rows, and the 680-row launches of the GEMMs and of the fused softmax-CE
+        // (less than one wave of 5 rows per SM) dragged the group averages down (softmax-CE 0.72 of HBM peak in-step)
+        const long long nch = (N + 4607) / 4608;
+        chunk = ((N + nch - 1) / nch + 127) / 128 * 128;
+    }
     chunk = std::min<long long>(chunk, std::max<long long>(N, 1));
     // Weight gradients are not on the serial chain: with the persistent recurrence in use they go to the low-priority
     // side stream and fill the SMs the recurrence launches of the layers below leave free (a third of the encoder's

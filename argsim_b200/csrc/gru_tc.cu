@@ -26,7 +26,7 @@ constexpr int HH = 512;
 constexpr int CL = 16;     // CTAs per group
 constexpr int UN = 32;     // hidden units per CTA
 constexpr int NTH = 256;
-constexpr int MAX_BSL = 256;
+constexpr int MAX_BSL = 288;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_A = 0;       // columns [0,256): R_own
 constexpr uint32_t TM_D = 256;     // columns [256, 256 + CN): accumulator
@@ -802,7 +802,7 @@ __global__ void __launch_bounds__(NTH2, 1) k_gru_tc_fwd2(const __grid_constant__
 // exchange (a release fence and two L2 round trips); with >= 2 chunks per step in flight that is hidden.
 // Used when no initial / final state is handed over (h0 == hT == null: whole-layer launches).
 // =========================================================================================
-constexpr int NTH3 = 320;
+// threads: GW gate warps + producer + MMA warp
 struct TcFwd3X {
     unsigned* flags;     // [group][CL][MAXCH3]
     int xcol[2];         // column of the direction's first unit in the hs matrix the tensor map covers
@@ -816,18 +816,25 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, int c
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
-template <int CN, int NS>
-__global__ void __launch_bounds__(NTH3, 1) k_gru_tc_fwd3(const __grid_constant__ TcFwdP P, const __grid_constant__ CUtensorMap tmH,
+__device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+template <int CN, int NS, int GW>
+__global__ void __launch_bounds__((GW + 2) * 32, 1) k_gru_tc_fwd3(const __grid_constant__ TcFwdP P, const __grid_constant__ CUtensorMap tmH,
                                                          const __grid_constant__ TcFwd3X XP) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     if ((int)(blockIdx.x / CL) >= P.ndir * P.nslices) return;
     const uint32_t sbase = (smem_u32(sm_raw) + 1023u) & ~1023u;
     unsigned char* const sm = sm_raw + (sbase - smem_u32(sm_raw));
-    // NS operand slots / accumulators / gate-exchange buffers of CN rows each
-    // [Hs: NS x CN KB][G: NS x 3*CN*32 f32][hst: bslr*32 f32][tables][barriers: full[NS], dfull[NS], dfree[NS]][slot]
+    // NS operand slots / accumulators of CN rows each; ONE gate-exchange buffer (two gate barriers per chunk protect it)
+    // [Hs: NS x CN KB][G: 3*CN*32 f32][hst: bslr*32 f32][tables][barriers: full[NS], dfull[NS], dfree[NS]][slot]
     const uint32_t Hs0 = sbase;
+    constexpr int NTH3 = (GW + 2) * 32;
+    constexpr int NPART = GW / 4;            // column parts: the GW/4 warps of a lane quadrant split the CN accumulator columns
+    constexpr int PC = CN / NPART;           // columns per part: a multiple of 4
+    static_assert(PC % 4 == 0 && CN % GW == 0, "chunk / gate-warp geometry");
     float* G0 = reinterpret_cast<float*>(sm + NS * CN * 1024);
-    float* hst = G0 + NS * 3 * CN * UN;
+    float* hst = G0 + 3 * CN * UN;
     int* s_nact = reinterpret_cast<int*>(hst + (size_t)P.bslr * UN);
     int* s_off = s_nact + P.Tseg + 2;
     unsigned long long* barp = reinterpret_cast<unsigned long long*>((reinterpret_cast<uintptr_t>(s_off + P.Tseg + 2) + 15) & ~uintptr_t(15));
@@ -847,7 +854,7 @@ __global__ void __launch_bounds__(NTH3, 1) k_gru_tc_fwd3(const __grid_constant__
         s_off[i] = (tt >= 0 && tt <= P.Ttot) ? P.off[tt] : 0;
     }
     if (tid == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(full(i), 1); mbar_init(dfull(i), 1); mbar_init(dfree(i), 6); }
+        for (int i = 0; i < NS; ++i) { mbar_init(full(i), 1); mbar_init(dfull(i), 1); mbar_init(dfree(i), 3 * NPART); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmH) : "memory");
     }
@@ -885,12 +892,12 @@ __global__ void __launch_bounds__(NTH3, 1) k_gru_tc_fwd3(const __grid_constant__
     __syncthreads();
     tc_fence_after();
 
-    if (warp < 8) {
+    if (warp < GW) {
         // =========================== GATE warps ===========================
-        const int gw = warp, quad = warp & 3, half = warp >> 2;
+        const int gw = warp, quad = warp & 3, part = warp >> 2;
         const int col = UN * c + lane;
         const float bRr = A.bR[col], bRu = A.bR[HH + col], bRn = A.bR[2 * HH + col];
-        constexpr int RPT = CN / 8;
+        constexpr int RPT = CN / GW;
         int q = 0, na_prev = 0, a = 0;
         for (int k = 0; k < P.Tseg; ++k) {
             const int t = A.reverse ? P.t0 + P.Tseg - 1 - k : P.t0 + k;
@@ -907,33 +914,34 @@ __global__ void __launch_bounds__(NTH3, 1) k_gru_tc_fwd3(const __grid_constant__
                 float gxv[RPT][3];
 #pragma unroll
                 for (int e = 0; e < RPT; ++e) {
-                    const int n = gw + 8 * e;
+                    const int n = gw + GW * e;
                     gxv[e][0] = gxv[e][1] = gxv[e][2] = 0.f;
                     if (n < nrows) {
                         const float* gp = A.gx + (size_t)(row_base + (long long)(ch * CN + n) * ns + sl) * A.ld_gx + col;
                         gxv[e][0] = ld_f32(gp); gxv[e][1] = ld_f32(gp + HH); gxv[e][2] = ld_f32(gp + 2 * HH);
                     }
                 }
-                float* G = G0 + (size_t)slot * 3 * CN * UN;
+                float* G = G0;
                 if (quad < 3) {
                     mbar_wait(dfull(slot), (uint32_t)(u & 1));
                     tc_fence_after();
-                    const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + TM_D + (uint32_t)(slot * CN + half * (CN / 2));
-                    uint32_t r[CN / 2];
+                    const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + TM_D + (uint32_t)(slot * CN + part * PC);
+                    uint32_t r[PC];
 #pragma unroll
-                    for (int i = 0; i < CN / 16; ++i) tc_ld8(ta + 8 * i, r + 8 * i);
+                    for (int i = 0; i < PC / 8; ++i) tc_ld8(ta + 8 * i, r + 8 * i);
+                    if (PC % 8) tc_ld4(ta + (PC / 8) * 8, r + (PC / 8) * 8);
                     tc_wait_ld();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(dfree(slot));
-                    float* gp = G + ((size_t)quad * CN + half * (CN / 2)) * UN + lane;
+                    float* gp = G + ((size_t)quad * CN + part * PC) * UN + lane;
 #pragma unroll
-                    for (int i = 0; i < CN / 2; ++i) gp[i * UN] = __uint_as_float(r[i]);
+                    for (int i = 0; i < PC; ++i) gp[i * UN] = __uint_as_float(r[i]);
                 }
-                gate_bar();
+                asm volatile("bar.sync 1, %0;" ::"n"(GW * 32) : "memory");
 #pragma unroll
                 for (int e = 0; e < RPT; ++e) {
-                    const int n = gw + 8 * e;
+                    const int n = gw + GW * e;
                     if (n < nrows) {
                         const int jl = ch * CN + n;
                         // rows without a predecessor (first step; rows that join here) start from h = 0: R h = 0, whatever the
@@ -957,7 +965,7 @@ __global__ void __launch_bounds__(NTH3, 1) k_gru_tc_fwd3(const __grid_constant__
                         }
                     }
                 }
-                gate_bar();   // all 8 gate warps have written their rows of the chunk (and are done with G[slot])
+                asm volatile("bar.sync 1, %0;" ::"n"(GW * 32) : "memory");   // all gate warps have written their rows of the chunk (and are done with G)
                 if (tid == 0) {
                     const unsigned val = P.tag_base + (unsigned)a + 1u;
                     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + c * MAXCH3 + ch), "r"(val) : "memory");
@@ -966,7 +974,7 @@ __global__ void __launch_bounds__(NTH3, 1) k_gru_tc_fwd3(const __grid_constant__
                     const int tn = A.reverse ? t - 2 : t + 2;
                     const int nan = NA(tn);
                     const long long rbn = OFF(tn);
-                    for (int n = gw; n < nan; n += 8) {
+                    for (int n = gw; n < nan; n += GW) {
                         const float* gp = A.gx + (size_t)(rbn + (long long)n * ns + sl) * A.ld_gx + UN * c;
                         if (lane < 3) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + lane * HH));
                     }
@@ -975,7 +983,7 @@ __global__ void __launch_bounds__(NTH3, 1) k_gru_tc_fwd3(const __grid_constant__
             na_prev = na;
             ++a;
         }
-    } else if (warp == 8) {
+    } else if (warp == GW) {
         // =========================== PRODUCER warp: flags + TMA ===========================
         const bool leader = elect_one();
         int q = 0, na_prev = 0, a = 0;
@@ -1509,7 +1517,7 @@ size_t fwd2_smem(int bslr, int Tseg) {
 }
 template <int CN, int NS>
 size_t fwd3_smem(int bslr, int Tseg) {
-    return 1024 + (size_t)NS * CN * 1024 + (size_t)NS * 3 * CN * UN * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 16 + (3 * NS + 2) * 8 + 16;
+    return 1024 + (size_t)NS * CN * 1024 + (size_t)3 * CN * UN * 4 + (size_t)bslr * UN * 4 + (size_t)(2 * Tseg + 4) * 4 + 16 + (3 * NS + 2) * 8 + 16;
 }
 template <int CN>
 size_t bwd_smem(int bslr, int Tseg) {
@@ -1531,8 +1539,11 @@ struct GruTcCtx {
     unsigned long long* ybuf[NSLOT] = {nullptr, nullptr, nullptr, nullptr};
     size_t ycap[NSLOT] = {0, 0, 0, 0};
     unsigned* flags[NSLOT] = {nullptr, nullptr, nullptr, nullptr};   // forward kernel 3: [group][CL][MAXCH3] step flags
-    int fwd3_cn = 64;            // ARGSIM_GRU_TC_FWD3_CN: 64 = two slots of 64 rows in flight (embed micro-batch 0: 3.09 ms), 32 = four slots of
-                                 // 32 rows (3.56 ms: the per-chunk costs -- flag round trip, 32 MMA issues -- do not shrink with the chunk)
+    int fwd3_cn = 6416;          // ARGSIM_GRU_TC_FWD3_CN: variant of the TMA-fed kernel.  Recurrence of the first embedding micro-batch (1,024
+                                 // rows, 153 steps, 3 layers): 6416 = two slots of 64 rows, 16 gate warps: 2.75 ms; 48 = three slots of 48 rows, 16
+                                 // gate warps: 3.02 ms; 64 = two slots of 64 rows, 8 gate warps: 3.09-3.22 ms; 32 = four slots of 32 rows, 8 gate
+                                 // warps: 3.56 ms (the per-chunk costs -- flag round trip, 32 MMA issues -- do not shrink with the chunk; the
+                                 // gate math does shrink with the number of gate warps)
     int fwd3_min_rows = 48;      // ARGSIM_GRU_TC_FWD3_ROWS: rows per slice from which whole-layer launches take the TMA-fed kernel
     int pad_groups = 8;
     int force_cn = 0;            // ARGSIM_GRU_TC_CN: rows per MMA chunk (16 / 32 / 64 / 128), 0 = by live rows
@@ -1557,8 +1568,10 @@ GruTcCtx* gru_tc_create(int device) {
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     if (const char* v = getenv("ARGSIM_GRU_TC_FWD")) c->fwd_version = atoi(v);
     if (const char* v = getenv("ARGSIM_GRU_TC_FWD3_ROWS")) c->fwd3_min_rows = atoi(v);
-    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd3<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd3<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd3<64, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd3<32, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd3<48, 3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd3<64, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     if (const char* v = getenv("ARGSIM_GRU_TC_FWD3_CN")) c->fwd3_cn = atoi(v);
     if (const char* v = getenv("ARGSIM_GRU_TC_DELAY")) c->poll_delay = atoi(v);
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_bwd<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -1598,7 +1611,7 @@ bool gru_tc_throughput(const GruTcCtx* c, int ndir, int b) {
     int ns, bslr, cn;
     tc_pick(c, ndir, b, 0, &ns, &bslr, &cn);
     const int per = (b + ns - 1) / ns;
-    return c->fwd_version >= 2 && per >= c->fwd3_min_rows && (per + 63) / 64 * 64 <= MAX_BSL;
+    return c->fwd_version >= 2 && per >= c->fwd3_min_rows && per <= 256;
 }
 bool gru_tc_fits(const GruTcCtx* c, int ndir, int b) {
     int ns, bslr, cn;
@@ -1640,7 +1653,11 @@ void gru_tc_fwd(GruTcCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& Pl
         }
         if (ok3) {
             const int per = (b_seg + ns - 1) / ns;
-            const int bslr3 = (per + 63) / 64 * 64;
+            // variant: rows per chunk x slots x gate warps.  48: 3 slots of 48 rows, 16 gate warps; 64 / 32: two / four slots, 8 gate warps;
+            // 6416: 2 slots of 64 rows, 16 gate warps
+            const int var = c->fwd3_cn;
+            const int cn3 = var == 48 ? 48 : var == 32 ? 32 : 64;
+            const int bslr3 = (per + cn3 - 1) / cn3 * cn3;
             if (bslr3 > MAX_BSL) throw std::runtime_error("gru_tc: batch too large for the persistent kernel");
             if (!c->flags[slot]) {
                 CUDA_CHECK(cudaMalloc(&c->flags[slot], (size_t)(c->num_sms / CL + 1) * CL * MAXCH3 * sizeof(unsigned)));
@@ -1652,18 +1669,20 @@ void gru_tc_fwd(GruTcCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& Pl
             P.tag_base = (c->launch_id++) << 12;
             if (c->launch_id >= (1u << 20)) c->launch_id = 1;
             P.prof = nullptr; P.poll_delay = 0;
-            const bool c32 = c->fwd3_cn == 32;
             CUtensorMap tm;
-            tma_encode_slice_rows_bf16(&tm, dirs[0].hs_h, dirs[0].ld_hs, Pl.rows, ns, c32 ? 32 : 64);
+            tma_encode_slice_rows_bf16(&tm, dirs[0].hs_h, dirs[0].ld_hs, Pl.rows, ns, cn3);
             TcFwd3X X3;
             X3.flags = c->flags[slot]; X3.xcol[0] = 0; X3.xcol[1] = (int)xc1;
             void* args3[] = {&P, &tm, &X3};
-            const size_t smem3 = c32 ? fwd3_smem<32, 4>(bslr3, Tseg) : fwd3_smem<64, 2>(bslr3, Tseg);
+            void* fn3; size_t smem3; int nth3;
+            if (var == 48) { fn3 = (void*)k_gru_tc_fwd3<48, 3, 16>; smem3 = fwd3_smem<48, 3>(bslr3, Tseg); nth3 = 18 * 32; }
+            else if (var == 32) { fn3 = (void*)k_gru_tc_fwd3<32, 4, 8>; smem3 = fwd3_smem<32, 4>(bslr3, Tseg); nth3 = 10 * 32; }
+            else if (var == 6416) { fn3 = (void*)k_gru_tc_fwd3<64, 2, 16>; smem3 = fwd3_smem<64, 2>(bslr3, Tseg); nth3 = 18 * 32; }
+            else { fn3 = (void*)k_gru_tc_fwd3<64, 2, 8>; smem3 = fwd3_smem<64, 2>(bslr3, Tseg); nth3 = 10 * 32; }
             if (smem3 > 232448) throw std::runtime_error("gru_tc: shared memory request exceeds 227 KB");
             const int gg = pad ? std::max(groups, c->pad_groups) : groups;
-            void* fn3 = c32 ? (void*)k_gru_tc_fwd3<32, 4> : (void*)k_gru_tc_fwd3<64, 2>;
-            if (pad == 2) CUDA_CHECK(cudaLaunchKernel(fn3, dim3(gg * CL), dim3(NTH3), args3, smem3, s));
-            else CUDA_CHECK(cudaLaunchCooperativeKernel(fn3, dim3(gg * CL), dim3(NTH3), args3, smem3, s));
+            if (pad == 2) CUDA_CHECK(cudaLaunchKernel(fn3, dim3(gg * CL), dim3(nth3), args3, smem3, s));
+            else CUDA_CHECK(cudaLaunchCooperativeKernel(fn3, dim3(gg * CL), dim3(nth3), args3, smem3, s));
             COUNT_LAUNCH();
             return;
         }

@@ -472,9 +472,12 @@ def main():
     if dom:
         d = kernels[dom]
         traffic = None
-        try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/), if there is one
-            with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
-                traffic = json.load(f).get(dom)
+        try:   # DRAM bytes per launch from the committed ncu --set full captures of this round (profiles/r2_traffic.json)
+            with open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')) as f:
+                tr = json.load(f)
+            tkey = [k for k in tr if ('k_gru_mma_bwd' in k if dom.startswith('gru_bwd') else 'k_gru_mma_fwd2' in k if dom.startswith('gru_fwd') else False)]
+            if tkey:
+                traffic = tr[tkey[0]]['dram_bytes_per_launch']
         except Exception:
             pass
         roofline = dict(kernel=dom, bound=d['bound'], achieved=d['achieved'], peak=d['peak'],
@@ -483,7 +486,7 @@ def main():
                         note='avg launch duration from CUDA events on the launching stream inside the timed region; '
                              'the recurrence is bound by serial-step latency (512 dependent steps per launch, one 16-CTA '
                              'exchange through L2 each: >= 1270 cycles, DESIGN.md section 5), not by the tensor pipe; '
-                             'traffic = dram bytes per launch from profiles/r1c_gru_*_enc_ncu.md')
+                             'traffic = dram bytes per launch of the same kernel on decoder segment launches (profiles/r2_gru_*_ncu.md, r2_traffic.json)')
         if dom.startswith('gru_'):
             # what actually bounds these kernels: serial steps x per-step latency.  Encoder: one launch (or segment chain)
             # per layer, Tmax_src dependent steps each; decoder: a 3-layer wavefront over Tmax_dec steps.

@@ -811,6 +811,8 @@ void Engine::program(int mode, bool apply_update) {
         // equal chunks of at most 4608 rows (75 MB of bf16 logits: L2 resident) instead of 4096-row chunks plus a tail: the C1
         // batch (N = 8,872) ran 4096 + 4096 + 680 rows, and the 680-row launches of the GEMMs and of the fused softmax-CE
         // (less than one wave of 5 rows per SM) dragged the group averages down (softmax-CE 0.72 of HBM peak in-step)
+        // (capping the chunk so that its logits stay L2 resident at V = 32768 -- 1,152 rows -- was measured slower on the scaled
+        // config: logits phase 11.6 -> 13.0 ms, 29 launches per GEMM instead of 8)
         const long long nch = (N + 4607) / 4608;
         chunk = ((N + nch - 1) / nch + 127) / 128 * 128;
     }

@@ -566,7 +566,7 @@ k_gemm_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 }
 }  // namespace v2
 
-void encode_map(CUtensorMap* map, const bf16* ptr, int ld, int mn_major, long long rows_mn, long long K, int tile_mn) {
+void encode_map_raw(CUtensorMap* map, const bf16* ptr, int ld, int mn_major, long long rows_mn, long long K, int tile_mn) {
     // K-major  : global (rows_mn, K), K contiguous  -> dims {K, rows_mn}, box {64, tile_mn}
     // MN-major : global (K, rows_mn), rows contiguous -> dims {rows_mn, K}, box {64, 64}
     cuuint64_t dims[2], strides[1];
@@ -585,6 +585,35 @@ void encode_map(CUtensorMap* map, const bf16* ptr, int ld, int mn_major, long lo
     if (rc != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)rc));
 }
 
+// ---- tensor-map cache.  cuTensorMapEncodeTiled costs ~1-2 us on the host and a step re-issues the same few hundred
+// (pointer, shape, box) combinations (three encodes per GEMM launch); the per-step generic recurrence of
+// wide models is host-bound on them.  Direct-mapped, 1024 entries, keyed on every argument of the encode.
+struct MapKey {
+    const void* ptr; long long d0, d1, d2; long long s0, s1; int b0, b1, b2, kind;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s0 == o.s0 && s1 == o.s1 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 && kind == o.kind;
+    }
+};
+struct MapSlot { MapKey key; CUtensorMap map; bool valid = false; };
+MapSlot g_map_cache[1024];
+std::mutex g_map_mu;
+inline size_t map_hash(const MapKey& k) {
+    unsigned long long h = (unsigned long long)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
+    h ^= (unsigned long long)k.d0 * 0xC2B2AE3D27D4EB4Full + (unsigned long long)k.d1 * 0x165667B19E3779F9ull + (unsigned long long)k.s0 * 31 + k.kind * 7 + k.b1;
+    return (size_t)((h >> 20) & 1023);
+}
+template <class F>
+void cached_map(CUtensorMap* out, const MapKey& key, F&& encode) {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    MapSlot& sl = g_map_cache[map_hash(key)];
+    if (!(sl.valid && sl.key == key)) {
+        encode(&sl.map);
+        sl.key = key;
+        sl.valid = true;
+    }
+    *out = sl.map;
+}
+
 template <int A_MN, int B_MN>
 void launch(const CUtensorMap& ta, const CUtensorMap& tb, float* Cf, bf16* Ch, int ldc, int M, int N, int K, float alpha,
             const float* bias, int mode, int kbps, int splits, int vec_ok, cudaStream_t s) {
@@ -598,7 +627,7 @@ void launch(const CUtensorMap& ta, const CUtensorMap& tb, float* Cf, bf16* Ch, i
     COUNT_LAUNCH();
 }
 
-void encode_c_map(CUtensorMap* map, void* ptr, int is_bf16, int ldc, long long M, long long N) {
+void encode_c_map_raw(CUtensorMap* map, void* ptr, int is_bf16, int ldc, long long M, long long N) {
     // output (M, N) row-major; one epilogue warp stores a box of 32 rows x 128 bytes (128B swizzle)
     cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M}, strides[1] = {(cuuint64_t)ldc * (is_bf16 ? 2 : 4)};
     cuuint32_t box[2] = {is_bf16 ? 64u : 32u, 32u}, estr[2] = {1, 1};
@@ -606,6 +635,15 @@ void encode_c_map(CUtensorMap* map, void* ptr, int is_bf16, int ldc, long long M
                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled (C) failed with code " + std::to_string((int)rc));
+}
+
+void encode_map(CUtensorMap* map, const bf16* ptr, int ld, int mn_major, long long rows_mn, long long K, int tile_mn) {
+    const MapKey key{ptr, rows_mn, K, 0, ld, 0, tile_mn, mn_major, 0, 1};
+    cached_map(map, key, [&](CUtensorMap* m) { encode_map_raw(m, ptr, ld, mn_major, rows_mn, K, tile_mn); });
+}
+void encode_c_map(CUtensorMap* map, void* ptr, int is_bf16, int ldc, long long M, long long N) {
+    const MapKey key{ptr, M, N, 0, ldc, 0, is_bf16, 0, 0, 2};
+    cached_map(map, key, [&](CUtensorMap* m) { encode_c_map_raw(m, ptr, is_bf16, ldc, M, N); });
 }
 
 template <int A_MN, int B_MN>
@@ -634,6 +672,12 @@ void tma_encode_slice_rows_bf16(void* map_out, const bf16* base, int ld, long lo
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled (slice rows) failed with code " + std::to_string((int)rc));
+}
+
+// plain 2-D map over a K-major bf16 matrix (rows, ld), box {64 columns, box_rows}, 128-byte swizzle; cached
+void tma_encode_2d_bf16(void* map_out, const bf16* base, int ld, long long rows, int cols, int box_rows) {
+    if (!g_ready) throw std::runtime_error("TMA descriptors unavailable (gemm_tc_init)");
+    encode_map((CUtensorMap*)map_out, base, ld, 0, rows, cols, box_rows);
 }
 
 void gemm_tc_init(int device) {

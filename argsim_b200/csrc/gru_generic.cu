@@ -12,18 +12,26 @@
 
 namespace {
 
-__global__ void __launch_bounds__(256) k_gate_fwd(const float* __restrict__ gx, int ld_gx, const float* __restrict__ gh,
+// nzero > na: the launch also covers rows [na, nzero) and clears their (dead) gh entries; every gh entry read is cleared
+// too, so the next step's split-K GEMM can reduce-add into gh without a memset in between (one device op less per step)
+__global__ void __launch_bounds__(256) k_gate_fwd(const float* __restrict__ gx, int ld_gx, float* __restrict__ gh,
                                                   const float* __restrict__ bR, float* __restrict__ state,
                                                   float* __restrict__ hs_f, bf16* __restrict__ hs_h, int ld_hs,
-                                                  float* __restrict__ cache, int na, int H, bf16* __restrict__ state_h) {
+                                                  float* __restrict__ cache, int na, int H, bf16* __restrict__ state_h, int nzero) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= na * H) return;
+    if (idx >= max(na, nzero) * H) return;
     const int j = idx / H, u = idx - j * H;
+    float* q3 = gh + (long long)j * 3 * H;
+    if (j >= na) {
+        q3[u] = 0.f; q3[H + u] = 0.f; q3[2 * H + u] = 0.f;
+        return;
+    }
     const float* g = gx + (long long)j * ld_gx;
-    const float* q3 = gh + (long long)j * 3 * H;
-    const float r = 1.f / (1.f + expf(-(g[u] + q3[u] + bR[u])));
-    const float z = 1.f / (1.f + expf(-(g[H + u] + q3[H + u] + bR[H + u])));
-    const float q = q3[2 * H + u] + bR[2 * H + u];
+    const float ghr = q3[u], ghu = q3[H + u], ghn = q3[2 * H + u];
+    if (nzero) { q3[u] = 0.f; q3[H + u] = 0.f; q3[2 * H + u] = 0.f; }
+    const float r = 1.f / (1.f + expf(-(g[u] + ghr + bR[u])));
+    const float z = 1.f / (1.f + expf(-(g[H + u] + ghu + bR[H + u])));
+    const float q = ghn + bR[2 * H + u];
     const float n = tanhf(g[2 * H + u] + r * q);
     const float hp = state[(long long)j * H + u];
     const float h = (1.f - z) * n + z * hp;
@@ -102,6 +110,39 @@ size_t gru_generic_work_floats(int b, int H) { return (size_t)b * H * 5; }
 void gru_generic_fwd(const GruFwdArgs* dirs, int ndir, const SeqPlan& P, int H, float* work, cudaStream_t* streams) {
     fork_join_init();
     const size_t wstride = gru_generic_work_floats(P.b, H);
+    // bf16 mode: ONE fused kernel per time step for all directions (TMA ring + tcgen05 + gate epilogue, gru_tc.cu) instead of
+    // {memset, split-K GEMM, gate kernel} per direction (ARGSIM_GENERIC_UNFUSED=1 restores the latter)
+    static const bool unfused = getenv("ARGSIM_GENERIC_UNFUSED") != nullptr;
+    if (!unfused && ndir <= 2 && use_tc_gemm(dirs[0].R_h, H) && gru_step_supported(H, P.b)) {
+        cudaStream_t s = streams[0];
+        float* state[2];
+        bf16* sh[2][2];
+        for (int d = 0; d < ndir; ++d) {
+            const GruFwdArgs& a = dirs[d];
+            state[d] = work + d * wstride;
+            sh[d][0] = reinterpret_cast<bf16*>(state[d] + (size_t)P.b * 4 * H);      // two bf16 (b,H) buffers in the last b*H floats
+            sh[d][1] = sh[d][0] + (size_t)P.b * H;
+            if (a.h0 && !a.reverse) CUDA_CHECK(cudaMemcpyAsync(state[d], a.h0, sizeof(float) * P.b * H, cudaMemcpyDeviceToDevice, s));
+            else CUDA_CHECK(cudaMemsetAsync(state[d], 0, sizeof(float) * P.b * H, s));
+            k_state_to_bf16<<<cdiv((long long)P.b * H, 256), 256, 0, s>>>(state[d], sh[d][0], (long long)P.b * H);
+            COUNT_LAUNCH();
+            CUDA_CHECK(cudaMemcpyAsync(sh[d][1], sh[d][0], sizeof(bf16) * P.b * H, cudaMemcpyDeviceToDevice, s));
+        }
+        for (int k = 0; k < P.Tmax; ++k) {
+            int na[2] = {0, 0};
+            long long row0[2] = {0, 0};
+            bf16 *cur[2], *nxt[2];
+            for (int d = 0; d < ndir; ++d) {
+                const int t = dirs[d].reverse ? P.Tmax - 1 - k : k;
+                na[d] = P.nact[t];
+                row0[d] = P.off[t];
+                cur[d] = sh[d][k & 1];
+                nxt[d] = sh[d][(k + 1) & 1];
+            }
+            gru_step_fwd(dirs, ndir, na, row0, P.b, H, state, cur, nxt, s);
+        }
+        return;
+    }
     if (ndir > 1) {
         CUDA_CHECK(cudaEventRecord(g_ev[0], streams[0]));
         for (int d = 1; d < ndir; ++d) CUDA_CHECK(cudaStreamWaitEvent(streams[d], g_ev[0], 0));
@@ -116,19 +157,27 @@ void gru_generic_fwd(const GruFwdArgs* dirs, int ndir, const SeqPlan& P, int H, 
             CUDA_CHECK(cudaMemcpyAsync(state, a.h0, sizeof(float) * P.b * H, cudaMemcpyDeviceToDevice, s));
         else
             CUDA_CHECK(cudaMemsetAsync(state, 0, sizeof(float) * P.b * H, s));
+        // tcgen05 path with a batch that fits one 128-row tile: the GEMM covers all P.b rows with constant shapes (cached tensor
+        // maps) and reduce-adds into a gh that the gate kernel clears behind itself
+        const bool selfclear = state_h != nullptr && P.b <= 128;
         if (state_h) {
             k_state_to_bf16<<<cdiv((long long)P.b * H, 256), 256, 0, s>>>(state, state_h, (long long)P.b * H);
             COUNT_LAUNCH();
         }
+        if (selfclear) CUDA_CHECK(cudaMemsetAsync(gh, 0, sizeof(float) * P.b * 3 * H, s));
         for (int k = 0; k < P.Tmax; ++k) {
             const int t = a.reverse ? P.Tmax - 1 - k : k;
             const int na = P.nact[t];
             const long long r0 = P.off[t];
-            if (state_h) gemm_tc(state_h, H, 0, a.R_h, H, 0, gh, nullptr, 3 * H, na, 3 * H, H, 1.f, nullptr, 0, s);
+            // all P.b state rows every step (rows >= na are dead and ignored by the gate kernel): an M = 64 product fills the same
+            // 128-row MMA tile as M = na, and constant shapes keep the three tensor maps in gemm_tc's cache
+            if (selfclear) gemm_tc(state_h, H, 0, a.R_h, H, 0, gh, nullptr, 3 * H, P.b, 3 * H, H, 1.f, nullptr, /*accumulate*/ 1, s);
+            else if (state_h) gemm_tc(state_h, H, 0, a.R_h, H, 0, gh, nullptr, 3 * H, na, 3 * H, H, 1.f, nullptr, 0, s);
             else gemm_simt(state, H, 0, a.R_f, H, 0, gh, 3 * H, na, 3 * H, H, 1.f, nullptr, 0, nullptr, s);
-            k_gate_fwd<<<cdiv((long long)na * H, 256), 256, 0, s>>>(
+            k_gate_fwd<<<cdiv((long long)(selfclear ? P.b : na) * H, 256), 256, 0, s>>>(
                 a.gx + r0 * a.ld_gx, a.ld_gx, gh, a.bR, state, a.hs_f ? a.hs_f + r0 * a.ld_hs : nullptr,
-                a.hs_h ? a.hs_h + r0 * a.ld_hs : nullptr, a.ld_hs, a.cache ? a.cache + r0 * 4 * H : nullptr, na, H, state_h);
+                a.hs_h ? a.hs_h + r0 * a.ld_hs : nullptr, a.ld_hs, a.cache ? a.cache + r0 * 4 * H : nullptr, na, H, state_h,
+                selfclear ? P.b : 0);
             COUNT_LAUNCH();
         }
     }
@@ -199,6 +248,6 @@ void gru_generic_bwd(const GruBwdArgs* dirs, int ndir, const SeqPlan& P, int H, 
 void gru_generic_cell(const float* gx, int ld_gx, const float* R, const float* bR, float* state, float* gh_work, int nb,
                       int H, cudaStream_t s) {
     gemm_simt(state, H, 0, R, H, 0, gh_work, 3 * H, nb, 3 * H, H, 1.f, nullptr, 0, nullptr, s);
-    k_gate_fwd<<<cdiv((long long)nb * H, 256), 256, 0, s>>>(gx, ld_gx, gh_work, bR, state, nullptr, nullptr, H, nullptr, nb, H, nullptr);
+    k_gate_fwd<<<cdiv((long long)nb * H, 256), 256, 0, s>>>(gx, ld_gx, gh_work, bR, state, nullptr, nullptr, H, nullptr, nb, H, nullptr, 0);
     COUNT_LAUNCH();
 }

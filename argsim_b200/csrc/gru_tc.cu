@@ -1421,6 +1421,196 @@ __global__ void __launch_bounds__(NTH, 1) k_gru_tc_bwd(const __grid_constant__ T
 }
 
 // =========================================================================================
+// one GRU time step for hidden sizes whose recurrent matrix does not fit on chip (H != 512, e.g. BASELINE configs[4],
+// H = 2048: R is 25 MB per direction-layer).  The generic path spent three device operations per step (memset, split-K
+// GEMM h.R^T with a TMA reduce-add epilogue, gate kernel); this kernel is the step: CTA c owns hidden units
+// [32c, 32c+32) = 96 rows of R, streams them and the bf16 state of up to 64 rows through a 4-stage TMA ring (A = R_own
+// as three 32-row boxes per k-block, B = h_prev), accumulates D[128 x 64] in tensor memory (SS form, M = 128, N = 64) and
+// finishes the cell in the epilogue exactly like the persistent kernels (TMEM lane quadrant = gate, gates of a unit meet
+// in shared memory).  No inter-CTA exchange: the launch boundary is the exchange; the bf16 state ping-pongs between two
+// buffers because the other CTAs still read the old one.  grid = (H/32, row chunks of 64, directions).
+// =========================================================================================
+struct StepDirP {
+    const float* gx; const float* bR; float* state_f; bf16* state_h_out; float* hs_f; bf16* hs_h; float* cache;
+    int ld_gx, ld_hs, na;
+};
+struct StepP {
+    StepDirP dir[2];
+    int H;
+};
+constexpr int STEP_STAGES = 3;         // 3 x 24 KB + the gate tile: two CTAs fit an SM, so the NEXT step's CTAs (programmatic dependent
+                                      // launch) become resident and prefetch their R blocks while this step still runs; 4 and 8 stages
+                                      // measured the same step time (the stream is L2-bandwidth-, not latency-bound)
+constexpr int STEP_A_BYTES = 128 * 128, STEP_B_BYTES = 64 * 128, STEP_STAGE_BYTES = STEP_A_BYTES + STEP_B_BYTES;
+constexpr int STEP_NTH = 10 * 32;      // warp 0 producer, warp 1 MMA, warps 2..9 gate
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_mma_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__global__ void __launch_bounds__(STEP_NTH, 1) k_gru_step_fwd(const __grid_constant__ StepP P, const __grid_constant__ CUtensorMap tmR0,
+                                                              const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmS0,
+                                                              const __grid_constant__ CUtensorMap tmS1) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int c = blockIdx.x, chunk = blockIdx.y, d = blockIdx.z;
+    const StepDirP& A = P.dir[d];
+    const int r0 = chunk * 64;
+    if (r0 >= A.na) return;                      // no live row in this chunk of this direction
+    const int nrows = min(64, A.na - r0);
+    const CUtensorMap* tmR = d ? &tmR1 : &tmR0;
+    const CUtensorMap* tmS = d ? &tmS1 : &tmS0;
+    const uint32_t sbase = (smem_u32(sm_raw) + 1023u) & ~1023u;
+    unsigned char* const sm = sm_raw + (sbase - smem_u32(sm_raw));
+    // [ring: 4 x (A 16 KB + B 8 KB)][G: 3*64*32 f32][barriers: full[4], empty[4], dfull][slot]
+    float* G = reinterpret_cast<float*>(sm + STEP_STAGES * STEP_STAGE_BYTES);
+    const uint32_t bars = sbase + STEP_STAGES * STEP_STAGE_BYTES + 3 * 64 * UN * 4;
+    auto full = [&](int st) { return bars + 8u * (uint32_t)st; };
+    auto empty = [&](int st) { return bars + 8u * (uint32_t)(STEP_STAGES + st); };
+    const uint32_t dfull = bars + 8u * (2 * STEP_STAGES);
+    const uint32_t tslot = dfull + 8;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int H = P.H, nkb = H / 64;
+    if (tid == 0) {
+        for (int i = 0; i < STEP_STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+        mbar_init(dfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(tmR) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(tmS) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tslot), "n"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot) : "memory");
+
+    // Programmatic dependent launch: the next step's grid may start now (its prologue and its first R blocks do not depend on this
+    // step); everything that does -- the state it reads, the state buffer it overwrites -- comes after griddepcontrol.wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (warp == 0) {
+        // ---- producer: R_own (three gate blocks of 32 rows) and the state rows of the chunk, one k-block per stage
+        const bool leader = elect_one();
+        const int npre = min(nkb, STEP_STAGES);
+        if (leader) {   // the first stages' R blocks: independent of the previous step
+            for (int i = 0; i < npre; ++i) {
+                const uint32_t sa = sbase + (uint32_t)(i * STEP_STAGE_BYTES);
+                mbar_expect_tx(full(i), (uint32_t)(3 * 32 * 128 + 64 * 128));
+#pragma unroll
+                for (int g = 0; g < 3; ++g) tma_load_2d(sa + (uint32_t)(g * 32 * 128), tmR, 64 * i, g * H + UN * c, full(i));
+            }
+        }
+        __syncwarp();
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        for (int i = 0; i < nkb; ++i) {
+            const int st = i % STEP_STAGES;
+            const uint32_t ph = (uint32_t)(i / STEP_STAGES) & 1u;
+            if (i >= npre) mbar_wait(empty(st), ph ^ 1u);
+            if (leader) {
+                const uint32_t sa = sbase + (uint32_t)(st * STEP_STAGE_BYTES), sb = sa + STEP_A_BYTES;
+                if (i >= npre) {
+                    mbar_expect_tx(full(st), (uint32_t)(3 * 32 * 128 + 64 * 128));
+#pragma unroll
+                    for (int g = 0; g < 3; ++g) tma_load_2d(sa + (uint32_t)(g * 32 * 128), tmR, 64 * i, g * H + UN * c, full(st));
+                }
+                tma_load_2d(sb, tmS, 64 * i, r0, full(st));
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ---- MMA: D[128 x 64] += A[128 x 16] . B[64 x 16]^T, four per k-block (rows 96..127 of A are never loaded: their
+        // accumulator lanes are garbage nobody reads)
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc(64);
+        for (int i = 0; i < nkb; ++i) {
+            const int st = i % STEP_STAGES;
+            const uint32_t ph = (uint32_t)(i / STEP_STAGES) & 1u;
+            mbar_wait(full(st), ph);
+            tc_fence_after();
+            if (leader) {
+                const uint32_t sa = sbase + (uint32_t)(st * STEP_STAGE_BYTES), sb = sa + STEP_A_BYTES;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) tc_mma_ss(tmem, make_desc_k(sa + j * 32), make_desc_k(sb + j * 32), idesc, (i > 0 || j > 0) ? 1u : 0u);
+                tc_commit(empty(st));
+                if (i == nkb - 1) tc_commit(dfull);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---- gate warps: gw = 0..7, lane quadrant = gate, two column halves
+        const int gw = warp - 2, quad = warp & 3, half = gw >> 2;
+        const int col = UN * c + lane;
+        const float bRr = A.bR[col], bRu = A.bR[H + col], bRn = A.bR[2 * H + col];
+        float gxv[8][3], hpv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int n = gw + 8 * e;
+            gxv[e][0] = gxv[e][1] = gxv[e][2] = 0.f; hpv[e] = 0.f;
+            if (n < nrows) {
+                const float* gp = A.gx + (size_t)(r0 + n) * A.ld_gx + col;
+                gxv[e][0] = ld_f32(gp); gxv[e][1] = ld_f32(gp + H); gxv[e][2] = ld_f32(gp + 2 * H);
+            }
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");     // the previous step's state is complete (and nobody reads its input any more)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int n = gw + 8 * e;
+            if (n < nrows) hpv[e] = ld_f32(A.state_f + (size_t)(r0 + n) * H + col);
+        }
+        if (quad < 3) {
+            mbar_wait(dfull, 0);
+            tc_fence_after();
+            const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 32);
+            uint32_t r[32];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tc_ld8(ta + 8 * i, r + 8 * i);
+            tc_wait_ld();
+            tc_fence_before();
+            float* gp = G + ((size_t)quad * 64 + half * 32) * UN + lane;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) gp[i * UN] = __uint_as_float(r[i]);
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int n = gw + 8 * e;
+            if (n < nrows) {
+                const float s0 = G[(0 * 64 + n) * UN + lane], s1 = G[(1 * 64 + n) * UN + lane], s2 = G[(2 * 64 + n) * UN + lane];
+                // same arithmetic as the generic gate kernel (expf / tanhf): the validation paths compare against it
+                const float r = 1.f / (1.f + expf(-(gxv[e][0] + s0 + bRr)));
+                const float z = 1.f / (1.f + expf(-(gxv[e][1] + s1 + bRu)));
+                const float qq = s2 + bRn;
+                const float nv = tanhf(gxv[e][2] + r * qq);
+                const float h = (1.f - z) * nv + z * hpv[e];
+                const size_t row = (size_t)(r0 + n);
+                A.state_f[row * H + col] = h;
+                const __nv_bfloat16 hb = __float2bfloat16(h);
+                A.state_h_out[row * H + col] = hb;
+                if (A.hs_h) A.hs_h[row * A.ld_hs + col] = hb;
+                if (A.hs_f) A.hs_f[row * A.ld_hs + col] = h;
+                if (A.cache) {
+                    float* cp = A.cache + row * 4 * H + col;
+                    cp[0] = r; cp[H] = z; cp[2 * H] = nv; cp[3 * H] = qq;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(64) : "memory");
+}
+
+// =========================================================================================
 // unit test of the TS-form building blocks: D[128 x N] = A[128 x K] . B[N x K]^T with A written to tensor memory by
 // tcgen05.st, B staged in swizzled shared memory by plain stores, K = 64 * kblocks
 // =========================================================================================
@@ -1800,6 +1990,48 @@ void gru_tc_bwd(GruTcCtx* c, const GruBwdArgs* dirs, int ndir, const SeqPlan& Pl
         for (int i = 0; i < 8; ++i) fprintf(stderr, " p%d=%.0f", i, avg[i] / Tseg);
         fprintf(stderr, "\n");
     }
+}
+
+// ---- per-step fused GRU forward for hidden sizes without a persistent kernel (see k_gru_step_fwd) -------------------------
+void tma_encode_2d_bf16(void* map_out, const bf16* base, int ld, long long rows, int cols, int box_rows);
+bool gru_step_supported(int H, int b) { return H % 64 == 0 && H >= 64 && b >= 1; }
+// state_f: (b,H) fp32 per direction (in/out); state_h[2]: (b,H) bf16 ping-pong per direction (state_h[cur] holds h_prev)
+void gru_step_fwd(const GruFwdArgs* dirs, int ndir, const int* na, const long long* row0, int b, int H, float* const* state_f,
+                  bf16* const* state_h_cur, bf16* const* state_h_next, cudaStream_t s) {
+    static bool configured = false;
+    const size_t smem = 1024 + (size_t)STEP_STAGES * STEP_STAGE_BYTES + 3 * 64 * UN * 4 + (2 * STEP_STAGES + 1) * 8 + 16;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_gru_step_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    StepP P;
+    P.H = H;
+    CUtensorMap tmR[2], tmS[2];
+    int na_max = 0;
+    for (int d = 0; d < 2; ++d) {
+        const int dd = d < ndir ? d : 0;
+        const GruFwdArgs& a = dirs[dd];
+        const long long r0 = row0[dd];
+        P.dir[d] = StepDirP{a.gx + r0 * a.ld_gx, a.bR, state_f[dd], state_h_next[dd], a.hs_f ? a.hs_f + r0 * a.ld_hs : nullptr,
+                            a.hs_h ? a.hs_h + r0 * a.ld_hs : nullptr, a.cache ? a.cache + r0 * 4 * H : nullptr, a.ld_gx, a.ld_hs,
+                            d < ndir ? na[dd] : 0};
+        tma_encode_2d_bf16(&tmR[d], a.R_h, H, 3LL * H, H, 32);
+        tma_encode_2d_bf16(&tmS[d], state_h_cur[dd], H, b, H, 64);
+        if (d < ndir) na_max = std::max(na_max, na[dd]);
+    }
+    if (na_max <= 0) return;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(H / UN, (na_max + 63) / 64, ndir);
+    cfg.blockDim = dim3(STEP_NTH);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gru_step_fwd, P, tmR[0], tmR[1], tmS[0], tmS[1]));
+    COUNT_LAUNCH();
 }
 
 // D(128,N) = A(128,K) . B(N,K)^T through tensor memory (TS form); device pointers, bf16 operands, fp32 out

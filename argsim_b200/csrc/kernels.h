@@ -124,6 +124,10 @@ bool gru_tc_fits(const GruTcCtx*, int ndir, int b);
 bool gru_tc_throughput(const GruTcCtx*, int ndir, int b);   // rows per slice large enough for the TMA-fed forward kernel
 void gru_tc_fwd(GruTcCtx*, const GruFwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
                 int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0, int rows_per_slice = 0, int pad = 0);
+// one fused time step (TMA ring + tcgen05 + gate epilogue) for hidden sizes without a persistent kernel (gru_tc.cu)
+bool gru_step_supported(int H, int b);
+void gru_step_fwd(const GruFwdArgs* dirs, int ndir, const int* na, const long long* row0, int b, int H, float* const* state_f,
+                  bf16* const* state_h_cur, bf16* const* state_h_next, cudaStream_t s);
 void gru_tc_bwd(GruTcCtx*, const GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
                 int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0, int rows_per_slice = 0, int pad = 0);
 // returns the cycles from the first MMA issue to the completion of the last (K/16 MMAs round robin over nacc accumulators)

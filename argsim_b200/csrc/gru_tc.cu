@@ -1456,6 +1456,21 @@ __device__ __forceinline__ void tc_mma_ss(uint32_t tmem_d, uint64_t da, uint64_t
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// MC = 8: clusters of 8 CTAs along the unit dimension share the state tile -- CTA r of a cluster loads rows [8r, 8r+8) of every
+// k-block and the TMA engine multicasts them into all 8 CTAs (every CTA still streams its own R rows): 40 % less L2 traffic.
+// A stage is free again when the MMA warps of ALL 8 CTAs have committed it (multicast commit onto everybody's empty barrier).
+template <int MC>
 __global__ void __launch_bounds__(STEP_NTH, 1) k_gru_step_fwd(const __grid_constant__ StepP P, const __grid_constant__ CUtensorMap tmR0,
                                                               const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmS0,
                                                               const __grid_constant__ CUtensorMap tmS1) {
@@ -1479,7 +1494,7 @@ __global__ void __launch_bounds__(STEP_NTH, 1) k_gru_step_fwd(const __grid_const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = P.H, nkb = H / 64;
     if (tid == 0) {
-        for (int i = 0; i < STEP_STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), 1); }
+        for (int i = 0; i < STEP_STAGES; ++i) { mbar_init(full(i), 1); mbar_init(empty(i), MC); }
         mbar_init(dfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(tmR) : "memory");
@@ -1494,6 +1509,11 @@ __global__ void __launch_bounds__(STEP_NTH, 1) k_gru_step_fwd(const __grid_const
     tc_fence_after();
     uint32_t tmem;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem) : "r"(tslot) : "memory");
+    uint32_t crank = 0;
+    if (MC > 1) {
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+        cluster_sync_all();     // every CTA's barriers are initialised before anybody multicasts into it
+    }
 
     // Programmatic dependent launch: the next step's grid may start now (its prologue and its first R blocks do not depend on this
     // step); everything that does -- the state it reads, the state buffer it overwrites -- comes after griddepcontrol.wait
@@ -1523,7 +1543,8 @@ __global__ void __launch_bounds__(STEP_NTH, 1) k_gru_step_fwd(const __grid_const
 #pragma unroll
                     for (int g = 0; g < 3; ++g) tma_load_2d(sa + (uint32_t)(g * 32 * 128), tmR, 64 * i, g * H + UN * c, full(st));
                 }
-                tma_load_2d(sb, tmS, 64 * i, r0, full(st));
+                if (MC > 1) tma_load_2d_mc(sb + crank * 1024u, tmS, 64 * i, r0 + 8 * (int)crank, full(st), (uint16_t)((1u << MC) - 1u));
+                else tma_load_2d(sb, tmS, 64 * i, r0, full(st));
             }
             __syncwarp();
         }
@@ -1541,7 +1562,8 @@ __global__ void __launch_bounds__(STEP_NTH, 1) k_gru_step_fwd(const __grid_const
                 const uint32_t sa = sbase + (uint32_t)(st * STEP_STAGE_BYTES), sb = sa + STEP_A_BYTES;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) tc_mma_ss(tmem, make_desc_k(sa + j * 32), make_desc_k(sb + j * 32), idesc, (i > 0 || j > 0) ? 1u : 0u);
-                tc_commit(empty(st));
+                if (MC > 1) tc_commit_mc(empty(st), (uint16_t)((1u << MC) - 1u));
+                else tc_commit(empty(st));
                 if (i == nkb - 1) tc_commit(dfull);
             }
             __syncwarp();
@@ -1607,6 +1629,7 @@ __global__ void __launch_bounds__(STEP_NTH, 1) k_gru_step_fwd(const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (MC > 1) cluster_sync_all();     // nobody leaves while a peer may still arrive on its barriers
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(64) : "memory");
 }
 
@@ -1999,11 +2022,16 @@ bool gru_step_supported(int H, int b) { return H % 64 == 0 && H >= 64 && b >= 1;
 void gru_step_fwd(const GruFwdArgs* dirs, int ndir, const int* na, const long long* row0, int b, int H, float* const* state_f,
                   bf16* const* state_h_cur, bf16* const* state_h_next, cudaStream_t s) {
     static bool configured = false;
+    // measured on the scaled config: multicast 146.7 ms per step, plain 144.0 (cluster syncs and lock-step stages cost more than
+    // the 40 % of L2 bytes they save: the stream is bound by every CTA's own R rows) -> off unless ARGSIM_STEP_MULTICAST=1
+    static const bool no_mc = getenv("ARGSIM_STEP_MULTICAST") == nullptr;
     const size_t smem = 1024 + (size_t)STEP_STAGES * STEP_STAGE_BYTES + 3 * 64 * UN * 4 + (2 * STEP_STAGES + 1) * 8 + 16;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_gru_step_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_gru_step_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_gru_step_fwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
+    const bool mc = !no_mc && (H / UN) % 8 == 0;
     StepP P;
     P.H = H;
     CUtensorMap tmR[2], tmS[2];
@@ -2016,7 +2044,7 @@ void gru_step_fwd(const GruFwdArgs* dirs, int ndir, const int* na, const long lo
                             a.hs_h ? a.hs_h + r0 * a.ld_hs : nullptr, a.cache ? a.cache + r0 * 4 * H : nullptr, a.ld_gx, a.ld_hs,
                             d < ndir ? na[dd] : 0};
         tma_encode_2d_bf16(&tmR[d], a.R_h, H, 3LL * H, H, 32);
-        tma_encode_2d_bf16(&tmS[d], state_h_cur[dd], H, b, H, 64);
+        tma_encode_2d_bf16(&tmS[d], state_h_cur[dd], H, b, H, mc ? 8 : 64);
         if (d < ndir) na_max = std::max(na_max, na[dd]);
     }
     if (na_max <= 0) return;
@@ -2025,12 +2053,15 @@ void gru_step_fwd(const GruFwdArgs* dirs, int ndir, const int* na, const long lo
     cfg.blockDim = dim3(STEP_NTH);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = 8; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gru_step_fwd, P, tmR[0], tmR[1], tmS[0], tmS[1]));
+    cfg.numAttrs = mc ? 2 : 1;
+    if (mc) CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gru_step_fwd<8>, P, tmR[0], tmR[1], tmS[0], tmS[1]));
+    else CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gru_step_fwd<1>, P, tmR[0], tmR[1], tmS[0], tmS[1]));
     COUNT_LAUNCH();
 }
 

@@ -31,8 +31,7 @@ void Engine::copy_sync(void* dst, const void* src, size_t bytes, cudaMemcpyKind 
 Engine::Engine(const argsim_config& c) : cfg(c) {
     V = c.dim_tgt; D = c.dim_emb; R = c.dim_rep; L = c.rnn_layers; H = D;
     if (V <= 0 || D <= 0 || R <= 0 || L <= 0) throw std::runtime_error("bad model dimensions");
-    if (c.attentive)
-        throw std::runtime_error("attentive=true is not implemented (unused by config.json; the reference marks it 'todo fixme', src/model.py:136)");
+    attentive = c.attentive != 0;   // src/model.py:136-145 ('todo fixme' there; the repaired form is stated in DESIGN.md section 6)
     enc_kind = (c.bidirectional && c.bidir_stacked) ? 0 : (c.bidirectional ? 1 : 2);
     EH = (enc_kind == 2) ? H : 2 * H;
     tied = c.logit_use_embed != 0;   // false: separate (D,V) projection + bias (src/model.py:167-168)
@@ -103,6 +102,14 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     add("latent/ex/kernel", R, D); add("latent/ex/bias", D, 0);
     add("latent/mu/kernel", EH, R); add("latent/mu/bias", R, 0);
     add("latent/lv/kernel", EH, R); add("latent/lv/bias", R, 0);
+    if (attentive) {   // same all-reduce bucket as the latent affines
+        if (EH % ATT_HEADS) throw std::runtime_error("attentive: the encoder width must be divisible by 8 heads");
+        add("encode/cata/LayerNorm/gamma", EH, 0); add("encode/cata/LayerNorm/beta", EH, 0);
+        for (const char* nm : {"p", "q", "k", "v"}) {
+            add(std::string("encode/cata/") + nm + "/kernel", EH, EH);
+            add(std::string("encode/cata/") + nm + "/bias", EH, 0);
+        }
+    }
     if (enc_kind != 0) {   // independent L-layer stack(s): layers in backward-completion order, directions adjacent
         for (int j = L - 1; j >= 0; --j)
             for (int d = 0; d < (enc_kind == 1 ? 2 : 1); ++d) {
@@ -202,6 +209,7 @@ void Engine::init_params(uint64_t seed_) {
     };
     for (const ParamInfo& pi : params) {
         float* dst = host.data() + pi.off;
+        if (pi.name == "encode/cata/LayerNorm/gamma") { for (size_t i = 0; i < pi.n; ++i) dst[i] = 1.f; continue; }   // layer_norm scale
         if (pi.rank == 1) continue;  // biases zero
         if (pi.name == "embed/embedding") {
             uni(dst, pi.n, sqrtf(6.0f / ((float)V / (float)D + 1.0f)));
@@ -666,6 +674,26 @@ void Engine::program(int mode, bool apply_update) {
     // ---------------- final state + latent (model.py:133-156)
     Mat henc = both(b, EH);
     RUN(launch_row_gather(encX[L].f, encX[L].h, EH, dp.enc_last, henc.f, henc.h, EH, nullptr, b, EH, s));
+    // attentive (model.py:136-145): h <- layer_norm(h + p(attend(q(h), k(hs), v(hs)))) over the sequence's own steps
+    struct { Mat h0, q, K, Vv, y; float *prob = nullptr, *xhat = nullptr, *rstd = nullptr; } att;
+    auto cata = [&](const char* nm, const char* what) { return std::string("encode/cata/") + nm + "/" + what; };
+    if (attentive) {
+        const Mat& HSx = encX[L];
+        att.h0 = henc;
+        att.q = f32(b, EH); att.K = f32(S, EH); att.Vv = f32(S, EH); att.y = both(b, EH);
+        att.prob = (float*)arena.alloc(sizeof(float) * S * ATT_HEADS);
+        att.xhat = (float*)arena.alloc(sizeof(float) * b * EH);
+        att.rstd = (float*)arena.alloc(sizeof(float) * b);
+        gemm(henc, 0, pmat(cata("q", "kernel")), 1, att.q, b, EH, EH, 1.f, p + pinfo(cata("q", "bias")).off, 0);
+        gemm(HSx, 0, pmat(cata("k", "kernel")), 1, att.K, S, EH, EH, 1.f, p + pinfo(cata("k", "bias")).off, 0);
+        gemm(HSx, 0, pmat(cata("v", "kernel")), 1, att.Vv, S, EH, EH, 1.f, p + pinfo(cata("v", "bias")).off, 0);
+        RUN(launch_attn_fwd(att.q.f, att.K.f, att.Vv.f, b, EH, ATT_HEADS, dp.enc_off, E.Tmax, dp.enc_last, att.prob, att.y.f, att.y.h, s));
+        Mat pp = f32(b, EH), hn = both(b, EH);
+        gemm(att.y, 0, pmat(cata("p", "kernel")), 1, pp, b, EH, EH, 1.f, p + pinfo(cata("p", "bias")).off, 0);
+        RUN(launch_resid_ln_fwd(henc.f, pp.f, p + pinfo("encode/cata/LayerNorm/gamma").off, p + pinfo("encode/cata/LayerNorm/beta").off,
+                                b, EH, att.xhat, att.rstd, hn.f, hn.h, s));
+        henc = hn;
+    }
     Mat mulv = f32(b, 2 * R);
     gemm(henc, 0, pmat("latent/mu/kernel"), 1, mulv.colslice(0, R), b, R, EH, 1.f, p + pinfo("latent/mu/bias").off, 0);
     outp = Out();
@@ -1007,9 +1035,10 @@ void Engine::program(int mode, bool apply_update) {
     Mat dmulv = both(b, 2 * R);
     RUN(launch_latent_bwd(dz.f, mulv.f, eps_used, b, R, 1, anneal / ((float)b_glob * (float)R), dmulv.f, dmulv.h, s));
     Mat dhenc = f32(b, EH);
+    Mat att_dK, att_dV;   // attentive: gradients of the key / value rows, folded into d hs below
     {   // the three affines' weight / bias gradients: behind the chain (side stream) when it is in use
-        cudaStream_t qw = side ? swg : nullptr;
-        if (side) side_after_main();
+        cudaStream_t qw = (side && !attentive) ? swg : nullptr;
+        if (qw) side_after_main();
         gemm(z, 1, dhx, 1, gmat("latent/ex/kernel"), R, D, b, 1.f, nullptr, 1, qw);
         colsum(dhx, b, D, gptr("latent/ex/bias"), 0, qw);
         gemm(henc, 1, dmulv.colslice(0, R), 1, gmat("latent/mu/kernel"), EH, R, b, 1.f, nullptr, 1, qw);
@@ -1019,7 +1048,30 @@ void Engine::program(int mode, bool apply_update) {
         colsum(a_lv, b, R, gptr("latent/lv/bias"), 0, qw);
         gemm(dmulv.colslice(0, R), 0, pmat("latent/mu/kernel"), 0, dhenc, b, EH, R, 1.f, nullptr, 0);
         gemm(dmulv.colslice(R, R), 0, pmat("latent/lv/kernel"), 0, dhenc, b, EH, R, 1.f, nullptr, 1);
-        const size_t end = pinfo("latent/lv/bias").off + align_up(R, 64);
+        size_t end = pinfo("latent/lv/bias").off + align_up(R, 64);
+        if (attentive) {   // back through the layer norm, p, the softmax and q / k / v (all on the main stream)
+            const Mat& HSx = encX[L];
+            Mat dx = both(b, EH), dgr = f32(b, EH), dyy = f32(b, EH), dq = both(b, EH);
+            att_dK = both(S, EH); att_dV = both(S, EH);
+            RUN(launch_ln_bwd(dhenc.f, att.xhat, att.rstd, p + pinfo("encode/cata/LayerNorm/gamma").off, b, EH, dx.f, dx.h, dgr.f, s));
+            colsum(dgr, b, EH, gptr("encode/cata/LayerNorm/gamma"), 0);
+            colsum(dhenc, b, EH, gptr("encode/cata/LayerNorm/beta"), 0);
+            gemm(att.y, 1, dx, 1, gmat(cata("p", "kernel")), EH, EH, b, 1.f, nullptr, 1);
+            colsum(Mat(dx.f, nullptr, b, EH, EH), b, EH, gptr(cata("p", "bias")), 0);
+            gemm(dx, 0, pmat(cata("p", "kernel")), 0, dyy, b, EH, EH, 1.f, nullptr, 0);
+            RUN(launch_attn_bwd(dyy.f, att.q.f, att.K.f, att.Vv.f, att.prob, b, EH, ATT_HEADS, dp.enc_off, E.Tmax, dp.enc_last,
+                                dq.f, dq.h, att_dK.f, att_dK.h, att_dV.f, att_dV.h, s));
+            gemm(att.h0, 1, dq, 1, gmat(cata("q", "kernel")), EH, EH, b, 1.f, nullptr, 1);
+            colsum(Mat(dq.f, nullptr, b, EH, EH), b, EH, gptr(cata("q", "bias")), 0);
+            gemm(HSx, 1, att_dK, 1, gmat(cata("k", "kernel")), EH, EH, S, 1.f, nullptr, 1);
+            colsum(Mat(att_dK.f, nullptr, S, EH, EH), S, EH, gptr(cata("k", "bias")), 0);
+            gemm(HSx, 1, att_dV, 1, gmat(cata("v", "kernel")), EH, EH, S, 1.f, nullptr, 1);
+            colsum(Mat(att_dV.f, nullptr, S, EH, EH), S, EH, gptr(cata("v", "bias")), 0);
+            // d h (the gathered final state) = residual branch + query branch
+            gemm(dq, 0, pmat(cata("q", "kernel")), 0, Mat(dx.f, nullptr, b, EH, EH), b, EH, EH, 1.f, nullptr, 1);
+            dhenc = Mat(dx.f, nullptr, b, EH, EH);
+            end = pinfo(cata("v", "bias")).off + align_up(EH, 64);
+        }
         allreduce_bucket(bucket_lo, end, qw);
         bucket_lo = end;
     }
@@ -1029,6 +1081,12 @@ void Engine::program(int mode, bool apply_update) {
     Mat dHS = f32(S, 2 * H), dHSn = f32(S, 2 * H);
     RUN(CUDA_CHECK(cudaMemsetAsync(dHS.f, 0, sizeof(float) * S * 2 * H, s)));
     if (enc_kind == 0) RUN(launch_row_scatter(dhenc.f, 2 * H, dHS.f, 2 * H, dp.enc_last, b, 2 * H, 0, s));
+    auto attn_into = [&](const Mat& dTopRows) {   // every step's output also fed a key and a value
+        if (!attentive) return;
+        gemm(att_dK, 0, pmat(cata("k", "kernel")), 0, dTopRows, S, EH, EH, 1.f, nullptr, 1);
+        gemm(att_dV, 0, pmat(cata("v", "kernel")), 0, dTopRows, S, EH, EH, 1.f, nullptr, 1);
+    };
+    if (enc_kind == 0) attn_into(dHS);
     size_t adam_split = 0;   // parameters [0, adam_split) were updated early on the side stream
     // Adam, TF-1 form (model.py:189): lr_t = lr sqrt(1 - b2^t) / (1 - b1^t), epsilon outside the bias-corrected root
     auto adam_range = [&](size_t lo, size_t hi, cudaStream_t q, const char* timer) {
@@ -1050,6 +1108,7 @@ void Engine::program(int mode, bool apply_update) {
         // BPTT through the independent stack(s): the top layer reads its slice of d hs, lower layers their own dX
         Mat dTop(dHS.f, nullptr, S, EH, EH);
         RUN(launch_row_scatter(dhenc.f, EH, dTop.f, EH, dp.enc_last, b, EH, 0, s));
+        attn_into(dTop);
         Mat dcur[2], dnext[2];
         for (int d = 0; d < nd_enc; ++d) { dcur[d] = f32(S, H); dnext[d] = f32(S, H); }
         Mat dX0(dHSn.f, nullptr, S, D, D);

@@ -590,3 +590,206 @@ void launch_fill(float* p, long long n, float v, cudaStream_t s) {
     k_fill<<<blocks, 256, 0, s>>>(p, n, v);
     COUNT_LAUNCH();
 }
+
+// ------------------------------------------------------------------------------------------
+// attentive=true (src/model.py:18-45,136-145 with the reshape at :36 and the feature axis of the affines repaired):
+// one query per sequence (its final state) attends over that sequence's own top-layer outputs, 8 heads, then
+// h <- layer_norm(h + p(attend)).  K and V live in the packed time-major row layout of the encoder (row of step t of
+// sorted sequence j = off[t] + j), so the mask of the reference (log of 0/1 over padding) is the loop bound here.
+// ------------------------------------------------------------------------------------------
+namespace {
+constexpr int ATT_NT = 128;
+__device__ __forceinline__ float block_sum_att(float v, float* red) {   // ATT_NT threads; red: 4 floats + 1
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return red[0] + red[1] + red[2] + red[3];
+}
+__device__ __forceinline__ float block_max_att(float v, float* red) {
+    v = warp_max(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+}
+// the sequence whose last step sits in packed row `last`: number of steps and sorted position
+__device__ __forceinline__ void seq_of_last_row(const int* __restrict__ off, int Tmax, int last, int* len, int* j) {
+    int lo = 0, hi = Tmax - 1;   // largest t with off[t] <= last
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (off[mid] <= last) lo = mid; else hi = mid - 1;
+    }
+    *len = lo + 1;
+    *j = last - off[lo];
+}
+}  // namespace
+
+// grid (b, heads): scores over the sequence's own steps, softmax, weighted sum of V.  prob: (S, heads) packed.
+__global__ void __launch_bounds__(ATT_NT) k_attn_fwd(const float* __restrict__ q, const float* __restrict__ Kf, const float* __restrict__ Vf,
+                                                     int dim, int heads, const int* __restrict__ off, int Tmax,
+                                                     const int* __restrict__ last_row, float* __restrict__ prob,
+                                                     float* __restrict__ y_f, bf16* __restrict__ y_h) {
+    extern __shared__ float att_sm[];
+    const int c = dim / heads;
+    float* qs = att_sm;            // c
+    float* sc = att_sm + c;        // Tmax
+    float* red = sc + Tmax;        // 4
+    const int i = blockIdx.x, hd = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    int len, j;
+    seq_of_last_row(off, Tmax, last_row[i], &len, &j);
+    for (int k = tid; k < c; k += ATT_NT) qs[k] = q[(size_t)i * dim + hd * c + k];
+    __syncthreads();
+    const float scale = rsqrtf((float)c);
+    for (int t = wrp; t < len; t += ATT_NT / 32) {
+        const float* kr = Kf + (size_t)(off[t] + j) * dim + hd * c;
+        float d = 0.f;
+        for (int k = lane; k < c; k += 32) d += qs[k] * kr[k];
+        d = warp_sum(d);
+        if (lane == 0) sc[t] = d * scale;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int t = tid; t < len; t += ATT_NT) mx = fmaxf(mx, sc[t]);
+    mx = block_max_att(mx, red);
+    float sm = 0.f;
+    for (int t = tid; t < len; t += ATT_NT) { const float e = __expf(sc[t] - mx); sc[t] = e; sm += e; }
+    sm = block_sum_att(sm, red);
+    const float inv = 1.0f / sm;
+    for (int t = tid; t < len; t += ATT_NT) {
+        const float a = sc[t] * inv;
+        sc[t] = a;
+        prob[(size_t)(off[t] + j) * heads + hd] = a;
+    }
+    __syncthreads();
+    for (int k = tid; k < c; k += ATT_NT) {
+        float acc = 0.f;
+        for (int t = 0; t < len; ++t) acc += sc[t] * Vf[(size_t)(off[t] + j) * dim + hd * c + k];
+        const size_t o = (size_t)i * dim + hd * c + k;
+        y_f[o] = acc;
+        if (y_h) y_h[o] = __float2bfloat16(acc);
+    }
+}
+void launch_attn_fwd(const float* q, const float* K, const float* V, int b, int dim, int heads, const int* off, int Tmax,
+                     const int* last_row, float* prob, float* y_f, bf16* y_h, cudaStream_t s) {
+    if (b <= 0) return;
+    const size_t smem = sizeof(float) * (dim / heads + Tmax + 8);
+    k_attn_fwd<<<dim3(b, heads), ATT_NT, smem, s>>>(q, K, V, dim, heads, off, Tmax, last_row, prob, y_f, y_h);
+    COUNT_LAUNCH();
+}
+
+// grid (b, heads): every (packed row, head) of dK / dV belongs to exactly one block -- no atomics, no memset
+__global__ void __launch_bounds__(ATT_NT) k_attn_bwd(const float* __restrict__ dy, const float* __restrict__ q, const float* __restrict__ Kf,
+                                                     const float* __restrict__ Vf, const float* __restrict__ prob, int dim, int heads,
+                                                     const int* __restrict__ off, int Tmax, const int* __restrict__ last_row,
+                                                     float* __restrict__ dq_f, bf16* __restrict__ dq_h, float* __restrict__ dK_f,
+                                                     bf16* __restrict__ dK_h, float* __restrict__ dV_f, bf16* __restrict__ dV_h) {
+    extern __shared__ float att_sm[];
+    const int c = dim / heads;
+    float* qs = att_sm;            // c
+    float* dys = qs + c;           // c
+    float* ds = dys + c;           // Tmax: d score
+    float* pa = ds + Tmax;         // Tmax: a
+    float* red = pa + Tmax;        // 4
+    const int i = blockIdx.x, hd = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    int len, j;
+    seq_of_last_row(off, Tmax, last_row[i], &len, &j);
+    for (int k = tid; k < c; k += ATT_NT) {
+        qs[k] = q[(size_t)i * dim + hd * c + k];
+        dys[k] = dy[(size_t)i * dim + hd * c + k];
+    }
+    __syncthreads();
+    const float scale = rsqrtf((float)c);
+    for (int t = wrp; t < len; t += ATT_NT / 32) {   // da[t] = dy . V[t]
+        const float* vr = Vf + (size_t)(off[t] + j) * dim + hd * c;
+        float d = 0.f;
+        for (int k = lane; k < c; k += 32) d += dys[k] * vr[k];
+        d = warp_sum(d);
+        if (lane == 0) { ds[t] = d; pa[t] = prob[(size_t)(off[t] + j) * heads + hd]; }
+    }
+    __syncthreads();
+    float dot = 0.f;
+    for (int t = tid; t < len; t += ATT_NT) dot += pa[t] * ds[t];
+    dot = block_sum_att(dot, red);
+    for (int t = tid; t < len; t += ATT_NT) ds[t] = pa[t] * (ds[t] - dot) * scale;   // d (q.k) including the c^-1/2
+    __syncthreads();
+    for (int k = tid; k < c; k += ATT_NT) {
+        float acc = 0.f;
+        const float qk = qs[k], dyk = dys[k];
+        for (int t = 0; t < len; ++t) {
+            const size_t o = (size_t)(off[t] + j) * dim + hd * c + k;
+            acc += ds[t] * Kf[o];
+            const float dk = ds[t] * qk, dv = pa[t] * dyk;
+            dK_f[o] = dk; dV_f[o] = dv;
+            if (dK_h) { dK_h[o] = __float2bfloat16(dk); dV_h[o] = __float2bfloat16(dv); }
+        }
+        const size_t o = (size_t)i * dim + hd * c + k;
+        dq_f[o] = acc;
+        if (dq_h) dq_h[o] = __float2bfloat16(acc);
+    }
+}
+void launch_attn_bwd(const float* dy, const float* q, const float* K, const float* V, const float* prob, int b, int dim, int heads,
+                     const int* off, int Tmax, const int* last_row, float* dq_f, bf16* dq_h, float* dK_f, bf16* dK_h, float* dV_f,
+                     bf16* dV_h, cudaStream_t s) {
+    if (b <= 0) return;
+    const size_t smem = sizeof(float) * (2 * (dim / heads) + 2 * Tmax + 8);
+    k_attn_bwd<<<dim3(b, heads), ATT_NT, smem, s>>>(dy, q, K, V, prob, dim, heads, off, Tmax, last_row, dq_f, dq_h, dK_f, dK_h, dV_f, dV_h);
+    COUNT_LAUNCH();
+}
+
+// tf.contrib.layers.layer_norm (src/model.py:11,139): over the last axis, biased variance, epsilon 1e-12, gamma / beta.
+// x = h + p (the residual is formed here).  Saves xhat and 1/sigma for the backward.
+__global__ void __launch_bounds__(ATT_NT) k_resid_ln_fwd(const float* __restrict__ h, const float* __restrict__ pp, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int dim, float* __restrict__ xhat,
+                                                         float* __restrict__ rstd, float* __restrict__ out_f, bf16* __restrict__ out_h) {
+    __shared__ float red[8];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const float* hr = h + (size_t)i * dim; const float* pr = pp + (size_t)i * dim;
+    float sm = 0.f;
+    for (int k = tid; k < dim; k += ATT_NT) sm += hr[k] + pr[k];
+    const float mean = block_sum_att(sm, red) / (float)dim;
+    float sq = 0.f;
+    for (int k = tid; k < dim; k += ATT_NT) { const float d = hr[k] + pr[k] - mean; sq += d * d; }
+    const float var = block_sum_att(sq, red) / (float)dim;
+    const float rs = rsqrtf(var + 1e-12f);
+    if (tid == 0) rstd[i] = rs;
+    for (int k = tid; k < dim; k += ATT_NT) {
+        const float xh = (hr[k] + pr[k] - mean) * rs;
+        const float o = xh * gamma[k] + beta[k];
+        xhat[(size_t)i * dim + k] = xh;
+        out_f[(size_t)i * dim + k] = o;
+        if (out_h) out_h[(size_t)i * dim + k] = __float2bfloat16(o);
+    }
+}
+void launch_resid_ln_fwd(const float* h, const float* pp, const float* gamma, const float* beta, int b, int dim, float* xhat, float* rstd,
+                         float* out_f, bf16* out_h, cudaStream_t s) {
+    if (b <= 0) return;
+    k_resid_ln_fwd<<<b, ATT_NT, 0, s>>>(h, pp, gamma, beta, dim, xhat, rstd, out_f, out_h);
+    COUNT_LAUNCH();
+}
+// dx = rstd (g - mean(g) - xhat mean(g xhat)), g = dout gamma; also writes dout * xhat (its column sum is d gamma)
+__global__ void __launch_bounds__(ATT_NT) k_ln_bwd(const float* __restrict__ dout, const float* __restrict__ xhat, const float* __restrict__ rstd,
+                                                   const float* __restrict__ gamma, int dim, float* __restrict__ dx_f, bf16* __restrict__ dx_h,
+                                                   float* __restrict__ dgam_rows) {
+    __shared__ float red[8];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const float* dr = dout + (size_t)i * dim; const float* xr = xhat + (size_t)i * dim;
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = tid; k < dim; k += ATT_NT) { const float gk = dr[k] * gamma[k]; s1 += gk; s2 += gk * xr[k]; }
+    const float m1 = block_sum_att(s1, red) / (float)dim;
+    const float m2 = block_sum_att(s2, red) / (float)dim;
+    const float rs = rstd[i];
+    for (int k = tid; k < dim; k += ATT_NT) {
+        const float gk = dr[k] * gamma[k];
+        const float dx = rs * (gk - m1 - xr[k] * m2);
+        dx_f[(size_t)i * dim + k] = dx;
+        if (dx_h) dx_h[(size_t)i * dim + k] = __float2bfloat16(dx);
+        dgam_rows[(size_t)i * dim + k] = dr[k] * xr[k];
+    }
+}
+void launch_ln_bwd(const float* dout, const float* xhat, const float* rstd, const float* gamma, int b, int dim, float* dx_f, bf16* dx_h,
+                   float* dgam_rows, cudaStream_t s) {
+    if (b <= 0) return;
+    k_ln_bwd<<<b, ATT_NT, 0, s>>>(dout, xhat, rstd, gamma, dim, dx_f, dx_h, dgam_rows);
+    COUNT_LAUNCH();
+}

@@ -134,3 +134,15 @@ void gru_tc_bwd(GruTcCtx*, const GruBwdArgs* dirs, int ndir, const SeqPlan& P, c
 long long gru_tc_test_mma(const bf16* A, const bf16* B, float* D, int N, int K, int nacc, cudaStream_t s);
 // xbench.cu: exchange-latency measurement hook
 int xbench_run(int device, int method, int groups, int rows, int iters, double* cycles_per_iter, int* max_clusters);
+
+// attentive=true (src/model.py:18-45,136-145): single-query multi-head attention over the packed encoder rows + residual
+// layer norm; see kernels.cu
+void launch_attn_fwd(const float* q, const float* K, const float* V, int b, int dim, int heads, const int* off, int Tmax,
+                     const int* last_row, float* prob, float* y_f, bf16* y_h, cudaStream_t s);
+void launch_attn_bwd(const float* dy, const float* q, const float* K, const float* V, const float* prob, int b, int dim, int heads,
+                     const int* off, int Tmax, const int* last_row, float* dq_f, bf16* dq_h, float* dK_f, bf16* dK_h, float* dV_f,
+                     bf16* dV_h, cudaStream_t s);
+void launch_resid_ln_fwd(const float* h, const float* pp, const float* gamma, const float* beta, int b, int dim, float* xhat, float* rstd,
+                         float* out_f, bf16* out_h, cudaStream_t s);
+void launch_ln_bwd(const float* dout, const float* xhat, const float* rstd, const float* gamma, int b, int dim, float* dx_f, bf16* dx_h,
+                   float* dgam_rows, cudaStream_t s);

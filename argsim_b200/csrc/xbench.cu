@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(XNT, 1) k_xbench(const XP P) {
     const bool cluster = P.method >= 2;
     if (P.method == 2)
         for (int i = tid; i < 2 * rows * wpr; i += XNT) sll[i] = 0ull;
-    if (P.method == 3 && tid == 0) {
+    if (P.method >= 3 && tid == 0) {
         for (int p = 0; p < 2; ++p)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&bars[p])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -105,6 +105,24 @@ __global__ void __launch_bounds__(XNT, 1) k_xbench(const XP P) {
                 const uint32_t la = smem_addr(sll + par * par_words + (size_t)row * wpr + c * (XUN / 2) + w);
                 const uint32_t data = carry + (uint32_t)(row * 7 + w);
                 asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(mapa(la, peer)), "r"(data), "r"(tag) : "memory");
+            }
+        } else if (P.method >= 4) {
+            // one bulk copy per peer: block layout [parity][source CTA][rows][64 B]; the source block is written locally
+            // first, then 16 threads (method 4: two lanes of each warp, method 5: 16 lanes of warp 0) push it
+            if (tid == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&bars[par])), "r"(rows * 64 * XCL) : "memory");
+            uint32_t* mine = reinterpret_cast<uint32_t*>(sm + XCL * rows * 64 * 2 + par * rows * 64);   // staging, outside the receive area
+            for (int i = tid; i < rows * 16; i += XNT) mine[i] = carry + (uint32_t)((i / 16) * 7 + (i % 16) / 4) + (uint32_t)(i & 3);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            const int lane = tid & 31, wrp = tid >> 5;
+            int peer = -1;
+            if (P.method == 4) { if (lane < 2) peer = wrp * 2 + lane; }
+            else if (wrp == 0 && lane < XCL) peer = lane;
+            if (peer >= 0) {
+                const uint32_t dst = smem_addr(sm) + (uint32_t)(par * XCL * rows * 64 + c * rows * 64);
+                asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(mapa(dst, peer)), "r"(smem_addr(mine)), "r"(rows * 64), "r"(mapa(smem_addr(&bars[par]), peer)) : "memory");
             }
         } else {
             // bf16 payload: row stride 1024 B, my 64 bytes = 4 x 16 B per row and peer
@@ -199,7 +217,7 @@ int xbench_run(int device, int method, int groups, int rows, int iters, double* 
         if (method >= 2) throw std::runtime_error("xbench: SM-id grouping is for the L2 methods");
         CUDA_CHECK(cudaMalloc(&P.smids, blocks * sizeof(int)));
     }
-    const size_t smem = method == 2 ? (size_t)2 * rows * (XH / 2) * 8 : (method == 3 ? (size_t)2 * rows * 1024 : 16);
+    const size_t smem = method == 2 ? (size_t)2 * rows * (XH / 2) * 8 : (method == 3 ? (size_t)2 * rows * 1024 : (method >= 4 ? (size_t)2 * rows * 1024 + 2 * rows * 64 : 16));
     CUDA_CHECK(cudaFuncSetAttribute(k_xbench, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     *max_clusters = 0;
     if (method >= 2) {

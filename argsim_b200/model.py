@@ -109,8 +109,6 @@ def vAe(mode, src=None, tgt=None, dim_tgt=8192, dim_emb=512, dim_rep=1024, rnn_l
     config = dict(dim_tgt=dim_tgt, dim_emb=dim_emb, dim_rep=dim_rep, rnn_layers=rnn_layers, bidirectional=bidirectional,
                   bidir_stacked=bidir_stacked, attentive=attentive, logit_use_embed=logit_use_embed, accelerate=accelerate,
                   learn_rate=learn_rate, bos=bos, eos=eos)
-    if attentive:
-        raise NotImplementedError("attentive=True is not on the hot path (config.json: false; 'todo fixme' at src/model.py:136)")
     if _state['config'] is None:
         _state['config'] = config
     elif _state['config'] != config:

@@ -36,6 +36,10 @@ enum { ARGSIM_FP32_VALIDATE = 0, ARGSIM_BF16 = 1 };
 typedef struct argsim_config {
     int32_t dim_tgt, dim_emb, dim_rep, rnn_layers;
     int32_t bidirectional, bidir_stacked, attentive, logit_use_embed;
+                                  /* attentive (src/model.py:136-145): the final state attends over its sequence's outputs,
+                                     8 heads, residual + layer norm; adds encode/cata/{q,k,v,p}/{kernel,bias} and
+                                     encode/cata/LayerNorm/{gamma,beta}.  The reference branch is marked "todo fixme" and
+                                     cannot execute; the repaired semantics are stated in DESIGN.md section 1, row A8 */
     float   accelerate, learn_rate;
     int32_t bos, eos;
     int32_t precision;            /* ARGSIM_FP32_VALIDATE | ARGSIM_BF16 */

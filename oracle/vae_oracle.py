@@ -119,7 +119,7 @@ def enc_stacks(cfg):
 
 
 def param_shapes(dim_tgt=8192, dim_emb=512, dim_rep=1024, rnn_layers=3, logit_use_embed=True, bidirectional=True,
-                 bidir_stacked=True, **_):
+                 bidir_stacked=True, attentive=False, **_):
     V, D, R, L = dim_tgt, dim_emb, dim_rep, rnn_layers
     H = D
     shp = {'embed/embedding': (V, D)}
@@ -142,6 +142,12 @@ def param_shapes(dim_tgt=8192, dim_emb=512, dim_rep=1024, rnn_layers=3, logit_us
                 shp[p + 'bW'] = (3 * H,)
                 shp[p + 'bR'] = (3 * H,)
     EH = 2 * H if bidirectional else H
+    if attentive:   # src/model.py:33-35,45 (layer_aff v,k,q,p under encode/cata) and :139 (layer_nrm)
+        for nm in 'qkvp':
+            shp['encode/cata/%s/kernel' % nm] = (EH, EH)
+            shp['encode/cata/%s/bias' % nm] = (EH,)
+        shp['encode/cata/LayerNorm/gamma'] = (EH,)
+        shp['encode/cata/LayerNorm/beta'] = (EH,)
     for nm, (i, o) in (('mu', (EH, R)), ('lv', (EH, R)), ('ex', (R, D))):
         shp['latent/%s/kernel' % nm] = (i, o)
         shp['latent/%s/bias' % nm] = (o,)
@@ -171,6 +177,8 @@ def init_params(cfg, seed=0, dtype=np.float64, bias_scale=0.0):
         if name == 'embed/embedding':
             bnd = (6.0 / (V / D + 1)) ** 0.5
             w = rng.uniform(-bnd, bnd, shp)
+        elif name.endswith('LayerNorm/gamma'):   # tf.contrib.layers.layer_norm: scale starts at one
+            w = 1.0 + (rng.uniform(-bias_scale, bias_scale, shp) if bias_scale else np.zeros(shp))
         elif len(shp) == 1:
             w = rng.uniform(-bias_scale, bias_scale, shp) if bias_scale else np.zeros(shp)
         elif name.endswith('/W') or name.endswith('/R'):
@@ -190,6 +198,75 @@ def init_params(cfg, seed=0, dtype=np.float64, bias_scale=0.0):
 
 def _sig(x):
     return 1.0 / (1.0 + np.exp(-x))
+
+
+# --------------------------------------------------------------------------------------
+# attentive=true (src/model.py:18-45,136-145)
+# --------------------------------------------------------------------------------------
+ATT_HEADS = 8        # attention(..., head=8), src/model.py:18
+LN_EPS = 1e-12       # tf.contrib.layers.layer_norm -> tf.nn.batch_normalization(variance_epsilon=1e-12)
+
+
+def cata_forward(P, h, hs, len_src):
+    """src/model.py:136-145 as its docstring (:19-26) and comments state it, with the two defects that keep the reference
+    from running repaired -- NOT a restatement of executable reference code (the branch is marked 'todo fixme' and
+    config.json never enables it):
+      * :33-35 apply tf.layers.dense to (b, d, s) tensors, i.e. over the TIME axis; the affines here act on the feature
+        axis d, which is what the shape comments 'bds <- bvs' / 'bdt <- bqt' ask for;
+      * :35 reshapes q to (b,h,c,s) although it has t (=1) positions; here (b,h,c,t).
+    query = the final state h (b,d), t = 1; keys / values = all outputs hs (s,b,d); mask = log(msk_src) = 0 on the
+    sequence's own steps, -inf on padding; 8 heads of c = d/8, scores scaled by c^-1/2; h <- layer_norm(h + p(y)) with
+    the layer norm over the feature axis (biased variance, epsilon 1e-12, gamma and beta).
+    Returns (h_out, cache)."""
+    s, b, d = hs.shape
+    hd, c = ATT_HEADS, d // ATT_HEADS
+    q = h @ P['encode/cata/q/kernel'] + P['encode/cata/q/bias']
+    k = hs @ P['encode/cata/k/kernel'] + P['encode/cata/k/bias']
+    v = hs @ P['encode/cata/v/kernel'] + P['encode/cata/v/bias']
+    a = np.einsum('bhc,sbhc->bhs', q.reshape(b, hd, c), k.reshape(s, b, hd, c)) * h.dtype.type(c ** -0.5)
+    pad = np.arange(s)[None, :] >= np.asarray(len_src)[:, None]            # (b,s)
+    a = np.where(pad[:, None, :], -np.inf, a)
+    a = np.exp(a - a.max(-1, keepdims=True))
+    a = a / a.sum(-1, keepdims=True)
+    y = np.einsum('bhs,sbhc->bhc', a, v.reshape(s, b, hd, c)).reshape(b, d)
+    pp = y @ P['encode/cata/p/kernel'] + P['encode/cata/p/bias']
+    x = h + pp
+    mean = x.mean(-1, keepdims=True)
+    var = ((x - mean) ** 2).mean(-1, keepdims=True)
+    rstd = 1.0 / np.sqrt(var + h.dtype.type(LN_EPS))
+    xhat = (x - mean) * rstd
+    out = xhat * P['encode/cata/LayerNorm/gamma'] + P['encode/cata/LayerNorm/beta']
+    return out, dict(h=h, hs=hs, q=q, k=k, v=v, a=a, y=y, xhat=xhat, rstd=rstd)
+
+
+def cata_backward(P, G, dout, cc):
+    """gradient of cata_forward: accumulates the parameter gradients into G, returns (d h, d hs)."""
+    h, hs, q, k, v, a, y, xhat, rstd = (cc[n] for n in ('h', 'hs', 'q', 'k', 'v', 'a', 'y', 'xhat', 'rstd'))
+    s, b, d = hs.shape
+    hd, c = ATT_HEADS, d // ATT_HEADS
+    G['encode/cata/LayerNorm/gamma'] += (dout * xhat).sum(0)
+    G['encode/cata/LayerNorm/beta'] += dout.sum(0)
+    g = dout * P['encode/cata/LayerNorm/gamma']
+    dx = rstd * (g - g.mean(-1, keepdims=True) - xhat * (g * xhat).mean(-1, keepdims=True))
+    G['encode/cata/p/kernel'] += y.T @ dx
+    G['encode/cata/p/bias'] += dx.sum(0)
+    dy = (dx @ P['encode/cata/p/kernel'].T).reshape(b, hd, c)
+    vh, kh, qh = v.reshape(s, b, hd, c), k.reshape(s, b, hd, c), q.reshape(b, hd, c)
+    da = np.einsum('bhc,sbhc->bhs', dy, vh)
+    dv = np.einsum('bhs,bhc->sbhc', a, dy).reshape(s, b, d)
+    dsc = a * (da - (a * da).sum(-1, keepdims=True)) * h.dtype.type(c ** -0.5)
+    dq = np.einsum('bhs,sbhc->bhc', dsc, kh).reshape(b, d)
+    dk = np.einsum('bhs,bhc->sbhc', dsc, qh).reshape(s, b, d)
+    G['encode/cata/q/kernel'] += h.T @ dq
+    G['encode/cata/q/bias'] += dq.sum(0)
+    hs2 = hs.reshape(s * b, d)
+    G['encode/cata/k/kernel'] += hs2.T @ dk.reshape(s * b, d)
+    G['encode/cata/k/bias'] += dk.sum((0, 1))
+    G['encode/cata/v/kernel'] += hs2.T @ dv.reshape(s * b, d)
+    G['encode/cata/v/bias'] += dv.sum((0, 1))
+    dh = dx + dq @ P['encode/cata/q/kernel'].T
+    dhs = dk @ P['encode/cata/k/kernel'].T + dv @ P['encode/cata/v/kernel'].T
+    return dh, dhs
 
 
 def gru_forward(x, h0, W, R, bW, bR):
@@ -287,6 +364,9 @@ def forward(P, cfg, src, tgt, mode='valid', step=0, keep=None, eps=None, want_pr
             outs.append(reverse_sequence(y, len_src) if k == 1 else y)
         hs = np.concatenate(outs, -1)
     h = hs[len_src - 1, np.arange(b)]
+    cata_cache = None
+    if cfg.get('attentive', False):                      # model.py:136-145
+        h, cata_cache = cata_forward(P, h, hs, len_src)
     mu = h @ P['latent/mu/kernel'] + P['latent/mu/bias']
     lv = h @ P['latent/lv/kernel'] + P['latent/lv/bias']
     z = mu
@@ -334,7 +414,7 @@ def forward(P, cfg, src, tgt, mode='valid', step=0, keep=None, eps=None, want_pr
         o['loss_kld'] = kld_samp.sum() / k_norm
         o['loss'] = o['rate_anneal'] * o['loss_kld'] + o['loss_gen']
         cache = dict(E=E, lead=lead, src_tm=src_tm, len_src=len_src, msk_tgt=msk_tgt, labels=labels,
-                     enc=enc_caches, dec=dec_caches, h=h, mu=mu, lv=lv, z=z, eps=eps, hd=hd, ho=ho,
+                     enc=enc_caches, dec=dec_caches, cata=cata_cache, h=h, mu=mu, lv=lv, z=z, eps=eps, hd=hd, ho=ho,
                      logits=logits, lse=lse, scale=scale, hs_shape=hs.shape, emb_tgt_shape=emb_tgt.shape,
                      mode=mode, anneal=o['rate_anneal'], n_norm=n_norm, k_norm=k_norm)
     return o, cache
@@ -387,7 +467,11 @@ def backward(P, cfg, cache):
     len_src = cache['len_src']
     b = len(len_src)
     dhs = np.zeros(cache['hs_shape'], dt)
-    dhs[len_src - 1, np.arange(b)] = dh
+    if cache.get('cata') is not None:
+        dh, dhs_att = cata_backward(P, G, dh, cache['cata'])
+        # padded positions carry softmax weight 0, so d k and d v -- and with them dhs_att -- are exactly 0 there
+        dhs += dhs_att
+    dhs[len_src - 1, np.arange(b)] += dh
     stacks = enc_stacks(cfg)
     if stacks is None:
         for i in range(L, 0, -1):

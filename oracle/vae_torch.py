@@ -63,6 +63,18 @@ def forward(P, cfg, src, tgt, mode='valid', step=0, keep=None, eps=None, encoder
             outs.append(reverse_sequence(y, len_src) if k == 1 else y)
         x = torch.cat(outs, -1)
     h = x[len_src - 1, torch.arange(b)]
+    if cfg.get('attentive', False):                         # model.py:136-145, repaired as oracle/vae_oracle.py:cata_forward states
+        s_, d_ = x.shape[0], x.shape[2]
+        hd, c = 8, d_ // 8
+        q = (h @ P['encode/cata/q/kernel'] + P['encode/cata/q/bias']).reshape(b, hd, c)
+        k = (x @ P['encode/cata/k/kernel'] + P['encode/cata/k/bias']).reshape(s_, b, hd, c)
+        v = (x @ P['encode/cata/v/kernel'] + P['encode/cata/v/bias']).reshape(s_, b, hd, c)
+        a = torch.einsum('bhc,sbhc->bhs', q, k) * (c ** -0.5)
+        pad = torch.arange(s_)[None, :] >= len_src[:, None]
+        a = torch.softmax(a.masked_fill(pad[:, None, :], float('-inf')), -1)
+        y = torch.einsum('bhs,sbhc->bhc', a, v).reshape(b, d_)
+        xx = h + y @ P['encode/cata/p/kernel'] + P['encode/cata/p/bias']
+        h = torch.nn.functional.layer_norm(xx, (d_,), P['encode/cata/LayerNorm/gamma'], P['encode/cata/LayerNorm/beta'], 1e-12)
     mu = h @ P['latent/mu/kernel'] + P['latent/mu/bias']
     o = dict(mu=mu, z=mu, rate_update=float(lr), rate_anneal=float(anneal))
     if encoder_only:

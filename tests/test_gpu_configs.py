@@ -85,6 +85,50 @@ def test_c1_full_size_all_gradients_match_torch_autograd(c1):
         h.close()
 
 
+def test_attentive_at_config_dims_matches_torch_autograd():
+    """attentive=true (src/model.py:136-145, repaired form: oracle/vae_oracle.py:cata_forward) at config.json's dimensions
+    (8 heads of 128 over the 1024-wide encoder output): every gradient against torch autograd, both precisions; the
+    persistent recurrence kernels now receive d hs at every step of the top layer, not only at the final state"""
+    from argsim_b200 import _lib
+    from argsim_b200.synth import synth_batch
+    torch, T = _torch()
+    cfg = dict(C1, attentive=True)
+    src = synth_batch(64, 'iac', cfg['dim_tgt'], seed=3)[:24, :96]
+    src[:, -1] = 1                      # every row keeps an eos pad after the cut
+    P = O.init_params(cfg, seed=2, dtype=np.float32, bias_scale=0.05)
+    keep, eps = _draw(src, 6)
+    Pt = T.to_torch(P, torch.float32, requires_grad=True)
+    o = T.forward(Pt, cfg, src, src, 'train', step=STEP, keep=_oracle_keep(keep, src, 1).astype(np.int64), eps=eps)
+    o['loss'].backward()
+    G = {k: v.grad.numpy() for k, v in Pt.items()}
+    gmax = max(float(np.abs(v).max()) for v in G.values())
+    assert np.linalg.norm(G['encode/rnn3/bwd/R']) > 1e-9        # no longer the exactly-zero case of the default graph
+    for name, prec in (('fp32', _lib.FP32_VALIDATE), ('bf16', _lib.BF16)):
+        h = _lib.Handle(precision=prec, **cfg)
+        h.set_params(P)
+        h.step = STEP
+        st = h.grad_step(src, src, keep=keep, eps=eps)
+        tol = 1e-3 if name == 'fp32' else 1e-2
+        for k in ('loss', 'loss_gen', 'loss_kld'):
+            assert rel(st[k], float(o[k])) < tol, (name, k, st[k], float(o[k]))
+        for k in P:
+            g, r = h.get_grad(k).astype(np.float64).ravel(), G[k].astype(np.float64).ravel()
+            if k == 'encode/cata/k/bias':   # identically zero (softmax shift invariance); fp32 rounding in the oracle too
+                assert np.abs(g).max() < (1e-5 if name == 'fp32' else 1e-2) * gmax, (name, k, np.abs(g).max())
+            elif name == 'fp32':
+                err = np.abs(g - r).max() / (np.abs(r).max() + 1e-30)
+                assert err < 5e-4, (name, k, err)
+            else:
+                cos = float(g @ r) / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30)
+                ratio = np.linalg.norm(g) / (np.linalg.norm(r) + 1e-30)
+                assert cos > 0.99, (name, k, cos)
+                assert abs(ratio - 1.0) < 0.05, (name, k, ratio)
+        mu = h.embed(src)
+        want = T.forward(T.to_torch(P), cfg, src, src, 'infer', encoder_only=True)['mu'].numpy()
+        assert np.abs(mu - want).max() <= (2e-4 if name == 'fp32' else 3e-2) * np.abs(want).max(), name
+        h.close()
+
+
 def test_c1_bf16_ten_step_trajectory_matches_oracle(c1):
     """10 training steps (forward, backward, TF-form Adam) on both sides with the same injected randomness."""
     from argsim_b200 import _lib

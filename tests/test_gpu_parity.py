@@ -256,6 +256,52 @@ def test_non_default_encoder_branches(prec, bidirectional, bidir_stacked):
     h.close()
 
 
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('bidirectional,bidir_stacked', [(True, True), (True, False), (False, True)])
+def test_attentive_branch(prec, bidirectional, bidir_stacked):
+    """src/model.py:136-145 (attentive=true; repaired form stated at oracle/vae_oracle.py:cata_forward): the final state
+    attends over its own sequence's outputs, residual + layer norm -- losses, every gradient (the q/k/v/p affines, the
+    layer-norm scale and shift, and the encoder underneath, which now receives gradient at every step), the embedding,
+    and two Adam steps."""
+    from argsim_b200 import _lib
+    cfg = dict(SMALL, bidirectional=bidirectional, bidir_stacked=bidir_stacked, attentive=True)
+    h, P = _mk(cfg, _lib.FP32_VALIDATE if prec == 'fp32' else _lib.BF16)
+    assert set(h.param_shapes()) == set(P) and all(h.param_shapes()[k] == v.shape for k, v in P.items())
+    src = ragged_batch(9, 13, cfg['dim_tgt'], 90)
+    tgt = ragged_batch(9, 10, cfg['dim_tgt'], 91)
+    keep, eps = _inject(cfg, tgt, 92)
+    h.step = 9000
+    o, cache = O.forward(P, cfg, src, tgt, 'train', step=9000, keep=_oracle_keep(keep, tgt, cfg['eos']), eps=eps.astype(np.float64))
+    G = O.backward(P, cfg, cache)
+    st = h.grad_step(src, tgt, keep=keep, eps=eps)
+    tol = 1e-3 if prec == 'fp32' else 1e-2
+    for k in ('loss', 'loss_gen', 'loss_kld'):
+        assert rel(st[k], o[k]) < tol, (k, st[k], o[k])
+    gmax = max(np.abs(v).max() for v in G.values())
+    for k in P:
+        g = h.get_grad(k).astype(np.float64)
+        if k == 'encode/cata/k/bias':   # softmax is shift invariant: the gradient is identically zero
+            assert np.abs(g).max() <= (1e-5 if prec == 'fp32' else 1e-2) * gmax, (k, np.abs(g).max())
+        elif prec == 'fp32':
+            assert np.abs(g - G[k]).max() <= 2e-4 * np.abs(G[k]).max() + 1e-9, k
+        elif np.linalg.norm(G[k]) > 1e-12:
+            cos = (g.ravel() @ G[k].ravel()) / (np.linalg.norm(g) * np.linalg.norm(G[k]) + 1e-30)
+            assert cos > 0.99, (k, cos)
+    mu = h.embed(src)
+    assert np.abs(mu - o['mu']).max() <= (1e-4 if prec == 'fp32' else 3e-2) * np.abs(o['mu']).max()
+    if prec == 'fp32':   # two optimizer steps track the oracle's parameters (the new tensors included)
+        Po = {k: v.copy() for k, v in P.items()}
+        M = {k: np.zeros_like(v) for k, v in P.items()}
+        Vv = {k: np.zeros_like(v) for k, v in P.items()}
+        h.step = 9000
+        for i in range(2):
+            O.train_step(Po, M, Vv, cfg, src, tgt, 9000 + i, _oracle_keep(keep, tgt, cfg['eos']), eps.astype(np.float64))
+            h.train_step(src, tgt, keep=keep, eps=eps)
+        for k in ('encode/cata/q/kernel', 'encode/cata/v/kernel', 'encode/cata/LayerNorm/gamma', 'encode/cata/p/bias'):
+            assert np.abs(h.get_param(k) - Po[k]).max() <= 2e-4, k
+    h.close()
+
+
 def test_tf_bundle_export_import_roundtrip(tmp_path):
     """Saver.save(tf_format=True) -> <path>.index / .data-00000-of-00001 under the reference's variable names -> Saver.restore
     into a fresh session: parameters (up to the r/u bias split the cuDNN-canonical form cannot keep), Adam slots, the

@@ -169,12 +169,14 @@ def test_facade_surface_and_fetch_routing():
         assert f in mv and f in mt and f not in mi, f
     assert 'train_step' in mt and 'train_step' not in mv
     assert mv.bos == 2 and mv.eos == 1 and mv.mu.shape[-1] == 1024
-    with pytest.raises(NotImplementedError):
-        M.vAe('valid', **dict(C, attentive=True))
+    with pytest.raises(ValueError):
+        M.vAe('valid', **dict(C, attentive=True))     # a different graph (src/model.py:136-145): its own variable set
     with pytest.raises(ValueError):
         M.vAe('valid', **dict(C, dim_rep=512))        # one variable set per process
     with pytest.raises(AssertionError):
         M.vAe('test', **C)
+    M.reset()
+    assert M.vAe('valid', **dict(C, attentive=True)).config['attentive'] is True
     M.reset()
 
 

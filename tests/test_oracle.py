@@ -68,8 +68,8 @@ def test_gru_cell_matches_torch_library_gru():
     np.testing.assert_allclose(hs, ref.numpy(), atol=1e-12)
 
 
-def _setup(seed=0, L=2):
-    cfg = dict(SMALL, dim_tgt=64, dim_emb=16, dim_rep=24, rnn_layers=L)
+def _setup(seed=0, L=2, **extra):
+    cfg = dict(SMALL, dim_tgt=64, dim_emb=16, dim_rep=24, rnn_layers=L, **extra)
     P = O.init_params(cfg, seed=seed, bias_scale=0.2)
     src = ragged_batch(4, 7, cfg['dim_tgt'], seed + 1)
     tgt = ragged_batch(4, 6, cfg['dim_tgt'], seed + 2)
@@ -92,6 +92,39 @@ def test_forward_and_analytic_backward_match_torch_autograd():
     ot['loss'].backward()
     for k in P:
         np.testing.assert_allclose(Pt[k].grad.numpy(), G[k], atol=2e-7 * max(1.0, np.abs(G[k]).max()), err_msg=k)
+
+
+def test_attentive_branch_backward_matches_torch_autograd_and_finite_differences():
+    """attentive=true (src/model.py:136-145, repaired as O.cata_forward states): the numpy analytic backward against torch
+    autograd of the independent torch statement, plus central differences on the new tensors"""
+    cfg, P, src, tgt, keep, eps = _setup(seed=7, attentive=True)
+    assert P['encode/cata/q/kernel'].shape == (32, 32) and np.abs(P['encode/cata/LayerNorm/gamma'] - 1).max() <= 0.2
+    o, cache = O.forward(P, cfg, src, tgt, 'train', step=7000, keep=keep, eps=eps)
+    G = O.backward(P, cfg, cache)
+    Pt = T.to_torch(P, torch.float64, requires_grad=True)
+    ot = T.forward(Pt, cfg, src, tgt, 'train', step=7000, keep=keep, eps=eps)
+    assert abs(float(ot['loss']) - float(o['loss'])) < 1e-5 * abs(float(o['loss']))
+    ot['loss'].backward()
+    for k in P:
+        np.testing.assert_allclose(Pt[k].grad.numpy(), G[k], atol=2e-7 * max(1.0, np.abs(G[k]).max()), err_msg=k)
+    assert np.abs(G['encode/cata/k/bias']).max() < 1e-12      # softmax is shift invariant
+    rng = np.random.default_rng(1)
+    for k in ('encode/cata/q/kernel', 'encode/cata/k/kernel', 'encode/cata/v/bias', 'encode/cata/p/kernel',
+              'encode/cata/LayerNorm/gamma', 'encode/rnn2/fwd/R'):
+        idx = tuple(rng.integers(0, s) for s in P[k].shape)
+        h = 1e-6
+        old = P[k][idx]
+        P[k][idx] = old + h
+        lp = O.forward(P, cfg, src, tgt, 'train', step=7000, keep=keep, eps=eps)[0]['loss']
+        P[k][idx] = old - h
+        lm = O.forward(P, cfg, src, tgt, 'train', step=7000, keep=keep, eps=eps)[0]['loss']
+        P[k][idx] = old
+        fd = (lp - lm) / (2 * h)
+        assert abs(fd - G[k][idx]) < 1e-6 + 1e-4 * abs(fd), (k, fd, G[k][idx])
+    # the mask: tokens appended after a row's eos padding do not change mu (they are outside every softmax)
+    mu0 = O.forward(P, cfg, src, tgt, 'infer')[0]['mu']
+    wide = np.concatenate([src, np.full((len(src), 3), 1, np.int32)], 1)
+    np.testing.assert_allclose(O.forward(P, cfg, wide, tgt, 'infer')[0]['mu'], mu0, atol=1e-12)
 
 
 def test_backward_finite_differences():

@@ -13,6 +13,8 @@ rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int
 torch.cuda.set_device(local)
 dist.init_process_group('cpu:gloo,cuda:nccl')
 cfg = dict(dim_tgt=8192, dim_emb=512, dim_rep=1024, rnn_layers=3, accelerate=1e-4, learn_rate=1e-3, bos=2, eos=1)
+if os.environ.get('ATTENTIVE'):   # src/model.py:136-145: its tensors share the latent affines' all-reduce bucket
+    cfg['attentive'] = True
 obj = [_lib.nccl_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(obj, src=0)
 prec = _lib.BF16 if os.environ.get('PREC', 'bf16') == 'bf16' else _lib.FP32_VALIDATE
@@ -26,6 +28,8 @@ s, t, rows, n_glob, b_glob = parallel.shard_batch(full, full, world, rank)
 h.step = 7000
 st = h.train_step(s, t, keep=keep[rows][:, :t.shape[1]], eps=eps[rows], n_tokens_global=n_glob, b_global=b_glob, row0=rank * len(rows))
 names = ['embed/embedding', 'decode/out/kernel', 'decode/rnn/l1/R', 'latent/mu/kernel', 'encode/rnn2/bwd/W', 'encode/rnn1/fwd/bR']
+if cfg.get('attentive'):
+    names += ['encode/cata/k/kernel', 'encode/cata/q/bias', 'encode/cata/LayerNorm/gamma', 'encode/rnn3/bwd/R']
 g = {k: h.get_grad(k) for k in names}
 p = {k: h.get_param(k) for k in names}
 # all ranks must hold identical reduced gradients and parameters

@@ -5,6 +5,7 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 echo "dp8 rc=$?"; tail -2 gpurun_out/gpu8_dp8.err
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --workload scaled --steps 4 --warmup 2 > gpurun_out/gpu8_scaled8.json 2> gpurun_out/gpu8_scaled8.err
 echo "scaled8 rc=$?"; tail -2 gpurun_out/gpu8_scaled8.err
+ATTENTIVE=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 scripts/dp_check.py 2>&1 | grep -E "DP_CHECK|grad |stats|Error|error" | tail -16
 python - <<'PY'
 import json
 d = json.loads(open('gpurun_out/gpu8_dp8.json').read().strip().splitlines()[-1])

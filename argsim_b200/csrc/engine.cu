@@ -1,5 +1,6 @@
 // engine.cu -- see engine.h.  Reference: src/model.py:75-189 (graph), src/train.py:104-121 (loops).
 #include "engine.h"
+#include <chrono>
 #include "nccl_dyn.h"
 #include <nvtx3/nvToolsExt.h>
 #include <math.h>
@@ -165,6 +166,7 @@ Engine::~Engine() {
     cudaFree(arena.base); cudaFree(d_stage); cudaFreeHost(h_stage); cudaFree(d_eps_in);
     for (auto& ps : pend) { if (ps.done) cudaEventDestroy(ps.done); if (ps.h_stats) cudaFreeHost(ps.h_stats); }
     cudaFree(d_stats); cudaFreeHost(h_stats); cudaFreeHost(h_out); cudaFree(gru_work);
+    delete dbuf;
     for (auto& e : pev) cudaEventDestroy(e);
     for (auto& k : ktimers) { cudaEventDestroy(k.a); cudaEventDestroy(k.b); }
     cudaEventDestroy(ev_bucket); cudaEventDestroy(ev_comm);
@@ -1520,110 +1522,242 @@ void Engine::embed(const int32_t* src, int b, int T, float* mu_out) {
     for (int r = (mb - 1) * cap; r < b; ++r) memcpy(mu_out + (size_t)order[r] * R, h_out + (size_t)r * R, sizeof(float) * R);
 }
 
-// decode(), model.py:204-219: fp32 SIMT path (host-driven single steps, batch <= a few hundred)
-void Engine::decode_init(const float* z, int b, float* state) {
-    float *dz, *dh;
-    CUDA_CHECK(cudaMalloc(&dz, sizeof(float) * b * R));
-    CUDA_CHECK(cudaMalloc(&dh, sizeof(float) * b * H));
-    copy_sync(dz, z, sizeof(float) * b * R, cudaMemcpyHostToDevice);
-    const ParamInfo& k = pinfo("latent/ex/kernel");
-    gemm_simt(dz, R, 0, p + k.off, D, 1, dh, H, b, D, R, 1.f, p + pinfo("latent/ex/bias").off, 0, nullptr, st[0]);
-    for (int l = 0; l < L; ++l)
-        CUDA_CHECK(cudaMemcpyAsync(state + (size_t)l * b * H, dh, sizeof(float) * b * H, cudaMemcpyDeviceToHost, st[0]));
+// decode(), model.py:204-219.  FP32_VALIDATE handles run fp32 SIMT GEMMs (bit-exact tokens against the oracle); BF16
+// handles run the step on the tensor cores: per layer one tcgen05 GEMM for W x + bW and the fused per-step recurrence
+// kernel (R streamed by TMA, tcgen05 SS form, gate epilogue: k_gru_step_fwd), then the out projection and the tied
+// vocabulary GEMM on k_gemm_tc2 and the arg-max kernel -- 11 launches per token, no host round trip in decode_loop.
+struct Engine::DecodeBufs {
+    int b = 0, out_steps = 0;
+    bool tc = false;
+    float *dz = nullptr, *st_f = nullptr, *x = nullptr, *gx = nullptr, *gh = nullptr, *ho = nullptr, *lg = nullptr;
+    ::bf16 *st_h = nullptr, *x_h = nullptr, *ho_h = nullptr, *z_h = nullptr;   // bf16 path: state ping-pong (2,L,b,H)
+    int *lead = nullptr, *pred = nullptr, *out = nullptr, *flag = nullptr;
+    int cur = 0;
+    cudaGraphExec_t two_steps = nullptr;   // bf16 path: two tokens (one ping-pong period) as one replayable graph
+    void release() {
+        if (two_steps) cudaGraphExecDestroy(two_steps);
+        two_steps = nullptr;
+        cudaFree(dz); cudaFree(st_f); cudaFree(x); cudaFree(gx); cudaFree(gh); cudaFree(ho); cudaFree(lg);
+        cudaFree(st_h); cudaFree(x_h); cudaFree(ho_h); cudaFree(z_h); cudaFree(lead); cudaFree(pred); cudaFree(out); cudaFree(flag);
+        dz = st_f = x = gx = gh = ho = lg = nullptr; st_h = x_h = ho_h = z_h = nullptr; lead = pred = out = flag = nullptr;
+        b = out_steps = 0;
+    }
+    ~DecodeBufs() { release(); }
+};
+
+// decode buffers live with the engine: reallocated only when the batch (or the step budget of the loop) changes
+Engine::DecodeBufs& Engine::decode_bufs(int b, int steps) {
+    if (!dbuf) dbuf = new DecodeBufs();
+    DecodeBufs& B = *dbuf;
+    if (B.b == b && B.out_steps >= steps) return B;
     CUDA_CHECK(cudaStreamSynchronize(st[0]));
-    cudaFree(dz); cudaFree(dh);
+    if (B.b == b) {   // a longer step budget: only the token buffer grows (the graph holds its address)
+        if (B.two_steps) cudaGraphExecDestroy(B.two_steps);
+        B.two_steps = nullptr;
+        cudaFree(B.out);
+        B.out = nullptr;
+        CUDA_CHECK(cudaMalloc(&B.out, sizeof(int) * (size_t)b * steps));
+        B.out_steps = steps;
+        return B;
+    }
+    const int keep_steps = steps;
+    B.release();
+    B.b = b;
+    B.out_steps = keep_steps;
+    B.tc = use_tc && gru_step_supported(H, b);
+    CUDA_CHECK(cudaMalloc(&B.dz, sizeof(float) * b * R));
+    CUDA_CHECK(cudaMalloc(&B.st_f, sizeof(float) * (L + 1) * b * H));
+    CUDA_CHECK(cudaMalloc(&B.gx, sizeof(float) * b * 3 * H));
+    CUDA_CHECK(cudaMalloc(&B.ho, sizeof(float) * b * D));
+    CUDA_CHECK(cudaMalloc(&B.lg, sizeof(float) * b * V));
+    CUDA_CHECK(cudaMalloc(&B.lead, sizeof(int) * b));
+    CUDA_CHECK(cudaMalloc(&B.pred, sizeof(int) * b));
+    CUDA_CHECK(cudaMalloc(&B.flag, sizeof(int) * 4));
+    if (keep_steps > 0) CUDA_CHECK(cudaMalloc(&B.out, sizeof(int) * (size_t)b * keep_steps));
+    if (B.tc) {
+        CUDA_CHECK(cudaMalloc(&B.st_h, sizeof(::bf16) * 2 * L * b * H));
+        CUDA_CHECK(cudaMalloc(&B.x_h, sizeof(::bf16) * b * D));
+        CUDA_CHECK(cudaMalloc(&B.ho_h, sizeof(::bf16) * b * D));
+        CUDA_CHECK(cudaMalloc(&B.z_h, sizeof(::bf16) * b * R));
+    } else {
+        CUDA_CHECK(cudaMalloc(&B.x, sizeof(float) * b * D));
+        CUDA_CHECK(cudaMalloc(&B.gh, sizeof(float) * b * 3 * H));
+    }
+    return B;
+}
+
+// state_in = stack((ex(z),) * L)  (model.py:156-158); dz holds z
+void Engine::decode_seed(DecodeBufs& B) {
+    cudaStream_t s = st[0];
+    const int b = B.b;
+    float* dh = B.st_f + (size_t)L * b * H;
+    if (B.tc) {
+        launch_cast_bf16(B.dz, B.z_h, (long long)b * R, s);
+        gemm(Mat(B.dz, B.z_h, b, R, R), 0, pmat("latent/ex/kernel"), 1, Mat(dh, nullptr, b, H, H), b, D, R, 1.f,
+             p + pinfo("latent/ex/bias").off, 0);
+    } else {
+        gemm_simt(B.dz, R, 0, p + pinfo("latent/ex/kernel").off, D, 1, dh, H, b, D, R, 1.f, p + pinfo("latent/ex/bias").off, 0, nullptr, s);
+    }
+    for (int l = 0; l < L; ++l)
+        CUDA_CHECK(cudaMemcpyAsync(B.st_f + (size_t)l * b * H, dh, sizeof(float) * b * H, cudaMemcpyDeviceToDevice, s));
+    decode_state_changed(B);
+}
+// the fp32 state (L,b,H) was written from outside the step: refresh the bf16 copy the tensor-core step reads
+void Engine::decode_state_changed(DecodeBufs& B) {
+    if (!B.tc) return;
+    B.cur = 0;
+    launch_cast_bf16(B.st_f, B.st_h, (long long)L * B.b * H, st[0]);
+}
+
+// one token: lead (b) -> state (L,b,H) updated in place, pred (b) = arg-max of the logits (lowest index on ties)
+void Engine::decode_one(DecodeBufs& B) {
+    cudaStream_t s = st[0];
+    const int b = B.b;
+    if (B.tc) {
+        launch_embed_gather_bf16(B.lead, b, ph + pinfo("embed/embedding").off, D, B.x_h, s);
+        const ::bf16* in = B.x_h;
+        ::bf16* cur = B.st_h + (size_t)B.cur * L * b * H;
+        ::bf16* nxt = B.st_h + (size_t)(1 - B.cur) * L * b * H;
+        for (int l = 0; l < L; ++l) {
+            const std::string pre = "decode/rnn/l" + std::to_string(l) + "/";
+            gemm(Mat(nullptr, const_cast<::bf16*>(in), b, D, D), 0, pmat(pre + "W"), 0, Mat(B.gx, nullptr, b, 3 * H, 3 * H), b, 3 * H, D, 1.f,
+                 p + pinfo(pre + "bW").off, 0);
+            GruFwdArgs a{};
+            a.gx = B.gx; a.ld_gx = 3 * H;
+            a.R_f = p + pinfo(pre + "R").off; a.R_h = ph + pinfo(pre + "R").off; a.bR = p + pinfo(pre + "bR").off;
+            a.ld_hs = H;
+            float* stf = B.st_f + (size_t)l * b * H;
+            ::bf16* hc = cur + (size_t)l * b * H;
+            ::bf16* hn = nxt + (size_t)l * b * H;
+            const long long zero = 0;
+            gru_step_fwd(&a, 1, &b, &zero, b, H, &stf, &hc, &hn, s, true);
+            in = hn;
+        }
+        B.cur ^= 1;
+        gemm(Mat(nullptr, const_cast<::bf16*>(in), b, H, H), 0, pmat("decode/out/kernel"), 1, Mat(B.ho, B.ho_h, b, D, D), b, D, D, 1.f,
+             p + pinfo("decode/out/bias").off, 0);
+        const Mat HO(B.ho, B.ho_h, b, D, D), LG(B.lg, nullptr, b, V, V);
+        if (tied) gemm(HO, 0, pmat("embed/embedding"), 0, LG, b, V, D, 1.0f / sqrtf((float)D), nullptr, 0);
+        else gemm(HO, 0, pmat("logits/dense/kernel"), 1, LG, b, V, D, 1.f, p + pinfo("logits/dense/bias").off, 0);
+    } else {
+        launch_embed_gather_f32(B.lead, b, p + pinfo("embed/embedding").off, D, B.x, s);
+        const float* in = B.x;
+        for (int l = 0; l < L; ++l) {
+            const std::string pre = "decode/rnn/l" + std::to_string(l) + "/";
+            gemm_simt(in, D, 0, p + pinfo(pre + "W").off, D, 0, B.gx, 3 * H, b, 3 * H, D, 1.f, p + pinfo(pre + "bW").off, 0, nullptr, s);
+            float* stl = B.st_f + (size_t)l * b * H;
+            gru_generic_cell(B.gx, 3 * H, p + pinfo(pre + "R").off, p + pinfo(pre + "bR").off, stl, B.gh, b, H, s);
+            in = stl;
+        }
+        gemm_simt(in, H, 0, p + pinfo("decode/out/kernel").off, D, 1, B.ho, D, b, D, D, 1.f, p + pinfo("decode/out/bias").off, 0, nullptr, s);
+        if (tied) gemm_simt(B.ho, D, 0, p + pinfo("embed/embedding").off, D, 0, B.lg, V, b, V, D, 1.0f / sqrtf((float)D), nullptr, 0, nullptr, s);
+        else gemm_simt(B.ho, D, 0, p + pinfo("logits/dense/kernel").off, V, 1, B.lg, V, b, V, D, 1.f, p + pinfo("logits/dense/bias").off, 0, nullptr, s);
+    }
+    launch_ce_f32(B.lg, V, nullptr, b, V, 0.f, 0, nullptr, nullptr, B.pred, d_stats, s);
+}
+
+void Engine::decode_init(const float* z, int b, float* state) {
+    if (b <= 0) throw std::runtime_error("decode_init: b must be positive");
+    DecodeBufs& B = decode_bufs(b, 0);
+    copy_sync(B.dz, z, sizeof(float) * b * R, cudaMemcpyHostToDevice);
+    decode_seed(B);
+    CUDA_CHECK(cudaMemcpyAsync(state, B.st_f, sizeof(float) * L * b * H, cudaMemcpyDeviceToHost, st[0]));
+    CUDA_CHECK(cudaStreamSynchronize(st[0]));
 }
 
 void Engine::decode_step(const int32_t* lead, int b, float* state, int32_t* pred) {
+    if (b <= 0) throw std::runtime_error("decode_step: b must be positive");
     for (int i = 0; i < b; ++i)
         if (lead[i] < 0 || lead[i] >= V) throw std::runtime_error("decode_step: token id out of range");
     cudaStream_t s = st[0];
-    int* dl; float *dst, *x, *gx, *gh, *ho, *lg; int* dpred;
-    CUDA_CHECK(cudaMalloc(&dl, sizeof(int) * b));
-    CUDA_CHECK(cudaMalloc(&dpred, sizeof(int) * b));
-    CUDA_CHECK(cudaMalloc(&dst, sizeof(float) * L * b * H));
-    CUDA_CHECK(cudaMalloc(&x, sizeof(float) * b * D));
-    CUDA_CHECK(cudaMalloc(&gx, sizeof(float) * b * 3 * H));
-    CUDA_CHECK(cudaMalloc(&gh, sizeof(float) * b * 3 * H));
-    CUDA_CHECK(cudaMalloc(&ho, sizeof(float) * b * D));
-    CUDA_CHECK(cudaMalloc(&lg, sizeof(float) * b * V));
-    CUDA_CHECK(cudaMemcpyAsync(dl, lead, sizeof(int) * b, cudaMemcpyHostToDevice, s));
-    CUDA_CHECK(cudaMemcpyAsync(dst, state, sizeof(float) * L * b * H, cudaMemcpyHostToDevice, s));
-    launch_embed_gather_f32(dl, b, p + pinfo("embed/embedding").off, D, x, s);
-    const float* in = x;
-    for (int l = 0; l < L; ++l) {
-        const std::string pre = "decode/rnn/l" + std::to_string(l) + "/";
-        gemm_simt(in, D, 0, p + pinfo(pre + "W").off, D, 0, gx, 3 * H, b, 3 * H, D, 1.f, p + pinfo(pre + "bW").off, 0, nullptr, s);
-        float* stl = dst + (size_t)l * b * H;
-        gru_generic_cell(gx, 3 * H, p + pinfo(pre + "R").off, p + pinfo(pre + "bR").off, stl, gh, b, H, s);
-        in = stl;
-    }
-    gemm_simt(in, H, 0, p + pinfo("decode/out/kernel").off, D, 1, ho, D, b, D, D, 1.f, p + pinfo("decode/out/bias").off, 0, nullptr, s);
-    if (tied) gemm_simt(ho, D, 0, p + pinfo("embed/embedding").off, D, 0, lg, V, b, V, D, 1.0f / sqrtf((float)D), nullptr, 0, nullptr, s);
-    else gemm_simt(ho, D, 0, p + pinfo("logits/dense/kernel").off, V, 1, lg, V, b, V, D, 1.f, p + pinfo("logits/dense/bias").off, 0, nullptr, s);
-    launch_ce_f32(lg, V, nullptr, b, V, 0.f, 0, nullptr, nullptr, dpred, d_stats, s);
-    CUDA_CHECK(cudaMemcpyAsync(pred, dpred, sizeof(int) * b, cudaMemcpyDeviceToHost, s));
-    CUDA_CHECK(cudaMemcpyAsync(state, dst, sizeof(float) * L * b * H, cudaMemcpyDeviceToHost, s));
+    DecodeBufs& B = decode_bufs(b, 0);
+    CUDA_CHECK(cudaMemcpyAsync(B.lead, lead, sizeof(int) * b, cudaMemcpyHostToDevice, s));
+    CUDA_CHECK(cudaMemcpyAsync(B.st_f, state, sizeof(float) * L * b * H, cudaMemcpyHostToDevice, s));
+    decode_state_changed(B);
+    decode_one(B);
+    CUDA_CHECK(cudaMemcpyAsync(pred, B.pred, sizeof(int) * b, cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaMemcpyAsync(state, B.st_f, sizeof(float) * L * b * H, cudaMemcpyDeviceToHost, s));
     CUDA_CHECK(cudaStreamSynchronize(s));
-    cudaFree(dl); cudaFree(dpred); cudaFree(dst); cudaFree(x); cudaFree(gx); cudaFree(gh); cudaFree(ho); cudaFree(lg);
 }
 
 // decode() of the reference as ONE device-resident loop: no host round trip per token (the
-// reference does a sess.run per step, model.py:215); the all-eos stop test runs on the device and the host looks at
-// it every 16 steps.  fp32 arithmetic, the same kernels as decode_step, so both paths give identical tokens.
+// reference does a sess.run per step, model.py:215); the step counter, the all-eos stop test and the step budget live on
+// the device and the host looks at the stop flag every 16 steps.  The same step as decode_step, so both paths give
+// identical tokens.  BF16 handles replay two steps (one period of the state ping-pong) as one CUDA graph -- 24 kernel
+// nodes per replay instead of 24 host launches (ARGSIM_DECODE_NO_GRAPH=1: plain launches).
 int Engine::decode_loop(const float* z, int b, int steps, int32_t* tokens) {
     if (b <= 0 || steps <= 0) throw std::runtime_error("decode: b and steps must be positive");
     cudaStream_t s = st[0];
-    float *dz, *dst, *x, *gx, *gh, *ho, *lg;
-    int *dlead, *dpred, *dout, *dflag;
-    CUDA_CHECK(cudaMalloc(&dz, sizeof(float) * b * R));
-    CUDA_CHECK(cudaMalloc(&dst, sizeof(float) * (L + 1) * b * H));
-    CUDA_CHECK(cudaMalloc(&x, sizeof(float) * b * D));
-    CUDA_CHECK(cudaMalloc(&gx, sizeof(float) * b * 3 * H));
-    CUDA_CHECK(cudaMalloc(&gh, sizeof(float) * b * 3 * H));
-    CUDA_CHECK(cudaMalloc(&ho, sizeof(float) * b * D));
-    CUDA_CHECK(cudaMalloc(&lg, sizeof(float) * b * V));
-    CUDA_CHECK(cudaMalloc(&dlead, sizeof(int) * b));
-    CUDA_CHECK(cudaMalloc(&dpred, sizeof(int) * b));
-    CUDA_CHECK(cudaMalloc(&dout, sizeof(int) * (size_t)b * steps));
-    CUDA_CHECK(cudaMalloc(&dflag, sizeof(int) * 2));
-    CUDA_CHECK(cudaMemsetAsync(dflag, 0, sizeof(int) * 2, s));
-    copy_sync(dz, z, sizeof(float) * b * R, cudaMemcpyHostToDevice);
-    // state_in = stack((ex(z),) * L)  (model.py:156-158)
-    float* dh = dst + (size_t)L * b * H;
-    gemm_simt(dz, R, 0, p + pinfo("latent/ex/kernel").off, D, 1, dh, H, b, D, R, 1.f, p + pinfo("latent/ex/bias").off, 0, nullptr, s);
-    for (int l = 0; l < L; ++l)
-        CUDA_CHECK(cudaMemcpyAsync(dst + (size_t)l * b * H, dh, sizeof(float) * b * H, cudaMemcpyDeviceToDevice, s));
-    launch_fill_i32(dlead, b, cfg.bos, s);
-    int flag[2] = {0, 0};
-    for (int t = 0; t < steps; ++t) {
-        launch_embed_gather_f32(dlead, b, p + pinfo("embed/embedding").off, D, x, s);
-        const float* in = x;
-        for (int l = 0; l < L; ++l) {
-            const std::string pre = "decode/rnn/l" + std::to_string(l) + "/";
-            gemm_simt(in, D, 0, p + pinfo(pre + "W").off, D, 0, gx, 3 * H, b, 3 * H, D, 1.f, p + pinfo(pre + "bW").off, 0, nullptr, s);
-            float* stl = dst + (size_t)l * b * H;
-            gru_generic_cell(gx, 3 * H, p + pinfo(pre + "R").off, p + pinfo(pre + "bR").off, stl, gh, b, H, s);
-            in = stl;
+    DecodeBufs& B = decode_bufs(b, steps);
+    const int init_flag[4] = {0, 0, steps, 0};
+    CUDA_CHECK(cudaMemcpyAsync(B.flag, init_flag, sizeof(init_flag), cudaMemcpyHostToDevice, s));
+    copy_sync(B.dz, z, sizeof(float) * b * R, cudaMemcpyHostToDevice);
+    decode_seed(B);
+    launch_fill_i32(B.lead, b, cfg.bos, s);
+    int flag[4] = {0, 0, 0, 0};
+    static const bool prof = getenv("ARGSIM_DECODE_PROF") != nullptr;   // device time of the loop against the host's issue time
+    static const bool no_graph = getenv("ARGSIM_DECODE_NO_GRAPH") != nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::chrono::steady_clock::time_point h0;
+    if (prof) {
+        CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        CUDA_CHECK(cudaEventRecord(e0, s));
+        h0 = std::chrono::steady_clock::now();
+    }
+    const bool graph = B.tc && !no_graph;
+    int t0 = 0;
+    if (graph && !B.two_steps) {   // B.cur is 0 here (decode_seed) and is 0 again after two steps
+        // the first two tokens eagerly: every kernel's one-time function attributes are set outside the capture
+        for (int k = 0; k < 2; ++k) {
+            decode_one(B);
+            launch_decode_advance(B.pred, b, cfg.eos, B.out, B.lead, B.flag, s);
         }
-        gemm_simt(in, H, 0, p + pinfo("decode/out/kernel").off, D, 1, ho, D, b, D, D, 1.f, p + pinfo("decode/out/bias").off, 0, nullptr, s);
-        if (tied) gemm_simt(ho, D, 0, p + pinfo("embed/embedding").off, D, 0, lg, V, b, V, D, 1.0f / sqrtf((float)D), nullptr, 0, nullptr, s);
-        else gemm_simt(ho, D, 0, p + pinfo("logits/dense/kernel").off, V, 1, lg, V, b, V, D, 1.f, p + pinfo("logits/dense/bias").off, 0, nullptr, s);
-        launch_ce_f32(lg, V, nullptr, b, V, 0.f, 0, nullptr, nullptr, dpred, d_stats, s);
-        launch_decode_advance(dpred, b, cfg.eos, dout + (size_t)t * b, dlead, dflag, t, s);
-        if ((t & 15) == 15 || t + 1 == steps) {
-            copy_sync(flag, dflag, sizeof(flag), cudaMemcpyDeviceToHost);
+        t0 = 2;
+        cudaGraph_t g = nullptr;
+        CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        try {
+            for (int k = 0; k < 2; ++k) {
+                decode_one(B);
+                launch_decode_advance(B.pred, b, cfg.eos, B.out, B.lead, B.flag, s);
+            }
+        } catch (...) {
+            cudaStreamEndCapture(s, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        CUDA_CHECK(cudaStreamEndCapture(s, &g));
+        CUDA_CHECK(cudaGraphInstantiate(&B.two_steps, g, 0));
+        CUDA_CHECK(cudaGraphDestroy(g));
+    }
+    for (int t = t0; t < steps; t += graph ? 2 : 1) {
+        if (graph) {
+            CUDA_CHECK(cudaGraphLaunch(B.two_steps, s));   // a step past the budget is dropped by k_decode_advance
+        } else {
+            decode_one(B);
+            launch_decode_advance(B.pred, b, cfg.eos, B.out, B.lead, B.flag, s);
+        }
+        const int done = t + (graph ? 2 : 1);
+        if ((done & 15) == 0 || done >= steps) {
+            copy_sync(flag, B.flag, sizeof(flag), cudaMemcpyDeviceToHost);
             if (flag[0]) break;
         }
     }
+    if (prof) {
+        const double issue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+        CUDA_CHECK(cudaEventRecord(e1, s));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float dev_ms = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&dev_ms, e0, e1));
+        fprintf(stderr, "[decode_prof] b=%d steps=%d device %.3f ms, host issue loop %.3f ms\n", b, flag[1], dev_ms, issue_ms);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
     const int T = flag[1];
     std::vector<int32_t> tb((size_t)std::max(T, 1) * b);
-    if (T > 0) copy_sync(tb.data(), dout, sizeof(int) * (size_t)T * b, cudaMemcpyDeviceToHost);
+    if (T > 0) copy_sync(tb.data(), B.out, sizeof(int) * (size_t)T * b, cudaMemcpyDeviceToHost);
     for (int i = 0; i < b; ++i)
         for (int t = 0; t < T; ++t) tokens[(size_t)i * steps + t] = tb[(size_t)t * b + i];
     CUDA_CHECK(cudaStreamSynchronize(s));
-    cudaFree(dz); cudaFree(dst); cudaFree(x); cudaFree(gx); cudaFree(gh); cudaFree(ho); cudaFree(lg);
-    cudaFree(dlead); cudaFree(dpred); cudaFree(dout); cudaFree(dflag);
     return T;
 }
 

@@ -73,6 +73,12 @@ public:
                    float* lkld, int64_t* n_rows, int32_t* pred);
     void embed(const int32_t* src, int b, int T, float* mu_out);
     void embed_one(const int32_t* src, int b, int T, float* mu_out);
+    struct DecodeBufs;
+    DecodeBufs* dbuf = nullptr;
+    DecodeBufs& decode_bufs(int b, int steps);
+    void decode_seed(DecodeBufs& B);
+    void decode_state_changed(DecodeBufs& B);
+    void decode_one(DecodeBufs& B);
     void decode_init(const float* z, int b, float* state);
     int decode_loop(const float* z, int b, int steps, int32_t* tokens);   // returns t <= steps; tokens is (b, steps) row-major
     void decode_step(const int32_t* lead, int b, float* state, int32_t* pred);

@@ -1437,6 +1437,7 @@ struct StepDirP {
 struct StepP {
     StepDirP dir[2];
     int H;
+    int gx_fresh;   // 1: gx was written by the kernel right before this one (decode): read it after griddepcontrol.wait
 };
 constexpr int STEP_STAGES = 3;         // 3 x 24 KB + the gate tile: two CTAs fit an SM, so the NEXT step's CTAs (programmatic dependent
                                       // launch) become resident and prefetch their R blocks while this step still runs; 4 and 8 stages
@@ -1578,7 +1579,7 @@ __global__ void __launch_bounds__(STEP_NTH, 1) k_gru_step_fwd(const __grid_const
         for (int e = 0; e < 8; ++e) {
             const int n = gw + 8 * e;
             gxv[e][0] = gxv[e][1] = gxv[e][2] = 0.f; hpv[e] = 0.f;
-            if (n < nrows) {
+            if (n < nrows && !P.gx_fresh) {
                 const float* gp = A.gx + (size_t)(r0 + n) * A.ld_gx + col;
                 gxv[e][0] = ld_f32(gp); gxv[e][1] = ld_f32(gp + H); gxv[e][2] = ld_f32(gp + 2 * H);
             }
@@ -1587,7 +1588,13 @@ __global__ void __launch_bounds__(STEP_NTH, 1) k_gru_step_fwd(const __grid_const
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int n = gw + 8 * e;
-            if (n < nrows) hpv[e] = ld_f32(A.state_f + (size_t)(r0 + n) * H + col);
+            if (n < nrows) {
+                hpv[e] = ld_f32(A.state_f + (size_t)(r0 + n) * H + col);
+                if (P.gx_fresh) {
+                    const float* gp = A.gx + (size_t)(r0 + n) * A.ld_gx + col;
+                    gxv[e][0] = ld_f32(gp); gxv[e][1] = ld_f32(gp + H); gxv[e][2] = ld_f32(gp + 2 * H);
+                }
+            }
         }
         if (quad < 3) {
             mbar_wait(dfull, 0);
@@ -2020,7 +2027,7 @@ void tma_encode_2d_bf16(void* map_out, const bf16* base, int ld, long long rows,
 bool gru_step_supported(int H, int b) { return H % 64 == 0 && H >= 64 && b >= 1; }
 // state_f: (b,H) fp32 per direction (in/out); state_h[2]: (b,H) bf16 ping-pong per direction (state_h[cur] holds h_prev)
 void gru_step_fwd(const GruFwdArgs* dirs, int ndir, const int* na, const long long* row0, int b, int H, float* const* state_f,
-                  bf16* const* state_h_cur, bf16* const* state_h_next, cudaStream_t s) {
+                  bf16* const* state_h_cur, bf16* const* state_h_next, cudaStream_t s, bool gx_fresh) {
     static bool configured = false;
     // measured on the scaled config: multicast 146.7 ms per step, plain 144.0 (cluster syncs and lock-step stages cost more than
     // the 40 % of L2 bytes they save: the stream is bound by every CTA's own R rows) -> off unless ARGSIM_STEP_MULTICAST=1
@@ -2034,6 +2041,7 @@ void gru_step_fwd(const GruFwdArgs* dirs, int ndir, const int* na, const long lo
     const bool mc = !no_mc && (H / UN) % 8 == 0;
     StepP P;
     P.H = H;
+    P.gx_fresh = gx_fresh ? 1 : 0;
     CUtensorMap tmR[2], tmS[2];
     int na_max = 0;
     for (int d = 0; d < 2; ++d) {
@@ -2060,6 +2068,9 @@ void gru_step_fwd(const GruFwdArgs* dirs, int ndir, const int* na, const long lo
     at[1].val.clusterDim.x = 8; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = mc ? 2 : 1;
+    static const bool no_pdl = getenv("ARGSIM_STEP_NO_PDL") != nullptr;
+    // gx written by the kernel right before (decode): nothing to overlap with, and the launch may sit in a captured graph
+    if ((no_pdl || gx_fresh) && !mc) cfg.numAttrs = 0;
     if (mc) CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gru_step_fwd<8>, P, tmR[0], tmR[1], tmS[0], tmS[1]));
     else CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gru_step_fwd<1>, P, tmR[0], tmR[1], tmS[0], tmS[1]));
     COUNT_LAUNCH();

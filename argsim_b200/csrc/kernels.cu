@@ -549,25 +549,28 @@ void launch_cast_f32(const bf16* in, float* out, long long n, cudaStream_t s) {
 // greedy decode (model.py:204-219), device-resident loop: one step's bookkeeping.  Appends pred to the output,
 // feeds it back as the next lead, and raises the stop flag when every row emitted eos (the reference breaks BEFORE
 // appending that step).  flag[0] = stopped, flag[1] = number of steps kept.
-__global__ void __launch_bounds__(256) k_decode_advance(const int* __restrict__ pred, int b, int eos, int* __restrict__ out_t,
-                                                        int* __restrict__ lead, int* __restrict__ flag, int t) {
-    if (flag[0]) return;
+__global__ void __launch_bounds__(256) k_decode_advance(const int* __restrict__ pred, int b, int eos, int* __restrict__ out,
+                                                        int* __restrict__ lead, int* __restrict__ flag) {
+    // flag[0] = stopped, flag[1] = steps kept so far (= index of this step), flag[2] = step budget: nothing here depends on
+    // the host, so the launch can be replayed from a CUDA graph
+    const int t = flag[1];
+    if (flag[0] || t >= flag[2]) return;
     int all = 1;
     for (int i = threadIdx.x; i < b; i += 256) all &= (pred[i] == eos);
     all = __syncthreads_and(all);
     if (all) {
-        if (threadIdx.x == 0) { flag[0] = 1; flag[1] = t; }
+        if (threadIdx.x == 0) flag[0] = 1;
         return;
     }
     for (int i = threadIdx.x; i < b; i += 256) {
         const int v = pred[i];
-        out_t[i] = v;
+        out[(size_t)t * b + i] = v;
         lead[i] = v;
     }
     if (threadIdx.x == 0) flag[1] = t + 1;
 }
-void launch_decode_advance(const int* pred, int b, int eos, int* out_t, int* lead, int* flag, int t, cudaStream_t s) {
-    k_decode_advance<<<1, 256, 0, s>>>(pred, b, eos, out_t, lead, flag, t);
+void launch_decode_advance(const int* pred, int b, int eos, int* out, int* lead, int* flag, cudaStream_t s) {
+    k_decode_advance<<<1, 256, 0, s>>>(pred, b, eos, out, lead, flag);
     COUNT_LAUNCH();
 }
 __global__ void __launch_bounds__(256) k_fill_i32(int* p, long long n, int v) {

@@ -37,7 +37,7 @@ void launch_row_scatter(const float* in, int ld_in, float* out, int ld_out, cons
                         int accumulate, cudaStream_t s);
 void launch_fill(float* p, long long n, float v, cudaStream_t s);
 void launch_fill_i32(int* p, long long n, int v, cudaStream_t s);
-void launch_decode_advance(const int* pred, int b, int eos, int* out_t, int* lead, int* flag, int t, cudaStream_t s);
+void launch_decode_advance(const int* pred, int b, int eos, int* out, int* lead, int* flag, cudaStream_t s);   // flag: stopped, steps kept, budget
 // one GRU cell step on nb rows (decode(), model.py:204-219): state updated in place
 void gru_generic_cell(const float* gx, int ld_gx, const float* R, const float* bR, float* state, float* gh_work, int nb,
                       int H, cudaStream_t s);
@@ -127,7 +127,7 @@ void gru_tc_fwd(GruTcCtx*, const GruFwdArgs* dirs, int ndir, const SeqPlan& P, c
 // one fused time step (TMA ring + tcgen05 + gate epilogue) for hidden sizes without a persistent kernel (gru_tc.cu)
 bool gru_step_supported(int H, int b);
 void gru_step_fwd(const GruFwdArgs* dirs, int ndir, const int* na, const long long* row0, int b, int H, float* const* state_f,
-                  bf16* const* state_h_cur, bf16* const* state_h_next, cudaStream_t s);
+                  bf16* const* state_h_cur, bf16* const* state_h_next, cudaStream_t s, bool gx_fresh = false);
 void gru_tc_bwd(GruTcCtx*, const GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_off, const int* d_nact,
                 int H, cudaStream_t s, int t0 = 0, int Tseg = -1, int slot = 0, int rows_per_slice = 0, int pad = 0);
 // returns the cycles from the first MMA issue to the completion of the last (K/16 MMAs round robin over nacc accumulators)

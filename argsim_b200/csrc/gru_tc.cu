@@ -1764,7 +1764,7 @@ struct GruTcCtx {
                                  // gate warps: 3.02 ms; 64 = two slots of 64 rows, 8 gate warps: 3.09-3.22 ms; 32 = four slots of 32 rows, 8 gate
                                  // warps: 3.56 ms (the per-chunk costs -- flag round trip, 32 MMA issues -- do not shrink with the chunk; the
                                  // gate math does shrink with the number of gate warps)
-    int fwd3_min_rows = 48;      // ARGSIM_GRU_TC_FWD3_ROWS: rows per slice from which whole-layer launches take the TMA-fed kernel
+    int fwd3_min_rows = 100;      // ARGSIM_GRU_TC_FWD3_ROWS: rows per slice from which whole-layer launches take the TMA-fed kernel
     int pad_groups = 8;
     int force_cn = 0;            // ARGSIM_GRU_TC_CN: rows per MMA chunk (16 / 32 / 64 / 128), 0 = by live rows
     int fwd_version = 2;         // ARGSIM_GRU_TC_FWD=1: the first (block-synchronous) forward kernel, for A/B runs

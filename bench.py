@@ -424,6 +424,19 @@ def main():
                                    note='algorithmic encoder flops (SURVEY 8d: 25.166 MFLOP per source token) over the e2e time'),
                      clocks=clk_e.stop(), finite=bool(np.isfinite(mu).all()))
 
+    # ---- decode: greedy generation (src/model.py:204-219) of 128 latent rows, 64 token steps, through argsim_decode
+    decode = None
+    if args.workload == 'train' and not args.no_extra and rank == 0:
+        zz = np.random.default_rng(7).standard_normal((128, CFG['dim_rep'])).astype(np.float32)
+        h.decode(zz, steps=64)
+        t0 = time.perf_counter()
+        tok = h.decode(zz, steps=64)
+        dt = time.perf_counter() - t0
+        decode = dict(metric='greedy decode tokens/sec', value=tok.size / dt if tok.size else 0.0, unit='tokens/s', rows=128,
+                      steps=int(tok.shape[1]), ms_per_token_step=1e3 * dt / max(int(tok.shape[1]), 1),
+                      timer='host perf_counter around one argsim_decode call (z H2D, device-resident loop, tokens D2H)',
+                      note='one GPU (rank 0); trained-from-step-count weights of the timed run, so the loop may stop early at all-eos')
+
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -516,6 +529,8 @@ def main():
                 last_step=dict(loss=st['loss'], loss_gen=st['loss_gen'], loss_kld=st['loss_kld']))
     if embed:
         line['embed'] = embed
+    if decode:
+        line['decode'] = decode
     if strong:
         line['strong_scaling'] = strong
     if dp_check:

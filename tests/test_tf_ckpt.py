@@ -52,7 +52,7 @@ def test_table_and_bundle_roundtrip(tmp_path):
 
 
 @pytest.mark.parametrize('extra', [dict(), dict(bidirectional=True, bidir_stacked=False), dict(bidirectional=False),
-                                   dict(logit_use_embed=False)])
+                                   dict(logit_use_embed=False), dict(attentive=True)])
 def test_name_and_layout_mapping_roundtrip(tmp_path, extra):
     cfg = dict(dim_tgt=40, dim_emb=8, dim_rep=16, rnn_layers=2, accelerate=1e-4, learn_rate=1e-3, bos=2, eos=1, **extra)
     P = O.init_params(cfg, seed=3, dtype=np.float32, bias_scale=0.2)

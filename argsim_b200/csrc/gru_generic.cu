@@ -54,6 +54,10 @@ __global__ void __launch_bounds__(256) k_gate_bwd(const float* __restrict__ dhs,
                                                   int ld_dg, float* __restrict__ hpo_f, bf16* __restrict__ hpo_h, int ld_hpo,
                                                   int na, int H) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    // programmatic dependent launch (no-ops on a plain launch): the GEMM behind this kernel may become resident; the carry this
+    // kernel reads is complete after the wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (idx >= na * H) return;
     const int j = idx / H, u = idx - j * H;
     const float* c = cache + (long long)j * 4 * H;
@@ -190,6 +194,8 @@ void gru_generic_fwd(const GruFwdArgs* dirs, int ndir, const SeqPlan& P, int H, 
 }
 
 void gru_generic_bwd(const GruBwdArgs* dirs, int ndir, const SeqPlan& P, int H, float* work, cudaStream_t* streams) {
+    // per-step chain {gate gradients, carry += dgh.R}: programmatic dependent launch hides each launch under its predecessor
+    static const bool pdl = getenv("ARGSIM_GENERIC_NO_PDL") == nullptr;
     fork_join_init();
     const size_t wstride = gru_generic_work_floats(P.b, H);
     if (ndir > 1) {
@@ -220,16 +226,27 @@ void gru_generic_bwd(const GruBwdArgs* dirs, int ndir, const SeqPlan& P, int H, 
                 h0 = a.h0;
                 nprev = na;
             }
-            k_gate_bwd<<<cdiv((long long)na * H, 256), 256, 0, s>>>(
-                a.dhs + r0 * a.ld_dhs, a.ld_dhs, a.cache + r0 * 4 * H, hp_f, hp_h, a.ld_hs, nprev, h0, carry, tmp,
-                a.dgx_f ? a.dgx_f + r0 * a.ld_dg : nullptr, a.dgx_h ? a.dgx_h + r0 * a.ld_dg : nullptr,
-                a.dgh_f ? a.dgh_f + r0 * a.ld_dg : nullptr, a.dgh_h ? a.dgh_h + r0 * a.ld_dg : nullptr, a.ld_dg,
-                a.hp_f ? a.hp_f + r0 * a.ld_hp : nullptr, a.hp_h ? a.hp_h + r0 * a.ld_hp : nullptr, a.ld_hp, na, H);
+            const bool tc_step = a.dgh_h && a.ld_dg % 8 == 0 && use_tc_gemm(a.R_h, H);
+            {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)cdiv((long long)na * H, 256)); cfg.blockDim = dim3(256); cfg.stream = s;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                at[0].val.programmaticStreamSerializationAllowed = 1;
+                cfg.attrs = at; cfg.numAttrs = (tc_step && pdl) ? 1 : 0;
+                CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gate_bwd,
+                    a.dhs + r0 * a.ld_dhs, a.ld_dhs, a.cache + r0 * 4 * H, hp_f, hp_h, a.ld_hs, nprev, h0, carry, tmp,
+                    a.dgx_f ? a.dgx_f + r0 * a.ld_dg : nullptr, a.dgx_h ? a.dgx_h + r0 * a.ld_dg : nullptr,
+                    a.dgh_f ? a.dgh_f + r0 * a.ld_dg : nullptr, a.dgh_h ? a.dgh_h + r0 * a.ld_dg : nullptr, a.ld_dg,
+                    a.hp_f ? a.hp_f + r0 * a.ld_hp : nullptr, a.hp_h ? a.hp_h + r0 * a.ld_hp : nullptr, a.ld_hp, na, H));
+            }
             COUNT_LAUNCH();
             // carry[0:na] += dgh[0:na] . R        (R is (3H,H): stored (K, N) -> b_mn = 1)
-            if (a.dgh_h && a.ld_dg % 8 == 0 && use_tc_gemm(a.R_h, H))
+            if (tc_step) {
+                gemm_tc_pdl(pdl);
                 gemm_tc(a.dgh_h + r0 * a.ld_dg, a.ld_dg, 0, a.R_h, H, 1, carry, nullptr, H, na, H, 3 * H, 1.f, nullptr, 1, s);
-            else
+                gemm_tc_pdl(false);
+            } else
                 gemm_simt(tmp, 3 * H, 0, a.R_f, H, 1, carry, H, na, H, 3 * H, 1.f, nullptr, 1, nullptr, s);
         }
         if (a.dh0 && !a.reverse) {

@@ -51,6 +51,7 @@ void gemm_simt(const float* A, int lda, int a_mn, const float* B, int ldb, int b
 // short_units > 0 (fp32 output): for GEMMs that share the chip with higher-priority kernels. The K range is split so
 // that a work unit has at most short_units k-blocks and every unit is its own CTA (not persistent): an SM is held
 // for a few microseconds at a time and a waiting block of the other kernel gets it between two units.
+void gemm_tc_pdl(bool on);   // the calling thread's next k_gemm_tc2 launches use programmatic dependent launch
 void gemm_tc(const bf16* A, int lda, int a_mn, const bf16* B, int ldb, int b_mn, float* Cf, bf16* Ch, int ldc,
              int M, int N, int K, float alpha, const float* bias, int accumulate, cudaStream_t s, int short_units = 0);
 void gemm_tc_init(int device);

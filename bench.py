@@ -426,7 +426,7 @@ def main():
 
     # ---- decode: greedy generation (src/model.py:204-219) of 128 latent rows, 64 token steps, through argsim_decode
     decode = None
-    if args.workload == 'train' and not args.no_extra and rank == 0:
+    if args.workload == 'train' and not args.no_extra:   # every rank runs it (ranks stay in step); rank 0's number is reported
         zz = np.random.default_rng(7).standard_normal((128, CFG['dim_rep'])).astype(np.float32)
         h.decode(zz, steps=64)
         t0 = time.perf_counter()
@@ -435,7 +435,7 @@ def main():
         decode = dict(metric='greedy decode tokens/sec', value=tok.size / dt if tok.size else 0.0, unit='tokens/s', rows=128,
                       steps=int(tok.shape[1]), ms_per_token_step=1e3 * dt / max(int(tok.shape[1]), 1),
                       timer='host perf_counter around one argsim_decode call (z H2D, device-resident loop, tokens D2H)',
-                      note='one GPU (rank 0); trained-from-step-count weights of the timed run, so the loop may stop early at all-eos')
+                      note='one GPU (rank 0 reported); weights of the timed run, so the loop may stop early at all-eos')
 
     if rank != 0:
         if dist:

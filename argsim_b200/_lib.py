@@ -73,7 +73,6 @@ SIGNATURES = {
     'argsim_test_softmax_ce': (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.c_int32, _f32p, _i32p, C.c_float, C.c_int32, _f32p,
                                          _f32p, _f32p, _i32p, C.POINTER(C.c_double)]),
     'argsim_test_ts_mma': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p, _f32p, _f32p, _i64p]),
-    'argsim_bench_exchange': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), _i32p]),
     'argsim_bench_kernel': (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32, _f32p, C.POINTER(C.c_double),
                                       C.POINTER(C.c_double)]),
     'argsim_plan_batch': (C.c_int, [_i32p, _i32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _u8p, _i32p,
@@ -206,13 +205,34 @@ def test_ts_mma(A, B, nacc=1, device=0, want_cycles=False):
     return (D, int(cyc[0])) if want_cycles else D
 
 
+DEV_SIGNATURES = {
+    'argsim_bench_exchange': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), _i32p]),
+    'argsim_dev_last_error': (C.c_char_p, []),
+}
+_dev = None
+
+
+def dev_lib():
+    """libargsim_b200_dev.so (include/argsim_b200_dev.h): development microbenchmarks, not loaded by anything on the hot path."""
+    global _dev
+    if _dev is None:
+        lib()                                   # builds both libraries when the sources are newer
+        L = C.CDLL(_build.DEV_LIB)
+        for name, (res, args) in DEV_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _dev = L
+    return _dev
+
+
 def bench_exchange(method, groups, rows, iters=2000, device=0):
-    """cycles per 16-CTA all-gather round for one exchange mechanism (see argsim_bench_exchange)."""
+    """cycles per 16-CTA all-gather round for one exchange mechanism (argsim_bench_exchange, development library)."""
     cyc = C.c_double()
     mc = np.zeros(1, np.int32)
-    rc = lib().argsim_bench_exchange(device, method, groups, rows, iters, C.byref(cyc), _p(mc, _i32p))
+    rc = dev_lib().argsim_bench_exchange(device, method, groups, rows, iters, C.byref(cyc), _p(mc, _i32p))
     if rc != 0:
-        raise RuntimeError(lib().argsim_last_error(None).decode())
+        raise RuntimeError(dev_lib().argsim_dev_last_error().decode())
     return cyc.value, int(mc[0])
 
 

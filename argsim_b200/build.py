@@ -1,4 +1,5 @@
-"""Builds libargsim_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+"""Builds libargsim_b200.so (the product) and libargsim_b200_dev.so (development microbenchmarks, include/argsim_b200_dev.h)
+in-tree with nvcc for sm_100a (no JIT cache: the .so files travel with the repo)."""
 import os
 import subprocess
 import sys
@@ -7,7 +8,9 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libargsim_b200.so')
-SOURCES = ['kernels.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'gru_generic.cu', 'gru_mma.cu', 'gru_tc.cu', 'xbench.cu', 'plan.cpp', 'engine.cu', 'capi.cu']
+DEV_LIB = os.path.join(HERE, 'libargsim_b200_dev.so')
+SOURCES = ['kernels.cu', 'gemm_simt.cu', 'gemm_tc.cu', 'gru_generic.cu', 'gru_mma.cu', 'gru_tc.cu', 'plan.cpp', 'engine.cu', 'capi.cu']
+DEV_SOURCES = ['xbench.cu', 'capi_dev.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
          '--expt-relaxed-constexpr']
@@ -19,8 +22,9 @@ def _deps_mtime():
 
 
 def needs_build():
-    hdr = os.path.join(HERE, '..', 'include', 'argsim_b200.h')
-    return (not os.path.exists(LIB)) or os.path.getmtime(LIB) < max(_deps_mtime(), os.path.getmtime(hdr))
+    inc = os.path.join(HERE, '..', 'include')
+    newest = max(_deps_mtime(), os.path.getmtime(os.path.join(inc, 'argsim_b200.h')), os.path.getmtime(os.path.join(inc, 'argsim_b200_dev.h')))
+    return any((not os.path.exists(l)) or os.path.getmtime(l) < newest for l in (LIB, DEV_LIB))
 
 
 def build(force=False, verbose=False):
@@ -53,17 +57,18 @@ def _build_locked(objdir, verbose):
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(cc, SOURCES))
-    tmp = LIB + '.tmp.%d' % os.getpid()
-    cmd = [NVCC, '-shared', '-o', tmp] + objs + ['-Xcompiler', '-fPIC', '-ldl', '-cudart', 'static',
-                                                  '-gencode', 'arch=compute_100a,code=sm_100a']
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        if os.path.exists(tmp):
-            os.unlink(tmp)
-        raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
-    os.replace(tmp, LIB)
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES) + len(DEV_SOURCES))) as ex:
+        objs = list(ex.map(cc, SOURCES + DEV_SOURCES))
+    for lib, lib_objs in ((DEV_LIB, objs[len(SOURCES):]), (LIB, objs[:len(SOURCES)])):
+        tmp = lib + '.tmp.%d' % os.getpid()
+        cmd = [NVCC, '-shared', '-o', tmp] + lib_objs + ['-Xcompiler', '-fPIC', '-ldl', '-cudart', 'static',
+                                                          '-gencode', 'arch=compute_100a,code=sm_100a']
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            if os.path.exists(tmp):
+                os.unlink(tmp)
+            raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+        os.replace(tmp, lib)
     return LIB
 
 

@@ -301,20 +301,6 @@ int argsim_test_ts_mma(int32_t device, int32_t N, int32_t K, int32_t nacc, const
     return 0;
 }
 
-int argsim_bench_exchange(int32_t device, int32_t method, int32_t groups, int32_t rows, int32_t iters, double* cycles_per_round,
-                          int32_t* max_clusters) {
-    try {
-        int mc = 0;
-        xbench_run(device, method, groups, rows, iters, cycles_per_round, &mc);
-        if (max_clusters) *max_clusters = mc;
-    } catch (const std::exception& ex) {
-        g_create_err = ex.what();
-        cudaGetLastError();
-        return -2;
-    }
-    return 0;
-}
-
 int argsim_test_softmax_ce(int32_t device, int32_t bf16_mode, int64_t n, int32_t V, const float* logits, const int32_t* labels,
                            float gscale, int32_t write_grad, float* grad_out, float* loss_samp, float* err_samp, int32_t* pred,
                            double stats[2]) {

@@ -168,12 +168,6 @@ int  argsim_test_softmax_ce(int32_t device, int32_t bf16_mode, int64_t n, int32_
  * go round robin over `nacc` accumulators (summed on read-back); *cycles = first issue -> completion of the last. */
 int  argsim_test_ts_mma(int32_t device, int32_t N, int32_t K, int32_t nacc, const float* A, const float* B, float* D,
                         int64_t* cycles);
-/* measurement hook: cycles per all-gather round among the 16 CTAs of a recurrence group (every CTA publishes
- * rows x 32 bf16 units and needs all 512 before going on), `groups` groups running side by side.  method 0: L2 words
- * with in-band tags, volatile; 1: the same, relaxed.gpu; 2: cluster, tagged words into the peers' shared memory;
- * 3: cluster, st.async + remote mbarrier.  Evidence for DESIGN.md "recurrence"; not on the product path. */
-int  argsim_bench_exchange(int32_t device, int32_t method, int32_t groups, int32_t rows, int32_t iters,
-                           double* cycles_per_round, int32_t* max_clusters_or_null);
 /* stand-alone timing of one hot kernel on synthetic device data with an L2 flush between
  * iterations (bench.py roofline / profiles).  which: "softmax_ce" | "adam" | "embed_gather" |
  * "logits_gemm".  Returns the mean ms per launch and the algorithmic bytes / flops per launch. */

@@ -21,6 +21,12 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     assert b'sm_100a' in L.argsim_version()
+    # development microbenchmarks live in their own library and header, outside the product
+    assert not hasattr(L, 'argsim_bench_exchange')
+    dev_hdr = open(os.path.join(ROOT, 'include', 'argsim_b200_dev.h')).read()
+    dev_declared = set(re.findall(r'\b(argsim_[a-z_0-9]+)\s*\(', dev_hdr))
+    D = _lib.dev_lib()
+    assert dev_declared == set(_lib.DEV_SIGNATURES) and all(hasattr(D, n) for n in dev_declared)
 
 
 def test_no_cpu_fallback_create_fails_loudly_without_gpu(have_gpu):

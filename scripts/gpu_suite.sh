@@ -4,6 +4,7 @@ mkdir -p gpurun_out
 echo "tests rc=$?" >> gpurun_out/suite_tests.log
 grep -E "^E |passed|failed|rc=|^real" gpurun_out/suite_tests.log | tail -6
 python scripts/gpu_embed_prof.py 2>&1 | sed -n 2,3p
+python __graft_entry__.py smoke 2>&1 | tail -2
 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/suite_bench.json 2>gpurun_out/suite_bench.err
 python - <<'PY'
 import json

@@ -677,6 +677,12 @@ void launch_attn_fwd(const float* q, const float* K, const float* V, int b, int 
                      const int* last_row, float* prob, float* y_f, bf16* y_h, cudaStream_t s) {
     if (b <= 0) return;
     const size_t smem = sizeof(float) * (dim / heads + Tmax + 8);
+    static bool configured = false;
+    if (!configured) {   // sequences of more than ~12,000 steps need more than the default 48 KB
+        CUDA_CHECK(cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    if (smem > 200 * 1024) throw std::runtime_error("attention: sequence too long for the per-sequence score buffer");
     k_attn_fwd<<<dim3(b, heads), ATT_NT, smem, s>>>(q, K, V, dim, heads, off, Tmax, last_row, prob, y_f, y_h);
     COUNT_LAUNCH();
 }
@@ -736,6 +742,12 @@ void launch_attn_bwd(const float* dy, const float* q, const float* K, const floa
                      bf16* dV_h, cudaStream_t s) {
     if (b <= 0) return;
     const size_t smem = sizeof(float) * (2 * (dim / heads) + 2 * Tmax + 8);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    if (smem > 200 * 1024) throw std::runtime_error("attention: sequence too long for the per-sequence score buffers");
     k_attn_bwd<<<dim3(b, heads), ATT_NT, smem, s>>>(dy, q, K, V, prob, dim, heads, off, Tmax, last_row, dq_f, dq_h, dK_f, dK_h, dV_f, dV_h);
     COUNT_LAUNCH();
 }

@@ -302,6 +302,24 @@ def test_attentive_branch(prec, bidirectional, bidir_stacked):
     h.close()
 
 
+def test_attentive_embedding_across_micro_batches():
+    """argsim_embed with attentive=true on more rows than one micro-batch holds (the attention reads each micro-batch's own
+    packed layout) and on a sequence long enough for the large score buffer: sampled rows against the oracle"""
+    from argsim_b200 import _lib
+    cfg = dict(SMALL, attentive=True)
+    h, P = _mk(cfg, _lib.FP32_VALIDATE)
+    src = ragged_batch(1100, 21, cfg['dim_tgt'], 95)
+    mu = h.embed(src)
+    pick = np.random.default_rng(96).choice(len(src), 24, replace=False)
+    want = O.forward(P, cfg, src[pick], src[pick], 'infer')[0]['mu']
+    assert np.abs(mu[pick] - want).max() <= 2e-4 * np.abs(want).max()
+    long = ragged_batch(3, 13000, cfg['dim_tgt'], 97, tmin=12500)
+    mu = h.embed(long)
+    want = O.forward(P, cfg, long, long, 'infer')[0]['mu']
+    assert np.abs(mu - want).max() <= 5e-4 * np.abs(want).max()
+    h.close()
+
+
 def test_tf_bundle_export_import_roundtrip(tmp_path):
     """Saver.save(tf_format=True) -> <path>.index / .data-00000-of-00001 under the reference's variable names -> Saver.restore
     into a fresh session: parameters (up to the r/u bias split the cuDNN-canonical form cannot keep), Adam slots, the

@@ -1767,7 +1767,9 @@ struct GruTcCtx {
     int fwd3_min_rows = 100;      // ARGSIM_GRU_TC_FWD3_ROWS: rows per slice from which whole-layer launches take the TMA-fed kernel
     int pad_groups = 8;
     int force_cn = 0;            // ARGSIM_GRU_TC_CN: rows per MMA chunk (16 / 32 / 64 / 128), 0 = by live rows
-    int fwd_version = 2;         // ARGSIM_GRU_TC_FWD=1: the first (block-synchronous) forward kernel, for A/B runs
+    int fwd_version = 1;         // LL-exchange forward kernel for launches the TMA-fed kernel does not take: 1 = block-synchronous
+                                 // k_gru_tc_fwd (2,700 cycles per C1 step), ARGSIM_GRU_TC_FWD=2 = warp-specialised k_gru_tc_fwd2 (3,230)
+    bool fwd3_on = true;         // ARGSIM_GRU_TC_FWD=0: no TMA-fed throughput kernel
     int poll_delay = 300;        // ARGSIM_GRU_TC_DELAY: cycles between the local publish and a stage warp's first poll round
     long long* prof = nullptr;   // ARGSIM_GRU_PROF=1
 };
@@ -1786,7 +1788,10 @@ GruTcCtx* gru_tc_create(int device) {
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd2<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd2<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-    if (const char* v = getenv("ARGSIM_GRU_TC_FWD")) c->fwd_version = atoi(v);
+    if (const char* v = getenv("ARGSIM_GRU_TC_FWD")) {
+        c->fwd_version = atoi(v) == 2 ? 2 : 1;
+        c->fwd3_on = atoi(v) != 0;
+    }
     if (const char* v = getenv("ARGSIM_GRU_TC_FWD3_ROWS")) c->fwd3_min_rows = atoi(v);
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd3<64, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     CUDA_CHECK(cudaFuncSetAttribute(k_gru_tc_fwd3<32, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -1831,7 +1836,7 @@ bool gru_tc_throughput(const GruTcCtx* c, int ndir, int b) {
     int ns, bslr, cn;
     tc_pick(c, ndir, b, 0, &ns, &bslr, &cn);
     const int per = (b + ns - 1) / ns;
-    return c->fwd_version >= 2 && per >= c->fwd3_min_rows && per <= 256;
+    return c->fwd3_on && per >= c->fwd3_min_rows && per <= 256;
 }
 bool gru_tc_fits(const GruTcCtx* c, int ndir, int b) {
     int ns, bslr, cn;
@@ -1864,7 +1869,7 @@ void gru_tc_fwd(GruTcCtx* c, const GruFwdArgs* dirs, int ndir, const SeqPlan& Pl
     if (ndir == 1) P.dir[1] = P.dir[0];
     const int groups = ndir * ns;
     {   // throughput form: whole-layer launches with many rows per slice read h_{t-1} from the layer's output through TMA
-        bool ok3 = c->fwd_version >= 2 && rows_per_slice == 0 && (b_seg + ns - 1) / ns >= c->fwd3_min_rows && t0 == 0 && Tseg == Pl.Tmax;
+        bool ok3 = c->fwd3_on && rows_per_slice == 0 && (b_seg + ns - 1) / ns >= c->fwd3_min_rows && t0 == 0 && Tseg == Pl.Tmax;
         for (int d = 0; d < ndir; ++d) ok3 = ok3 && dirs[d].hs_h && !dirs[d].h0 && !dirs[d].hT && dirs[d].ld_hs == dirs[0].ld_hs;
         long long xc1 = 0;
         if (ok3 && ndir == 2) {

@@ -38,7 +38,7 @@ def test_ts_form_mma_matches_numpy(N, K, nacc):
 
 # mode 1: forward recurrences on gru_tc.cu, backward on gru_mma.cu; 3: both on gru_tc.cu; 4 (the default): whole-layer
 # forward launches with many rows per slice take the TMA-fed tensor-memory kernel (flags + hs as the exchange), the rest mma.sync
-@pytest.mark.parametrize('mode', [1, 3, 4])
+@pytest.mark.parametrize('mode', [1, 3, 4, 12])
 @pytest.mark.parametrize('b,tmax', [(3, 9), (64, 40), (100, 23), (150, 23), (257, 12), (512, 9), (500, 33)])
 def test_tensor_memory_recurrence_matches_generic(monkeypatch, b, tmax, mode):
     """recurrences on gru_tc.cu (ARGSIM_GRU_TC) against the per-step generic GRU: losses, every gradient (the gate cache
@@ -46,6 +46,9 @@ def test_tensor_memory_recurrence_matches_generic(monkeypatch, b, tmax, mode):
     from argsim_b200 import _lib
     cfg = dict(dim_tgt=1024, dim_emb=512, dim_rep=256, rnn_layers=2, accelerate=1e-4, learn_rate=1e-3, bos=2, eos=1)
     hg, P = _mk(cfg, _lib.BF16, flags=4)
+    if mode == 12:   # mode 1 with the warp-specialised LL forward kernel (k_gru_tc_fwd2) instead of the block-synchronous one
+        monkeypatch.setenv('ARGSIM_GRU_TC_FWD', '2')
+        mode = 1
     monkeypatch.setenv('ARGSIM_GRU_TC', str(mode))
     hm, _ = _mk(cfg, _lib.BF16, flags=0)
     src = ragged_batch(b, tmax, cfg['dim_tgt'], 60 + b)

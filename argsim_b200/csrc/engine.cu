@@ -59,6 +59,7 @@ Engine::Engine(const argsim_config& c) : cfg(c) {
     if (const char* ev = getenv("ARGSIM_ENC_BWD_CHUNK")) enc_bwd_chunk = atoi(ev);
     slice_budget = getenv("ARGSIM_NO_SLICE_BUDGET") == nullptr;
     early_adam = getenv("ARGSIM_NO_EARLY_ADAM") == nullptr;
+    dp_one_allreduce = getenv("ARGSIM_DP_ONE_ALLREDUCE") != nullptr;
     seg_wgrad_on = getenv("ARGSIM_NO_SEG_WGRAD") == nullptr;
     if (const char* ev = getenv("ARGSIM_LOGIT_CHUNK")) logit_chunk = std::max(128, atoi(ev));
     const int prio_chain = wgrad_overlap ? prio_greatest : prio_least;
@@ -375,6 +376,11 @@ void Engine::gru_bwd(GruBwdArgs* dirs, int ndir, const SeqPlan& P, const int* d_
 
 void Engine::allreduce_bucket(size_t off0, size_t off1, cudaStream_t after) {
     if (arena.dry || cfg.nranks <= 1 || off1 <= off0) return;
+    if (dp_one_allreduce) {   // A/B: no overlapped buckets, one all-reduce of every gradient behind the backward pass
+        if (off1 != nflat) return;
+        off0 = 0;
+        after = nullptr;      // the main stream has joined the side stream by then
+    }
     NcclApi& n = NcclApi::get();
     CUDA_CHECK(cudaEventRecord(ev_bucket, after ? after : st[0]));
     CUDA_CHECK(cudaStreamWaitEvent(st[2], ev_bucket, 0));
@@ -1098,7 +1104,7 @@ void Engine::program(int mode, bool apply_update) {
         launch_adam(p + lo, g + lo, m + lo, v + lo, ph ? ph + lo : nullptr, (long long)(hi - lo), lr_t, 0.9f, 0.999f, 1e-8f, q);
         kend(q);
     };
-    const bool adam_early = apply_update && L >= 2 && early_adam;
+    const bool adam_early = apply_update && L >= 2 && early_adam && !(dp_one_allreduce && cfg.nranks > 1);
     Mat dGXe1 = act(S, 6 * H), dGHe1 = act(S, 6 * H), HPe1 = act(S, 2 * H);
     // second set of gate-gradient buffers: layer i's weight-gradient GEMMs read one set on the side stream while layer
     // i-1's recurrence fills the other

@@ -189,6 +189,7 @@ private:
     void kend(cudaStream_t q = nullptr, double gflop = 0.0);
     bool in_ktimer = false;
     bool tied = true;   // logit_use_embed (src/model.py:164-168)
+    bool dp_one_allreduce = false;   // ARGSIM_DP_ONE_ALLREDUCE: one all-reduce behind the backward pass instead of overlapped buckets
     bool attentive = false;   // src/model.py:136-145
     static constexpr int ATT_HEADS = 8;   // attention(..., head=8), src/model.py:18
     int enc_kind = 0;   // 0: stacked bidirectional (config.json); 1: two L-layer stacks, concatenated at the top; 2: one stack

@@ -270,7 +270,7 @@ void Engine::gemm(const Mat& A, int a_mn, const Mat& B, int b_mn, const Mat& C, 
     if (use_tc) {
         if (!A.h || !B.h) throw std::runtime_error("gemm: bf16 operand view missing (internal error)");
         // per-group device timers (bench.py roofline): batched GEMMs outside the explicitly named groups, by role
-        const bool timed = (cfg.flags & 8) && !in_ktimer && M >= 256;
+        const bool timed = (cfg.flags & 8) && !in_ktimer && !decoding && M >= 256;   // decode steps may sit in a captured graph
         const bool on_side = q == swg;   // stretched by design: reported apart from the chain's GEMMs
         if (timed) kbegin(a_mn ? (on_side ? "k:gemm_wgrad_side" : "k:gemm_wgrad")
                           : b_mn ? (on_side ? "k:gemm_dgrad_or_dense_side" : "k:gemm_dgrad_or_dense")
@@ -1596,6 +1596,7 @@ Engine::DecodeBufs& Engine::decode_bufs(int b, int steps) {
 void Engine::decode_seed(DecodeBufs& B) {
     cudaStream_t s = st[0];
     const int b = B.b;
+    struct Guard { bool& f; Guard(bool& x) : f(x) { f = true; } ~Guard() { f = false; } } guard(decoding);
     float* dh = B.st_f + (size_t)L * b * H;
     if (B.tc) {
         launch_cast_bf16(B.dz, B.z_h, (long long)b * R, s);
@@ -1619,6 +1620,7 @@ void Engine::decode_state_changed(DecodeBufs& B) {
 void Engine::decode_one(DecodeBufs& B) {
     cudaStream_t s = st[0];
     const int b = B.b;
+    struct Guard { bool& f; Guard(bool& x) : f(x) { f = true; } ~Guard() { f = false; } } guard(decoding);
     if (B.tc) {
         launch_embed_gather_bf16(B.lead, b, ph + pinfo("embed/embedding").off, D, B.x_h, s);
         const ::bf16* in = B.x_h;

@@ -188,6 +188,7 @@ private:
     void kbegin(const char* name, cudaStream_t q = nullptr);
     void kend(cudaStream_t q = nullptr, double gflop = 0.0);
     bool in_ktimer = false;
+    bool decoding = false;      // inside decode_one: no per-GEMM timers (the launches may be captured into a graph)
     bool tied = true;   // logit_use_embed (src/model.py:164-168)
     bool dp_one_allreduce = false;   // ARGSIM_DP_ONE_ALLREDUCE: one all-reduce behind the backward pass instead of overlapped buckets
     bool attentive = false;   // src/model.py:136-145

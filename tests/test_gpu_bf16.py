@@ -244,3 +244,23 @@ def test_bf16_decode_on_tensor_cores_tracks_the_fp32_path(dims):
     np.testing.assert_array_equal(tok, np.stack(ys, 1) if ys else np.zeros((b, 0), np.int32))
     assert tok.min() >= 0 and tok.max() < cfg['dim_tgt']
     h32.close(); hb.close()
+
+
+def test_bf16_decode_with_kernel_timers_and_a_large_batch():
+    """the CUDA-graph replay of the decode step next to the library's per-GEMM event timers (bench.py's handles): decode,
+    train step with timings, decode again with a longer budget (the token buffer grows, the graph is rebuilt)"""
+    from argsim_b200 import _lib
+    cfg = dict(dim_tgt=1024, dim_emb=512, dim_rep=256, rnn_layers=2, accelerate=1e-4, learn_rate=1e-3, bos=2, eos=1)
+    h = _lib.Handle(precision=_lib.BF16, flags=_lib.FLAG_KERNEL_TIMERS, **cfg)
+    h.init_params(3)
+    z = np.random.default_rng(5).standard_normal((300, cfg['dim_rep'])).astype(np.float32)
+    a = h.decode(z, steps=6)
+    src = ragged_batch(300, 12, cfg['dim_tgt'], 7)
+    st = h.train_step(src, src)
+    assert np.isfinite(st['loss']) and any(k.startswith('k:') for k in h.last_timings())
+    h.step = 0
+    h.init_params(3)
+    b = h.decode(z, steps=9)
+    assert a.shape[0] == 300 and b.shape[1] >= a.shape[1]
+    np.testing.assert_array_equal(b[:, :a.shape[1]], a)
+    h.close()

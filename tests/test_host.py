@@ -266,3 +266,25 @@ def test_keep_mask_streams_are_keyed_by_global_row():
     b = rng.keep_mask(3, 11, 0.6, 1234, 77, rows=[4, 0, 5])
     np.testing.assert_array_equal(b, a[[4, 0, 5]])                          # a row's stream follows its global index
     np.testing.assert_array_equal(rng.keep_mask(3, 11, 0.6, 1234, 77, row0=3), a[3:6])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs next to the GPU arm): one JSON line with the same metric, unit
+    and config.workload as the repo arm, impl = reference, a cpu_baseline block and an e2e block without copies.  A time
+    budget truncates the steps here (labelled as such in the line); the driver's run is full length."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, ARGSIM_REF_BUDGET_S='3', OMP_NUM_THREADS='4')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line['impl'] == 'reference' and line['metric'] == bench.METRIC and line['unit'] == 'sequences/s'
+    assert line['higher_is_better'] is True and line['vs_baseline'] is None and line['n_gpus'] == 1
+    assert line['config']['workload'] == bench.workload_config(1)['workload']
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1 and line['cpu_baseline']['value'] == line['value']
+    assert line['e2e']['value'] == line['value'] and line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
+    assert line['value'] > 0 and 'EXTRAPOLATED' in line['cpu_baseline']['sample']
